@@ -1,0 +1,198 @@
+/*
+ * mppi_b200.h — C ABI of the B200-native MPPI rollout-and-reweight engine.
+ *
+ * The reference (UM-ARM-Lab/pytorch_mppi) is pure Python and has no FFI; the drop-in boundary is
+ * its Python class API.  This header is the boundary *below* that API: the Python
+ * controllers in pytorch_mppi_b200/ bind these symbols with ctypes (INTEGRATION.md shows the stub a
+ * reference maintainer would add to mppi.py to do the same).  Every entry point
+ *   - takes plain pointers / sizes / a cudaStream_t passed as void*  (no torch types),
+ *   - never allocates or frees caller-visible memory (buffers are caller-owned device memory),
+ *   - launches asynchronously on the given stream and returns 0 or a negative MppiStatus,
+ *   - is not re-entrant per controller (one controller <-> one stream, as the reference).
+ *
+ * Each entry point cites the reference code it replaces (file:line into
+ * /root/reference/src/pytorch_mppi/mppi.py).
+ */
+#ifndef MPPI_B200_H
+#define MPPI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPPI_B200_ABI_VERSION 1
+
+#define MPPI_MAX_NU 4            /* control dimension supported by the fused registry            */
+#define MPPI_MAX_NX 8            /* state dimension supported by the fused registry              */
+#define MPPI_MODEL_PARAM_DOUBLES 48
+#define MPPI_MAX_RANKS 8         /* GPUs of one NVSwitch box                                     */
+
+typedef enum MppiStatus {
+    MPPI_OK = 0,
+    MPPI_ERR_BAD_ARG = -1,        /* null pointer / out-of-range dimension / unknown enum        */
+    MPPI_ERR_UNSUPPORTED = -2,    /* (model, variant, dtype) not in the compiled registry        */
+    MPPI_ERR_WORKSPACE = -3,      /* workspace too small (see mppi_fused_query)                  */
+    MPPI_ERR_CUDA = -4,           /* a CUDA runtime call failed; see mppi_last_cuda_error()      */
+    MPPI_ERR_ABI = -5,            /* struct_size does not match this library                     */
+    MPPI_ERR_TIMEOUT = -6         /* peer exchange timed out (reported via the status word)      */
+} MppiStatus;
+
+typedef enum MppiVariant { MPPI_VARIANT_MPPI = 0, MPPI_VARIANT_SMPPI = 1, MPPI_VARIANT_KMPPI = 2 } MppiVariant;
+typedef enum MppiDType { MPPI_F32 = 0, MPPI_F64 = 1 } MppiDType;
+
+/* Registry of analytic models whose dynamics + running cost are compiled into the fused kernel.
+ * (The reference takes arbitrary Python callables, mppi.py:147-157; arbitrary callables use the
+ * per-step entry points further down.) */
+typedef enum MppiModel {
+    MPPI_MODEL_PENDULUM = 1,      /* /root/reference/tests/pendulum.py:30-60                      */
+    MPPI_MODEL_LINEAR_POINT = 2   /* tests/test_mppi.py:24-51 and tests/smooth_mppi.py:29-142    */
+} MppiModel;
+
+/* model_params layouts (doubles):
+ *  PENDULUM     : [0]=g [1]=m [2]=l [3]=dt [4]=max_torque [5]=max_speed [6]=w_thdot(0.1)
+ *  LINEAR_POINT : [0..3]=B(2x2 row-major) [4..5]=goal [6..9]=Q [10]=has_R [11..14]=R
+ *                 [15]=terminal_scale [16]=n_hills(<=3) then per hill h at 17+7h:
+ *                 Qh(4) centre(2) height(1)
+ */
+
+enum {
+    MPPI_FLAG_SHIFT = 1u << 0,            /* shift_nominal_trajectory before sampling (mppi.py:232-238, 249-250) */
+    MPPI_FLAG_NULL_ACTION = 1u << 1,      /* sample_null_action: global sample 0 is zeroed before the clamp (:390-392) */
+    MPPI_FLAG_ABS_COST = 1u << 2,         /* noise_abs_cost (:190-191, 196-197)                                  */
+    MPPI_FLAG_DIAG_SIGMA = 1u << 3,       /* diagonal covariance fast path (:131-136, 188-193, 204-205)          */
+    MPPI_FLAG_STATE_DEVICE = 1u << 4,     /* read the state from state_dev instead of the by-value copy          */
+    MPPI_FLAG_STATE_PER_SAMPLE = 1u << 5, /* state_dev is (K,nx): one start state per sample (:302-303)          */
+    MPPI_FLAG_EXPORT_PARTIAL = 1u << 6,   /* multi-GPU, library collective: write this rank's (beta,eta,V) to
+                                             partial_out and do NOT update U (mppi_apply_partials finishes)    */
+    MPPI_FLAG_NOMINAL_PADDED = 1u << 7    /* U (and A) are 16-byte aligned allocations padded to a multiple of
+                                             16 bytes: lets the kernel stage them with one TMA bulk copy        */
+};
+
+/* One `command()` of a registered analytic model: replaces, in one launch,
+ *   shift_nominal_trajectory            mppi.py:232-238 (SMPPI :489-493, KMPPI :617-619)
+ *   _compute_perturbed_action_and_noise mppi.py:375-385 (SMPPI :539-552, KMPPI :657-670)
+ *   _compute_rollout_costs_single       mppi.py:297-332
+ *   _compute_total_cost_batch           mppi.py:407-417 (SMPPI :554-570)
+ *   _compute_weighting                  mppi.py:254-259
+ *   the einsum update in _command       mppi.py:268-270 (SMPPI :527-531, KMPPI :679-682)
+ * All pointers are device pointers of element type `dtype` unless noted. */
+typedef struct MppiFusedParams {
+    uint32_t struct_size;        /* sizeof(MppiFusedParams), ABI check                                  */
+    int32_t variant;             /* MppiVariant                                                         */
+    int32_t model;               /* MppiModel                                                           */
+    int32_t dtype;               /* MppiDType                                                           */
+    int32_t K;                   /* samples rolled out by THIS rank                                     */
+    int32_t T;                   /* horizon                                                             */
+    int32_t nx, nu;              /* must match the model                                                */
+    int32_t S;                   /* KMPPI: number of support points (else 0)                            */
+    int32_t u_per_command;       /* rows of the action sequence copied to action_out                    */
+    uint32_t flags;              /* MPPI_FLAG_*                                                         */
+    int32_t block_threads;       /* 0 = library default                                                 */
+    int32_t grid_blocks;         /* 0 = library default (<= SMs * resident CTAs)                        */
+    int32_t _pad0;
+    int64_t k_offset;            /* global index of this rank's first sample (keys the RNG, null action)*/
+    uint64_t seed, offset;       /* Philox4x32-10 key / counter base (see oracle/philox_oracle.py)      */
+    double lambda_;              /* temperature                                                         */
+    double u_scale;
+    double noise_mu[MPPI_MAX_NU];
+    double chol[MPPI_MAX_NU * MPPI_MAX_NU];      /* row-major lower Cholesky factor L of noise_sigma; diag: sqrt on the diagonal */
+    double sigma_inv[MPPI_MAX_NU * MPPI_MAX_NU]; /* row-major inverse covariance                                         */
+    double u_min[MPPI_MAX_NU], u_max[MPPI_MAX_NU];
+    double u_init[MPPI_MAX_NU];
+    double action_min[MPPI_MAX_NU], action_max[MPPI_MAX_NU];   /* SMPPI (mppi.py:464-477)              */
+    double w_action_seq_cost, delta_t;                         /* SMPPI (mppi.py:456-459)              */
+    double model_params[MPPI_MODEL_PARAM_DOUBLES];
+    double state[MPPI_MAX_NX];   /* start state by value: no host->device copy on the hot path          */
+    const void* state_dev;       /* optional device state, (nx) or (K,nx)                               */
+    void* U;                     /* (T,nu) in/out nominal controls (SMPPI: control derivative)          */
+    void* A;                     /* SMPPI: (T,nu) in/out action_sequence                                */
+    void* theta;                 /* KMPPI: (S,nu) in/out control points                                 */
+    const void* W;               /* KMPPI: (T,S)  k(Hs,Tk) k(Tk,Tk)^-1                                  */
+    const void* Wshift;          /* KMPPI: (S,S)  k(Tk+1,Tk) k(Tk,Tk)^-1                                */
+    void* cost_total;            /* (K) out                                                             */
+    void* action_out;            /* (u_per_command,nu) out                                              */
+    void* nominal_used;          /* out, 3*(T*nu) elements: U | A | theta as used for sampling (post-shift,
+                                    pre-update); lets noise/perturbed_action be materialised lazily     */
+    void* stats;                 /* out, 4 doubles: beta, eta, (reserved), status word                  */
+    const void* z;               /* optional injected standard normals (K,T,nu) / KMPPI (K,S,nu); NULL = Philox */
+    void* z_out;                 /* optional: the standard normals actually used, same shape            */
+    void* workspace;             /* caller-owned scratch, zero-initialised ONCE by the caller           */
+    uint64_t workspace_bytes;
+    /* ---- multi-GPU (K sharded over ranks) ---- */
+    int32_t rank, world;
+    uint64_t epoch;              /* strictly increasing per command; keys the peer-exchange flags        */
+    void* peer_slots[MPPI_MAX_RANKS];   /* in-kernel exchange: pointer to every rank's mailbox (own included),
+                                           from mppi_xchg_*; all NULL = no in-kernel exchange            */
+    void* partial_out;           /* MPPI_FLAG_EXPORT_PARTIAL: (2 + R) doubles out                        */
+} MppiFusedParams;
+
+typedef struct MppiLaunchInfo {
+    int32_t block_threads, grid_blocks;
+    int32_t smem_bytes, regs_per_thread;
+    int32_t max_blocks_per_sm, sm_count;
+    uint64_t workspace_bytes;    /* minimum workspace for these dimensions                               */
+    int32_t tma_staging;         /* 1 if the nominal sequence is staged with cp.async.bulk (TMA)         */
+    int32_t _pad;
+} MppiLaunchInfo;
+
+int mppi_b200_abi_version(void);
+/* Layout probe for foreign-language mirrors of MppiFusedParams: which=0 sizeof, 1 offsetof(seed),
+ * 2 offsetof(state), 3 offsetof(U), 4 offsetof(rank), 5 offsetof(partial_out), 6 sizeof(MppiLaunchInfo). */
+uint64_t mppi_abi_layout(int which);
+const char* mppi_status_string(int status);
+const char* mppi_last_cuda_error(void);
+
+/* Launch geometry / scratch needs for these parameters (no launch). */
+int mppi_fused_query(const MppiFusedParams* p, MppiLaunchInfo* out);
+/* The fused command (see struct comment).  `stream` is a cudaStream_t. */
+int mppi_fused_command(const MppiFusedParams* p, void* stream);
+
+/* Multi-GPU, library-collective route: after every rank exported its partial and the caller
+ * all-gathered them (NCCL), finish the update on each rank: beta=min, rescale, U += sum/eta
+ * (mppi.py:254-259, 268-270 across shards).  `partials` is (world, 2+R) doubles on device. */
+int mppi_apply_partials(const MppiFusedParams* p, const void* partials, void* stream);
+
+/* Peer mailboxes for the in-kernel NVLink exchange.  The library owns these small buffers
+ * (cudaMalloc + cudaIpc), because IPC handles must cover a whole allocation. */
+int mppi_xchg_create(void** mailbox, void* ipc_handle_out_64B);       /* local mailbox + its IPC handle */
+int mppi_xchg_open(const void* ipc_handle_64B, void** peer_mailbox);  /* map a peer's mailbox           */
+int mppi_xchg_close(void* peer_mailbox);
+int mppi_xchg_destroy(void* mailbox);
+uint64_t mppi_xchg_bytes(void);
+
+/* ---- API-visible intermediates, produced on demand (off the hot path) -------------------------
+ * The reference stores noise / perturbed_action (mppi.py:383-385) and, with a terminal cost,
+ * states / actions (mppi.py:307-322) on every command.  The fused kernel keeps them in shared
+ * memory only; these entry points regenerate them from (seed, offset | z) and nominal_used. */
+int mppi_materialize(const MppiFusedParams* p, void* perturbed_action /*(K,T,nu)*/, void* noise /*(K,T,nu)*/,
+                     void* noise_theta /*KMPPI (K,S,nu) or NULL*/, void* states /*(K,T,nx) or NULL*/, void* stream);
+
+/* ---- Per-step entry points for arbitrary Python dynamics/cost callables ------------------------
+ * The T-loop stays in Python (mppi.py:312-322); sampling, cost accumulation and the softmin update
+ * are kernels. */
+
+/* mppi.py:375-385 + 186-199 + 415 (SMPPI :539-562, KMPPI :657-670): fills perturbed_action, noise
+ * (and noise_theta) and initialises cost_init[k] = sum_t U . action_cost (+ SMPPI smoothness).
+ * `override` (n_override,T,nu) rows replace samples [override_start, ...) before the clamp
+ * (SpecificActionSampler, mppi.py:393-399). */
+int mppi_sample_perturb(const MppiFusedParams* p, void* perturbed_action, void* noise, void* noise_theta,
+                        void* cost_init, const void* override_rows, int32_t n_override, int32_t override_start,
+                        void* stream);
+/* mppi.py:318-319 / 362-364: cost[m,k] += c[m,k]; M>1 also var_acc[k] += var_m(c) * discount. */
+int mppi_cost_accumulate(void* cost /*(M,K)*/, const void* c /*(M*K)*/, void* var_acc /*(K) or NULL*/,
+                         int32_t M, int32_t K, double discount, int32_t dtype, void* stream);
+/* mppi.py:254-259 + 268-270 from materialised tensors: cost_total (K) and eps = noise (K,T,nu)
+ * (KMPPI: noise_theta (K,S,nu)).  Reads the post-shift nominal from p->nominal_used (written by
+ * mppi_sample_perturb), writes p->U / A / theta, p->action_out and p->stats. */
+int mppi_softmin_update(const MppiFusedParams* p, const void* cost_total, const void* eps, void* stream);
+/* omega (mppi.py:256-258) from cost_total and the (beta, eta) a command left in `stats`. */
+int mppi_omega(const void* cost_total, void* omega_out, const void* stats, double lambda_, int32_t K, int32_t dtype,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPPI_B200_H */

@@ -1,0 +1,569 @@
+// mppi_b200.cu — C-ABI entry points (include/mppi_b200.h) and kernel dispatch.
+// Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
+// No torch types cross this boundary; the Python side binds it with ctypes.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mppi_b200.h"
+#include "mppi_fused.cuh"
+
+using namespace mppi;
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return MPPI_ERR_CUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+
+struct DevInfo {
+    int sm_count = 0;
+    int max_smem_optin = 0;
+};
+int get_dev_info(DevInfo& d) {
+    static thread_local int cached_dev = -1;
+    static thread_local DevInfo cached;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        CK(cudaDeviceGetAttribute(&cached.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        CK(cudaDeviceGetAttribute(&cached.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cached_dev = dev;
+    }
+    d = cached;
+    return MPPI_OK;
+}
+
+int validate(const MppiFusedParams* p) {
+    if (p == nullptr) return MPPI_ERR_BAD_ARG;
+    if (p->struct_size != sizeof(MppiFusedParams)) return MPPI_ERR_ABI;
+    if (p->K <= 0 || p->T <= 0 || p->nu <= 0 || p->nu > MPPI_MAX_NU || p->nx <= 0 || p->nx > MPPI_MAX_NX) return MPPI_ERR_BAD_ARG;
+    if (p->variant < 0 || p->variant > 2) return MPPI_ERR_BAD_ARG;
+    if (p->dtype != MPPI_F32 && p->dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
+    if (p->variant == MPPI_VARIANT_KMPPI && (p->S <= 0 || p->W == nullptr || p->theta == nullptr)) return MPPI_ERR_BAD_ARG;
+    if (p->variant == MPPI_VARIANT_SMPPI && (p->A == nullptr || p->T < 2)) return MPPI_ERR_BAD_ARG;
+    if ((p->flags & MPPI_FLAG_SHIFT) && p->variant == MPPI_VARIANT_KMPPI && p->Wshift == nullptr) return MPPI_ERR_BAD_ARG;
+    if (p->lambda_ <= 0.0) return MPPI_ERR_BAD_ARG;
+    if (p->world < 0 || p->world > MPPI_MAX_RANKS) return MPPI_ERR_BAD_ARG;
+    if (p->u_per_command < 1 || p->u_per_command > p->T) return MPPI_ERR_BAD_ARG;
+    return MPPI_OK;
+}
+
+inline int rows_of(const MppiFusedParams* p) { return (p->variant == MPPI_VARIANT_KMPPI ? p->S : p->T) * p->nu; }
+
+template <typename real> void fill_noise_model(const MppiFusedParams* p, NoiseModel<real>& nm) {
+    for (int i = 0; i < MPPI_MAX_NU; ++i) {
+        nm.mu[i] = (real)p->noise_mu[i];
+        nm.u_min[i] = (real)p->u_min[i];
+        nm.u_max[i] = (real)p->u_max[i];
+        nm.a_min[i] = (real)p->action_min[i];
+        nm.a_max[i] = (real)p->action_max[i];
+    }
+    for (int i = 0; i < MPPI_MAX_NU * MPPI_MAX_NU; ++i) {
+        nm.L[i] = (real)p->chol[i];
+        nm.Sinv[i] = (real)p->sigma_inv[i];
+    }
+    nm.lambda_ = (real)p->lambda_;
+    nm.neg_inv_lambda = (real)(-(1.0 / p->lambda_));   // mppi.py:256: -factor * (cost - beta), factor = 1/lambda
+    nm.u_scale = (real)p->u_scale;
+    nm.w_smooth = (real)p->w_action_seq_cost;
+    nm.delta_t = (real)p->delta_t;
+    nm.diag = (p->flags & MPPI_FLAG_DIAG_SIGMA) ? 1 : 0;
+    nm.abs_cost = (p->flags & MPPI_FLAG_ABS_COST) ? 1 : 0;
+}
+
+inline uint64_t ws_bytes(int nb, int R, int es) {
+    return 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
+}
+
+template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BD, int nb) {
+    memset(&a, 0, sizeof(a));
+    fill_noise_model<real>(p, a.nm);
+    for (int i = 0; i < MPPI_MAX_NU; ++i) a.u_init[i] = (real)p->u_init[i];
+    for (int i = 0; i < MPPI_MAX_NX; ++i) a.x0[i] = (real)p->state[i];
+    a.state_dev = (p->flags & MPPI_FLAG_STATE_DEVICE) ? (const real*)p->state_dev : nullptr;
+    a.state_per_sample = (p->flags & MPPI_FLAG_STATE_PER_SAMPLE) ? 1 : 0;
+    a.U = (real*)p->U;
+    a.A = (real*)p->A;
+    a.theta = (real*)p->theta;
+    a.W = (const real*)p->W;
+    a.Wshift = (const real*)p->Wshift;
+    a.cost_total = (real*)p->cost_total;
+    a.action_out = (real*)p->action_out;
+    a.nominal_used = (real*)p->nominal_used;
+    a.stats = (double*)p->stats;
+    a.z = (const real*)p->z;
+    a.z_out = (real*)p->z_out;
+    a.K = p->K;
+    a.T = p->T;
+    a.S = p->S;
+    a.R = rows_of(p);
+    a.TN = p->T * p->nu;
+    a.upc = p->u_per_command;
+    a.n_tiles = (p->K + BD - 1) / BD;
+    a.k_offset = p->k_offset;
+    a.seed = p->seed;
+    a.offset = p->offset;
+    a.shift = (p->flags & MPPI_FLAG_SHIFT) ? 1 : 0;
+    a.null_action = (p->flags & MPPI_FLAG_NULL_ACTION) ? 1 : 0;
+    const int es = (int)sizeof(real);
+    const bool padded = (p->flags & MPPI_FLAG_NOMINAL_PADDED) || ((a.TN * es) % 16 == 0);
+    a.tma_ok = padded && ((uintptr_t)p->U % 16 == 0) && (p->variant != MPPI_VARIANT_SMPPI || (uintptr_t)p->A % 16 == 0);
+    // workspace carve
+    if (p->workspace != nullptr) {
+        unsigned char* w = (unsigned char*)p->workspace;
+        a.ticket = (unsigned int*)w;
+        a.betaP = (real*)(w + 16);
+        a.etaP = (real*)(w + 16 + align_up(nb * es, 16));
+        a.VP = (real*)(w + 16 + 2 * align_up(nb * es, 16));
+    }
+    a.rank = p->rank;
+    a.world = p->world <= 0 ? 1 : p->world;
+    a.epoch = p->epoch;
+    a.export_partial = (p->flags & MPPI_FLAG_EXPORT_PARTIAL) ? 1 : 0;
+    a.partial_out = (double*)p->partial_out;
+    bool any_peer = false;
+    for (int g = 0; g < MPPI_MAX_RANKS; ++g) {
+        a.peers[g] = (unsigned long long*)p->peer_slots[g];
+        any_peer = any_peer || p->peer_slots[g] != nullptr;
+    }
+    if (!any_peer || a.export_partial) a.world = a.export_partial ? a.world : 1;
+    return MPPI_OK;
+}
+
+struct Geometry {
+    int BD, nb, smem, occ, regs;
+};
+
+struct GeomKey {
+    const void* kernel;
+    int dev, variant, K, T, nu, S, bt, gb, r2, single;
+    bool operator==(const GeomKey& o) const {
+        return kernel == o.kernel && dev == o.dev && variant == o.variant && K == o.K && T == o.T && nu == o.nu && S == o.S &&
+               bt == o.bt && gb == o.gb && r2 == o.r2 && single == o.single;
+    }
+};
+
+// Launch geometry for (kernel, dimensions).  The occupancy / attribute queries cost microseconds, so
+// the last few results are cached per thread: a steady-state command() pays only the lookup.
+template <typename KernelT>
+int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_rows2, bool single_partial_grid, Geometry& g,
+                  SmemLayout (*layout)(int, int, int, int, int, int, int, int)) {
+    static thread_local GeomKey keys[8];
+    static thread_local Geometry vals[8];
+    static thread_local int n_cached = 0, next_slot = 0;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    const GeomKey key{(const void*)kernel, dev, p->variant, p->K, p->T, p->nu, p->S, p->block_threads, p->grid_blocks,
+                      need_rows2, single_partial_grid ? 1 : 0};
+    for (int i = 0; i < n_cached; ++i)
+        if (keys[i] == key) {
+            g = vals[i];
+            return MPPI_OK;
+        }
+    DevInfo di;
+    int rc = get_dev_info(di);
+    if (rc) return rc;
+    const int R = rows_of(p);
+    int BD = p->block_threads;
+    if (BD <= 0) BD = (p->K <= di.sm_count * 128 * 2) ? 128 : 256;
+    if (BD % 32 != 0 || BD < 32 || BD > 512) return MPPI_ERR_BAD_ARG;
+    const int n_tiles = (p->K + BD - 1) / BD;
+    const int cap = di.sm_count * 16;
+    SmemLayout L = layout(p->variant, p->T, p->nu, p->S, R, BD, single_partial_grid ? 1 : cap, need_rows2);
+    if (L.total > di.max_smem_optin) return MPPI_ERR_UNSUPPORTED;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
+    if (occ < 1) return MPPI_ERR_UNSUPPORTED;
+    int nb = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
+    if (nb > cap) nb = cap;
+    if (p->grid_blocks > 0 && p->grid_blocks < nb) nb = p->grid_blocks;
+    L = layout(p->variant, p->T, p->nu, p->S, R, BD, single_partial_grid ? 1 : nb, need_rows2);
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kernel));
+    g.BD = BD;
+    g.nb = nb;
+    g.smem = L.total;
+    g.occ = occ;
+    g.regs = fa.numRegs;
+    (void)es;
+    keys[next_slot] = key;
+    vals[next_slot] = g;
+    next_slot = (next_slot + 1) % 8;
+    if (n_cached < 8) ++n_cached;
+    return MPPI_OK;
+}
+
+template <typename real> SmemLayout layout_fn(int v, int T, int nu, int S, int R, int BD, int nb, int r2) {
+    return make_layout<real>(v, T, nu, S, R, BD, nb, r2);
+}
+
+// ---- fused command ----------------------------------------------------------------------------
+template <class Model, typename real, int V>
+int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    auto kernel = fused_command_kernel<Model, real, V>;
+    Geometry g;
+    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
+    if (rc) return rc;
+    const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
+    KArgs<real> a;
+    fill_kargs<real>(p, a, g.BD, g.nb);
+    if (info != nullptr) {
+        DevInfo di;
+        get_dev_info(di);
+        info->block_threads = g.BD;
+        info->grid_blocks = g.nb;
+        info->smem_bytes = g.smem;
+        info->regs_per_thread = g.regs;
+        info->max_blocks_per_sm = g.occ;
+        info->sm_count = di.sm_count;
+        // report the worst case so one allocation serves any later geometry for these dimensions
+        info->workspace_bytes = ws_bytes(di.sm_count * 16, rows_of(p), (int)sizeof(real));
+        info->tma_staging = a.tma_ok;
+        return MPPI_OK;
+    }
+    if (p->U == nullptr || p->cost_total == nullptr || p->action_out == nullptr || p->nominal_used == nullptr ||
+        p->stats == nullptr || p->workspace == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    if (p->workspace_bytes < need_ws) return MPPI_ERR_WORKSPACE;
+    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
+    if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
+    typename Model::template P<real> mp;
+    Model::template load<real>(mp, p->model_params);
+    kernel<<<g.nb, g.BD, g.smem, stream>>>(a, mp);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+template <class Model, typename real>
+int run_fused_variant(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
+    switch (p->variant) {
+        case MPPI_VARIANT_MPPI: return run_fused<Model, real, V_MPPI>(p, s, info);
+        case MPPI_VARIANT_SMPPI: return run_fused<Model, real, V_SMPPI>(p, s, info);
+        case MPPI_VARIANT_KMPPI: return run_fused<Model, real, V_KMPPI>(p, s, info);
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+
+template <class Model> int run_fused_dtype(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
+    return p->dtype == MPPI_F32 ? run_fused_variant<Model, float>(p, s, info) : run_fused_variant<Model, double>(p, s, info);
+}
+
+int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
+    int rc = validate(p);
+    if (rc) return rc;
+    switch (p->model) {
+        case MPPI_MODEL_PENDULUM: return run_fused_dtype<PendulumModel>(p, s, info);
+        case MPPI_MODEL_LINEAR_POINT: return run_fused_dtype<LinearPointModel>(p, s, info);
+    }
+    return MPPI_ERR_UNSUPPORTED;
+}
+
+// ---- generic path: sample / softmin -------------------------------------------------------------
+template <typename real, int V, int NU>
+int run_sample(const MppiFusedParams* p, KArgs<real>& a_extra, cudaStream_t stream) {
+    auto kernel = sample_kernel<real, V, NU>;
+    Geometry g;
+    int rc = plan_geometry(kernel, p, (int)sizeof(real), V == V_KMPPI, true, g, layout_fn<real>);
+    if (rc) return rc;
+    KArgs<real> a;
+    fill_kargs<real>(p, a, g.BD, g.nb);
+    a.out_pa = a_extra.out_pa;
+    a.out_noise = a_extra.out_noise;
+    a.out_noise_theta = a_extra.out_noise_theta;
+    a.out_cost_init = a_extra.out_cost_init;
+    a.override_rows = a_extra.override_rows;
+    a.n_override = a_extra.n_override;
+    a.override_start = a_extra.override_start;
+    if (a_extra.shift < 0) {   // materialise from nominal_used: no shift, plain loads
+        a.U = (real*)p->nominal_used;
+        a.A = a.U + a.TN;
+        a.theta = a.U + 2 * a.TN;
+        a.shift = 0;
+        a.tma_ok = 0;
+        a.nominal_used = nullptr;
+    }
+    kernel<<<g.nb, g.BD, g.smem, stream>>>(a);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+template <typename real, int V> int run_sample_nu(const MppiFusedParams* p, KArgs<real>& e, cudaStream_t s) {
+    switch (p->nu) {
+        case 1: return run_sample<real, V, 1>(p, e, s);
+        case 2: return run_sample<real, V, 2>(p, e, s);
+        case 3: return run_sample<real, V, 3>(p, e, s);
+        case 4: return run_sample<real, V, 4>(p, e, s);
+    }
+    return MPPI_ERR_UNSUPPORTED;
+}
+
+template <typename real>
+int run_sample_any(const MppiFusedParams* p, void* pa, void* noise, void* noise_theta, void* cost_init, const void* ovr,
+                   int n_ovr, int ovr_start, bool from_nominal_used, cudaStream_t s) {
+    KArgs<real> e;
+    memset(&e, 0, sizeof(e));
+    e.out_pa = (real*)pa;
+    e.out_noise = (real*)noise;
+    e.out_noise_theta = (real*)noise_theta;
+    e.out_cost_init = (real*)cost_init;
+    e.override_rows = (const real*)ovr;
+    e.n_override = n_ovr;
+    e.override_start = ovr_start;
+    e.shift = from_nominal_used ? -1 : 0;
+    switch (p->variant) {
+        case MPPI_VARIANT_MPPI: return run_sample_nu<real, V_MPPI>(p, e, s);
+        case MPPI_VARIANT_SMPPI: return run_sample_nu<real, V_SMPPI>(p, e, s);
+        case MPPI_VARIANT_KMPPI: return run_sample_nu<real, V_KMPPI>(p, e, s);
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+
+template <typename real, int V, int NU>
+int run_softmin(const MppiFusedParams* p, const void* cost, const void* eps, cudaStream_t stream) {
+    auto kernel = softmin_update_kernel<real, V, NU>;
+    Geometry g;
+    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
+    if (rc) return rc;
+    if (p->workspace == nullptr || p->workspace_bytes < ws_bytes(g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
+    KArgs<real> a;
+    fill_kargs<real>(p, a, g.BD, g.nb);
+    a.in_cost = (const real*)cost;
+    a.in_eps = (const real*)eps;
+    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
+    kernel<<<g.nb, g.BD, g.smem, stream>>>(a);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+template <typename real, int V> int run_softmin_nu(const MppiFusedParams* p, const void* c, const void* e, cudaStream_t s) {
+    switch (p->nu) {
+        case 1: return run_softmin<real, V, 1>(p, c, e, s);
+        case 2: return run_softmin<real, V, 2>(p, c, e, s);
+        case 3: return run_softmin<real, V, 3>(p, c, e, s);
+        case 4: return run_softmin<real, V, 4>(p, c, e, s);
+    }
+    return MPPI_ERR_UNSUPPORTED;
+}
+template <typename real> int run_softmin_any(const MppiFusedParams* p, const void* c, const void* e, cudaStream_t s) {
+    switch (p->variant) {
+        case MPPI_VARIANT_MPPI: return run_softmin_nu<real, V_MPPI>(p, c, e, s);
+        case MPPI_VARIANT_SMPPI: return run_softmin_nu<real, V_SMPPI>(p, c, e, s);
+        case MPPI_VARIANT_KMPPI: return run_softmin_nu<real, V_KMPPI>(p, c, e, s);
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+
+template <class Model, typename real>
+int run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStream_t stream) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    KArgs<real> a;
+    fill_kargs<real>(p, a, 128, 1);
+    typename Model::template P<real> mp;
+    Model::template load<real>(mp, p->model_params);
+    states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+template <typename real, int V>
+int run_apply(const MppiFusedParams* p, const void* partials, cudaStream_t stream) {
+    KArgs<real> a;
+    fill_kargs<real>(p, a, 128, 1);
+    a.world = p->world <= 0 ? 1 : p->world;
+    const int smem = align_up((2 * a.TN + a.R + a.T * a.S) * (int)sizeof(real), 16) + (a.R + 2) * 8 + 16;
+    apply_partials_kernel<real, V><<<1, 128, smem, stream>>>(a, (const double*)partials, p->nu);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mppi_b200_abi_version(void) { return MPPI_B200_ABI_VERSION; }
+
+uint64_t mppi_abi_layout(int which) {
+    switch (which) {
+        case 0: return sizeof(MppiFusedParams);
+        case 1: return offsetof(MppiFusedParams, seed);
+        case 2: return offsetof(MppiFusedParams, state);
+        case 3: return offsetof(MppiFusedParams, U);
+        case 4: return offsetof(MppiFusedParams, rank);
+        case 5: return offsetof(MppiFusedParams, partial_out);
+        case 6: return sizeof(MppiLaunchInfo);
+    }
+    return 0;
+}
+
+const char* mppi_status_string(int s) {
+    switch (s) {
+        case MPPI_OK: return "ok";
+        case MPPI_ERR_BAD_ARG: return "bad argument";
+        case MPPI_ERR_UNSUPPORTED: return "unsupported (model, variant, dtype, size) combination";
+        case MPPI_ERR_WORKSPACE: return "workspace too small";
+        case MPPI_ERR_CUDA: return "CUDA error";
+        case MPPI_ERR_ABI: return "MppiFusedParams size mismatch (ABI)";
+        case MPPI_ERR_TIMEOUT: return "peer exchange timed out";
+    }
+    return "unknown status";
+}
+
+const char* mppi_last_cuda_error(void) { return g_cuda_err; }
+
+int mppi_fused_query(const MppiFusedParams* p, MppiLaunchInfo* out) {
+    if (out == nullptr) return MPPI_ERR_BAD_ARG;
+    memset(out, 0, sizeof(*out));
+    return dispatch_fused(p, nullptr, out);
+}
+
+int mppi_fused_command(const MppiFusedParams* p, void* stream) { return dispatch_fused(p, (cudaStream_t)stream, nullptr); }
+
+int mppi_apply_partials(const MppiFusedParams* p, const void* partials, void* stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (partials == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->U == nullptr || p->action_out == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->dtype == MPPI_F32) {
+        switch (p->variant) {
+            case MPPI_VARIANT_MPPI: return run_apply<float, V_MPPI>(p, partials, s);
+            case MPPI_VARIANT_SMPPI: return run_apply<float, V_SMPPI>(p, partials, s);
+            case MPPI_VARIANT_KMPPI: return run_apply<float, V_KMPPI>(p, partials, s);
+        }
+    } else {
+        switch (p->variant) {
+            case MPPI_VARIANT_MPPI: return run_apply<double, V_MPPI>(p, partials, s);
+            case MPPI_VARIANT_SMPPI: return run_apply<double, V_SMPPI>(p, partials, s);
+            case MPPI_VARIANT_KMPPI: return run_apply<double, V_KMPPI>(p, partials, s);
+        }
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+
+uint64_t mppi_xchg_bytes(void) { return (uint64_t)2 * MPPI_MAX_RANKS * MPPI_XCHG_MAX_WORDS * sizeof(unsigned long long); }
+
+int mppi_xchg_create(void** mailbox, void* ipc_handle_out_64B) {
+    if (mailbox == nullptr || ipc_handle_out_64B == nullptr) return MPPI_ERR_BAD_ARG;
+    void* ptr = nullptr;
+    CK(cudaMalloc(&ptr, mppi_xchg_bytes()));
+    CK(cudaMemset(ptr, 0, mppi_xchg_bytes()));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out_64B, &h, 64);
+    *mailbox = ptr;
+    return MPPI_OK;
+}
+
+int mppi_xchg_open(const void* ipc_handle_64B, void** peer_mailbox) {
+    if (ipc_handle_64B == nullptr || peer_mailbox == nullptr) return MPPI_ERR_BAD_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64B, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    *peer_mailbox = ptr;
+    return MPPI_OK;
+}
+
+int mppi_xchg_close(void* peer_mailbox) {
+    if (peer_mailbox == nullptr) return MPPI_ERR_BAD_ARG;
+    CK(cudaIpcCloseMemHandle(peer_mailbox));
+    return MPPI_OK;
+}
+
+int mppi_xchg_destroy(void* mailbox) {
+    if (mailbox == nullptr) return MPPI_ERR_BAD_ARG;
+    CK(cudaFree(mailbox));
+    return MPPI_OK;
+}
+
+int mppi_materialize(const MppiFusedParams* p, void* perturbed_action, void* noise, void* noise_theta, void* states,
+                     void* stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (p->nominal_used == nullptr) return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (states != nullptr && perturbed_action == nullptr) return MPPI_ERR_BAD_ARG;
+    rc = p->dtype == MPPI_F32
+             ? run_sample_any<float>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s)
+             : run_sample_any<double>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s);
+    if (rc || states == nullptr) return rc;
+    switch (p->model) {
+        case MPPI_MODEL_PENDULUM:
+            return p->dtype == MPPI_F32 ? run_states<PendulumModel, float>(p, perturbed_action, states, s)
+                                        : run_states<PendulumModel, double>(p, perturbed_action, states, s);
+        case MPPI_MODEL_LINEAR_POINT:
+            return p->dtype == MPPI_F32 ? run_states<LinearPointModel, float>(p, perturbed_action, states, s)
+                                        : run_states<LinearPointModel, double>(p, perturbed_action, states, s);
+    }
+    return MPPI_ERR_UNSUPPORTED;
+}
+
+int mppi_sample_perturb(const MppiFusedParams* p, void* perturbed_action, void* noise, void* noise_theta, void* cost_init,
+                        const void* override_rows, int32_t n_override, int32_t override_start, void* stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (p->U == nullptr || perturbed_action == nullptr || noise == nullptr || p->nominal_used == nullptr) return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    return p->dtype == MPPI_F32 ? run_sample_any<float>(p, perturbed_action, noise, noise_theta, cost_init, override_rows,
+                                                        n_override, override_start, false, s)
+                                : run_sample_any<double>(p, perturbed_action, noise, noise_theta, cost_init, override_rows,
+                                                         n_override, override_start, false, s);
+}
+
+int mppi_cost_accumulate(void* cost, const void* c, void* var_acc, int32_t M, int32_t K, double discount, int32_t dtype,
+                         void* stream) {
+    if (cost == nullptr || c == nullptr || M < 1 || K < 1) return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int BD = 256, nb = (K + BD - 1) / BD;
+    if (dtype == MPPI_F32)
+        cost_accumulate_kernel<float><<<nb, BD, 0, s>>>((float*)cost, (const float*)c, (float*)var_acc, M, K, (float)discount);
+    else if (dtype == MPPI_F64)
+        cost_accumulate_kernel<double><<<nb, BD, 0, s>>>((double*)cost, (const double*)c, (double*)var_acc, M, K, discount);
+    else
+        return MPPI_ERR_BAD_ARG;
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+int mppi_softmin_update(const MppiFusedParams* p, const void* cost_total, const void* eps, void* stream) {
+    int rc = validate(p);
+    if (rc) return rc;
+    if (cost_total == nullptr || eps == nullptr || p->nominal_used == nullptr || p->U == nullptr || p->action_out == nullptr ||
+        p->stats == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    return p->dtype == MPPI_F32 ? run_softmin_any<float>(p, cost_total, eps, s) : run_softmin_any<double>(p, cost_total, eps, s);
+}
+
+int mppi_omega(const void* cost_total, void* omega_out, const void* stats, double lambda_, int32_t K, int32_t dtype,
+               void* stream) {
+    if (cost_total == nullptr || omega_out == nullptr || stats == nullptr || K < 1 || lambda_ <= 0) return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int BD = 256, nb = (K + BD - 1) / BD;
+    if (dtype == MPPI_F32)
+        omega_kernel<float><<<nb, BD, 0, s>>>((const float*)cost_total, (float*)omega_out, (const double*)stats,
+                                              (float)(-(1.0 / lambda_)), K);
+    else if (dtype == MPPI_F64)
+        omega_kernel<double><<<nb, BD, 0, s>>>((const double*)cost_total, (double*)omega_out, (const double*)stats,
+                                               -(1.0 / lambda_), K);
+    else
+        return MPPI_ERR_BAD_ARG;
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+}  // extern "C"

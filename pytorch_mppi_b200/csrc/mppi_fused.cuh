@@ -1,0 +1,931 @@
+// mppi_fused.cuh — device side of the MPPI engine.
+//
+// fused_command_kernel: one kernel per MPPI/SMPPI/KMPPI command() for registered analytic models.
+// One thread rolls out one sample; a CTA owns tiles of `blockDim.x` samples (grid-stride over tiles,
+// so grid <= SMs x resident CTAs for any K).  Per tile:
+//   A. standard normals -> shared-memory tile rows[R][BD+1]  (in-kernel Philox4x32-10 keyed by the
+//      GLOBAL sample index, or an injected z tensor loaded coalesced)
+//   B. colour with the Cholesky factor, add the nominal sequence (staged in shared memory by a TMA
+//      bulk copy), clamp -> the tile now holds the perturbed actions (KMPPI: the control points)
+//   C. T-step rollout with the state in registers, cost accumulated in the reference's op order
+//   D. online-softmin fold of the tile into the CTA's running partial (beta_b, eta_b, V_b[R])
+// The last CTA to finish (atomic ticket) rescales all CTA partials to the global beta, optionally
+// exchanges the rank partial with peer GPUs through NVLink mailboxes, and writes the updated nominal
+// sequence: `U += sum_k w_k eps_k / eta` lands without a second launch.
+//
+// sample_kernel / softmin_update_kernel: the same stages split at the Python T-loop, for arbitrary
+// dynamics/cost callables (A+B with coalesced write-out; D + finish from materialised tensors).
+//
+// Reference lines replaced: mppi.py:232-238, 375-385, 297-332, 407-417, 254-259, 268-270
+// (SMPPI :489-493, 520-570; KMPPI :617-619, 657-688).
+#pragma once
+
+#include <cuda_runtime.h>
+#include "mppi_math.cuh"
+
+namespace mppi {
+
+enum { V_MPPI = 0, V_SMPPI = 1, V_KMPPI = 2 };
+
+template <typename real> struct KArgs {
+    NoiseModel<real> nm;
+    real u_init[MPPI_MAX_NU];
+    real x0[MPPI_MAX_NX];
+    const real* state_dev;
+    real* U;
+    real* A;
+    real* theta;
+    const real* W;
+    const real* Wshift;
+    real* cost_total;
+    real* action_out;
+    real* nominal_used;
+    double* stats;
+    const real* z;
+    real* z_out;
+    // workspace carve
+    unsigned int* ticket;
+    real* betaP;
+    real* etaP;
+    real* VP;
+    // multi-GPU
+    unsigned long long* peers[8];
+    double* partial_out;
+    unsigned long long epoch;
+    int rank, world, export_partial;
+    // sizes
+    int K, T, S, R, TN, upc, n_tiles;
+    long long k_offset;
+    unsigned long long seed, offset;
+    int shift, null_action, tma_ok, state_per_sample;
+    // generic-path extras (sample_kernel / softmin_update_kernel)
+    real* out_pa;
+    real* out_noise;
+    real* out_noise_theta;
+    real* out_cost_init;
+    const real* override_rows;
+    int n_override, override_start;
+    const real* in_cost;
+    const real* in_eps;
+    real* out_omega;
+};
+
+// ---- shared-memory carve, computed identically on host and device -------------------------------
+struct SmemLayout {
+    int off_uraw, off_araw, off_thraw, off_us, off_as, off_ths, off_w, off_wsh, off_vrun, off_ws, off_red,
+        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, total;
+    int LD;
+};
+
+__host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// rows2 (a second TN-row tile) is only used by sample_kernel for KMPPI
+template <typename real>
+__host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int nb, int need_rows2) {
+    SmemLayout L;
+    const int es = (int)sizeof(real);
+    const int TN = T * nu, SN = S * nu, nw = BD / 32;
+    int o = 16;  // [0,8): mbarrier
+    L.off_uraw = o; o = align_up(o + TN * es, 16);
+    L.off_araw = o; o = align_up(o + (variant == V_SMPPI ? TN : 0) * es, 16);
+    L.off_thraw = o; o = align_up(o + (variant == V_KMPPI ? SN : 0) * es, 16);
+    L.off_us = o; o = align_up(o + TN * es, 16);
+    L.off_as = o; o = align_up(o + (variant == V_SMPPI ? TN : 0) * es, 16);
+    L.off_ths = o; o = align_up(o + (variant == V_KMPPI ? SN : 0) * es, 16);
+    L.off_w = o; o = align_up(o + (variant == V_KMPPI ? T * S : 0) * es, 16);
+    L.off_wsh = o; o = align_up(o + (variant == V_KMPPI ? S * S : 0) * es, 16);
+    L.off_vrun = o; o = align_up(o + R * es, 16);
+    L.off_ws = o; o = align_up(o + BD * es, 16);
+    L.off_red = o; o = align_up(o + 64 * es, 16);
+    L.off_part = o; o = align_up(o + nw * R * es, 16);
+    L.LD = BD + 1;
+    L.off_rows = o; o = align_up(o + R * L.LD * es, 16);
+    L.off_rows2 = o; o = align_up(o + (need_rows2 ? TN * L.LD : 0) * es, 16);
+    L.off_ss = o; o = align_up(o + nb * es, 16);
+    L.off_part2 = o; o = align_up(o + nw * R * 8, 16);
+    L.off_numd = o; o = align_up(o + (R + 2) * 8, 16);
+    L.off_redd = o; o = align_up(o + 64 * 8, 16);
+    L.total = o;
+    return L;
+}
+
+#define MPPI_XCHG_MAX_R 1024
+#define MPPI_XCHG_MAX_WORDS (2 * (MPPI_XCHG_MAX_R + 2))
+
+#if defined(__CUDACC__)
+
+// ---- mbarrier + TMA bulk copy (cp.async.bulk; SASS: UBLKCP) --------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t phase) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+
+// ---- block reductions (deterministic: fixed shuffle tree, fixed warp order) ----------------------
+template <typename T> __device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other < v ? other : v;
+    }
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// all threads get the result; `red` has >= 32 entries; each contains two __syncthreads
+template <typename T> __device__ __forceinline__ T block_min(T v, T* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_min(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    T r = red[0];
+    for (int i = 1; i < nw; ++i) r = red[i] < r ? red[i] : r;
+    return r;
+}
+template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    T r = red[0];
+    for (int i = 1; i < nw; ++i) r += red[i];
+    return r;
+}
+
+// ---- shared-memory view ---------------------------------------------------------------------
+template <typename real> struct Smem {
+    unsigned long long* bar;
+    real *Uraw, *Araw, *thraw, *Us, *As, *ths, *Ws, *Wsh, *Vrun, *w_s, *red, *part, *rows, *rows2, *sS;
+    double *part2, *numd, *redd;
+    int LD;
+    __device__ Smem(unsigned char* smem, const SmemLayout& L) {
+        bar = reinterpret_cast<unsigned long long*>(smem);
+        Uraw = reinterpret_cast<real*>(smem + L.off_uraw);
+        Araw = reinterpret_cast<real*>(smem + L.off_araw);
+        thraw = reinterpret_cast<real*>(smem + L.off_thraw);
+        Us = reinterpret_cast<real*>(smem + L.off_us);
+        As = reinterpret_cast<real*>(smem + L.off_as);
+        ths = reinterpret_cast<real*>(smem + L.off_ths);
+        Ws = reinterpret_cast<real*>(smem + L.off_w);
+        Wsh = reinterpret_cast<real*>(smem + L.off_wsh);
+        Vrun = reinterpret_cast<real*>(smem + L.off_vrun);
+        w_s = reinterpret_cast<real*>(smem + L.off_ws);
+        red = reinterpret_cast<real*>(smem + L.off_red);
+        part = reinterpret_cast<real*>(smem + L.off_part);
+        rows = reinterpret_cast<real*>(smem + L.off_rows);
+        rows2 = reinterpret_cast<real*>(smem + L.off_rows2);
+        sS = reinterpret_cast<real*>(smem + L.off_ss);
+        part2 = reinterpret_cast<double*>(smem + L.off_part2);
+        numd = reinterpret_cast<double*>(smem + L.off_numd);
+        redd = reinterpret_cast<double*>(smem + L.off_redd);
+        LD = L.LD;
+    }
+};
+
+// ---- stage 0: nominal sequence(s) into shared memory, shift folded in ----------------------------
+template <typename real, int VARIANT, int NU>
+__device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
+    typedef Ops<real> O;
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const int T = a.T, S = a.S, R = a.R, TN = a.TN;
+    if (tid == 0) mbar_init(sm.bar, 1);
+    __syncthreads();
+    if (a.tma_ok) {
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)align_up(TN * (int)sizeof(real), 16);
+            mbar_expect_tx(sm.bar, VARIANT == V_SMPPI ? 2 * bytes : bytes);
+            tma_bulk_g2s(sm.Uraw, a.U, bytes, sm.bar);
+            if (VARIANT == V_SMPPI) tma_bulk_g2s(sm.Araw, a.A, bytes, sm.bar);
+        }
+    } else {
+        for (int j = tid; j < TN; j += BD) {
+            sm.Uraw[j] = a.U[j];
+            if (VARIANT == V_SMPPI) sm.Araw[j] = a.A[j];
+        }
+    }
+    for (int j = tid; j < R; j += BD) sm.Vrun[j] = (real)0;
+    if (VARIANT == V_KMPPI) {
+        for (int j = tid; j < R; j += BD) sm.thraw[j] = a.theta[j];
+        for (int j = tid; j < T * S; j += BD) sm.Ws[j] = a.W[j];
+        if (a.shift)
+            for (int j = tid; j < S * S; j += BD) sm.Wsh[j] = a.Wshift[j];
+    }
+    if (a.tma_ok) mbar_wait(sm.bar, 0);
+    __syncthreads();
+    for (int j = tid; j < TN; j += BD) {
+        const int t = j / NU, n = j - t * NU;
+        sm.Us[j] = a.shift ? (t + 1 < T ? sm.Uraw[j + NU] : a.u_init[n]) : sm.Uraw[j];               // mppi.py:237-238
+        if (VARIANT == V_SMPPI) sm.As[j] = a.shift ? (t + 1 < T ? sm.Araw[j + NU] : sm.Araw[j]) : sm.Araw[j];  // :492-493
+    }
+    if (VARIANT == V_KMPPI) {
+        for (int j = tid; j < R; j += BD) {
+            const int s = j / NU, n = j - s * NU;
+            if (a.shift) {                                                                 // mppi.py:619
+                real acc = O::mul(sm.Wsh[s * S], sm.thraw[n]);
+                for (int q = 1; q < S; ++q) acc = O::add(acc, O::mul(sm.Wsh[s * S + q], sm.thraw[q * NU + n]));
+                sm.ths[j] = acc;
+            } else {
+                sm.ths[j] = sm.thraw[j];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- stage A: standard normals into the tile ------------------------------------------------------
+template <typename real>
+__device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, bool active, unsigned long long kg, int nvalid) {
+    const int tid = threadIdx.x, BD = blockDim.x, R = a.R, LD = sm.LD;
+    if (a.z != nullptr) {
+        const size_t base = (size_t)tile * BD * R;
+        const int count = nvalid * R;
+        for (int e = tid; e < count; e += BD) {
+            const int s = e / R, j = e - s * R;
+            sm.rows[j * LD + s] = a.z[base + e];
+        }
+        __syncthreads();
+    } else if (active) {
+        constexpr int PER = Normals<real>::PER_CALL;
+        real* col = sm.rows + tid;
+        for (int c = 0; c * PER < R; ++c) {
+            real tmp[PER];
+            Normals<real>::draw(a.seed, kg, a.offset + (unsigned long long)c, tmp);
+#pragma unroll
+            for (int q = 0; q < PER; ++q)
+                if (c * PER + q < R) col[(c * PER + q) * LD] = tmp[q];
+        }
+    }
+    if (a.z_out != nullptr) {
+        __syncthreads();
+        const size_t base = (size_t)tile * BD * R;
+        const int count = nvalid * R;
+        for (int e = tid; e < count; e += BD) {
+            const int s = e / R, j = e - s * R;
+            a.z_out[base + e] = sm.rows[j * LD + s];
+        }
+        __syncthreads();
+    }
+}
+
+// value that overrides the sampled action before the clamp: null action (mppi.py:390-392) or a
+// SpecificActionSampler row (mppi.py:393-399); returns true if overridden
+template <typename real>
+__device__ __forceinline__ bool override_value(const KArgs<real>& a, unsigned long long kg, int j, real& p) {
+    if (a.null_action && kg == 0ull) { p = (real)0; return true; }
+    if (a.override_rows != nullptr) {
+        const long long r = (long long)kg - a.override_start;
+        if (r >= 0 && r < a.n_override) { p = a.override_rows[(size_t)r * a.TN + j]; return true; }
+    }
+    return false;
+}
+
+// ---- stage B: colour + nominal + clamp, in place in this thread's column --------------------------
+template <typename real, int VARIANT, int NU>
+__device__ __forceinline__ void transform_column(const KArgs<real>& a, Smem<real>& sm, unsigned long long kg) {
+    typedef Ops<real> O;
+    const NoiseModel<real>& nm = a.nm;
+    const int LD = sm.LD;
+    real* col = sm.rows + threadIdx.x;
+    if (VARIANT == V_KMPPI) {
+        for (int s = 0; s < a.S; ++s) {                                                   // mppi.py:660-664
+            real zr[NU], e[NU];
+#pragma unroll
+            for (int n = 0; n < NU; ++n) zr[n] = col[(s * NU + n) * LD];
+            colour<real, NU>(nm, zr, e);
+#pragma unroll
+            for (int n = 0; n < NU; ++n)
+                col[(s * NU + n) * LD] = clamp<real>(O::add(sm.ths[s * NU + n], e[n]), nm.u_min[n], nm.u_max[n]);
+        }
+    } else {
+        for (int t = 0; t < a.T; ++t) {
+            real zr[NU], e[NU];
+#pragma unroll
+            for (int n = 0; n < NU; ++n) zr[n] = col[(t * NU + n) * LD];
+            colour<real, NU>(nm, zr, e);
+#pragma unroll
+            for (int n = 0; n < NU; ++n) {
+                real p = O::add(sm.Us[t * NU + n], e[n]);                                 // mppi.py:380 / :544
+                if (VARIANT == V_SMPPI) {
+                    p = O::add(sm.As[t * NU + n], O::mul(p, nm.delta_t));                 // mppi.py:548
+                    override_value<real>(a, kg, t * NU + n, p);                           // mppi.py:549
+                    p = clamp<real>(p, nm.a_min[n], nm.a_max[n]);                         // mppi.py:550
+                } else {
+                    override_value<real>(a, kg, t * NU + n, p);                           // mppi.py:381
+                    p = clamp<real>(p, nm.u_min[n], nm.u_max[n]);                         // mppi.py:383
+                }
+                col[(t * NU + n) * LD] = p;
+            }
+        }
+    }
+}
+
+// perturbed action at step t for this thread (KMPPI interpolates the control points: mppi.py:665-668)
+template <typename real, int VARIANT, int NU>
+__device__ __forceinline__ void action_at(const KArgs<real>& a, const Smem<real>& sm, unsigned long long kg, int t, real* v) {
+    typedef Ops<real> O;
+    const int LD = sm.LD;
+    const real* col = sm.rows + threadIdx.x;
+    if (VARIANT == V_KMPPI) {
+        const int S = a.S;
+#pragma unroll
+        for (int n = 0; n < NU; ++n) {
+            real acc = O::mul(sm.Ws[t * S], col[n * LD]);
+            for (int s = 1; s < S; ++s) acc = O::add(acc, O::mul(sm.Ws[t * S + s], col[(s * NU + n) * LD]));
+            override_value<real>(a, kg, t * NU + n, acc);
+            v[n] = clamp<real>(acc, a.nm.u_min[n], a.nm.u_max[n]);
+        }
+    } else {
+#pragma unroll
+        for (int n = 0; n < NU; ++n) v[n] = col[(t * NU + n) * LD];
+    }
+}
+
+// effective noise entering the action cost at step t (mppi.py:385 / :552 / :670)
+template <typename real, int VARIANT, int NU>
+__device__ __forceinline__ void noise_at(const KArgs<real>& a, const Smem<real>& sm, int t, const real* v, real* eps) {
+    typedef Ops<real> O;
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+        if (VARIANT == V_SMPPI)
+            eps[n] = O::sub(O::div(O::sub(v[n], sm.As[t * NU + n]), a.nm.delta_t), sm.Us[t * NU + n]);
+        else
+            eps[n] = O::sub(v[n], sm.Us[t * NU + n]);
+    }
+}
+
+// the weighted quantity for row j given the stored tile value (the thing the softmin averages)
+template <typename real, int VARIANT>
+__device__ __forceinline__ real eps_of(const NoiseModel<real>& nm, real val, real us, real as_or_ths) {
+    typedef Ops<real> O;
+    if (VARIANT == V_MPPI) return O::sub(val, us);                                          // mppi.py:385
+    if (VARIANT == V_SMPPI) return O::sub(O::div(O::sub(val, as_or_ths), nm.delta_t), us);  // mppi.py:552
+    return O::sub(val, as_or_ths);                                                          // mppi.py:664
+}
+
+// ---- stage D: fold one tile into the CTA's running softmin partial --------------------------------
+// rows hold v / theta_k (EPS_DIRECT=false) or eps itself (EPS_DIRECT=true)
+template <typename real, int VARIANT, bool EPS_DIRECT>
+__device__ void fold_tile(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool active, int nvalid, real& beta_run,
+                          real& eta_run, real& w_out) {
+    typedef Ops<real> O;
+    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
+    const int R = a.R, LD = sm.LD;
+    const real nfl = a.nm.neg_inv_lambda;
+    const real tile_min = block_min<real>(c_tot, sm.red);
+    const real beta_new = tile_min < beta_run ? tile_min : beta_run;
+    const real w = active ? O::exp_(nfl * (c_tot - beta_new)) : (real)0;                  // mppi.py:12-13, 256
+    const real resc = (beta_run == O::inf()) ? (real)0 : O::exp_(nfl * (beta_run - beta_new));
+    sm.w_s[tid] = w;
+    w_out = w;
+    const real eta_tile = block_sum<real>(w, sm.red);   // (its barriers also publish w_s)
+    for (int j = lane; j < R; j += 32) {
+        const real us = (VARIANT == V_KMPPI || EPS_DIRECT) ? (real)0 : sm.Us[j];
+        const real a2 = EPS_DIRECT ? (real)0 : (VARIANT == V_SMPPI ? sm.As[j] : (VARIANT == V_KMPPI ? sm.ths[j] : (real)0));
+        real acc = (real)0;
+        const int i0 = warp * 32;
+        const int i1 = min(i0 + 32, nvalid);
+        for (int i = i0; i < i1; ++i) {
+            const real val = sm.rows[j * LD + i];
+            acc += sm.w_s[i] * (EPS_DIRECT ? val : eps_of<real, VARIANT>(a.nm, val, us, a2));   // mppi.py:268
+        }
+        sm.part[warp * R + j] = acc;
+    }
+    __syncthreads();
+    for (int j = tid; j < R; j += BD) {
+        real s = sm.part[j];
+        for (int q = 1; q < nw; ++q) s += sm.part[q * R + j];
+        sm.Vrun[j] = sm.Vrun[j] * resc + s;
+    }
+    eta_run = eta_run * resc + eta_tile;
+    beta_run = beta_new;
+    __syncthreads();
+}
+
+// ---- peer exchange over NVLink mailboxes (LL-style 8-byte records: payload32 | flag32) ----------
+// mailbox layout per rank: [2 parity][MPPI_MAX_RANKS src][MPPI_XCHG_MAX_WORDS] u64
+__device__ __forceinline__ void st_peer(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_poll(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// numd[0]=beta, numd[1]=eta, numd[2..2+R) = numerators of THIS rank; on return they hold the
+// all-rank combination (bit-identical on every rank).  Returns 0, or 1 on timeout.
+template <typename real>
+__device__ int exchange_partials(const KArgs<real>& a, double* numd, double* scratch /*world*(R+2)*/, double nfl) {
+    const int R = a.R, nwords = 2 * (R + 2);
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
+    const size_t par_off = (size_t)(a.epoch & 1ull) * 8 * MPPI_XCHG_MAX_WORDS;
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    for (int i = tid; i < nwords; i += BD) {
+        unsigned long long bits = (unsigned long long)__double_as_longlong(numd[i >> 1]);
+        uint32_t half = (i & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+        unsigned long long rec = ((unsigned long long)flag << 32) | half;
+        for (int g = 0; g < a.world; ++g) st_peer(a.peers[g] + par_off + (size_t)a.rank * MPPI_XCHG_MAX_WORDS + i, rec);
+    }
+    const unsigned long long* mine = a.peers[a.rank] + par_off;
+    const long long t0 = clock64();
+    for (int e = tid; e < a.world * nwords; e += BD) {
+        const int g = e / nwords, i = e - g * nwords;
+        unsigned long long rec;
+        while (true) {
+            rec = ld_poll(mine + (size_t)g * MPPI_XCHG_MAX_WORDS + i);
+            if ((uint32_t)(rec >> 32) == flag) break;
+            if (clock64() - t0 > 4000000000ll) { s_timeout = 1; break; }
+        }
+        reinterpret_cast<uint32_t*>(scratch)[(size_t)g * nwords + i] = (uint32_t)rec;
+    }
+    __syncthreads();
+    if (s_timeout) return 1;
+    double beta = scratch[0];
+    for (int g = 1; g < a.world; ++g) beta = fmin(beta, scratch[(size_t)g * (R + 2)]);
+    __syncthreads();
+    for (int j = tid; j < R + 1; j += BD) {   // j==0 -> eta, j>=1 -> numerator j-1
+        double acc = 0.0;
+        for (int g = 0; g < a.world; ++g) {
+            const double* rec = scratch + (size_t)g * (R + 2);
+            acc += exp(nfl * (rec[0] - beta)) * rec[1 + j];
+        }
+        numd[1 + j] = acc;
+    }
+    if (tid == 0) numd[0] = beta;
+    __syncthreads();
+    return 0;
+}
+
+// ---- final update from (beta, eta, numerators) with the post-shift nominal in shared memory -----
+template <typename real, int VARIANT>
+__device__ void finish_update(const KArgs<real>& a, const double* numd, const real* Us, const real* As, real* ths,
+                              const real* Ws, int nu) {
+    typedef Ops<real> O;
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const int TN = a.TN, R = a.R;
+    const double eta = numd[1];
+    const double inv_eta = 1.0 / eta;
+    // nominal_used: U | A | theta slots, as sampled from (post-shift, pre-update)
+    for (int j = tid; j < TN; j += BD) {
+        a.nominal_used[j] = Us[j];
+        if (VARIANT == V_SMPPI) a.nominal_used[TN + j] = As[j];
+    }
+    if (VARIANT == V_KMPPI)
+        for (int j = tid; j < R; j += BD) a.nominal_used[2 * TN + j] = ths[j];
+    if (tid == 0) {
+        a.stats[0] = numd[0];
+        a.stats[1] = eta;
+    }
+    if (VARIANT == V_MPPI) {
+        for (int j = tid; j < TN; j += BD) {
+            const real un = O::add(Us[j], (real)(numd[2 + j] * inv_eta));                // mppi.py:270
+            a.U[j] = un;
+            if (j < a.upc * nu) a.action_out[j] = un;                                      // mppi.py:271-275
+        }
+    } else if (VARIANT == V_SMPPI) {
+        for (int j = tid; j < TN; j += BD) {
+            const real un = O::add(Us[j], (real)(numd[2 + j] * inv_eta));                // mppi.py:529
+            const real an = O::add(As[j], O::mul(un, a.nm.delta_t));                       // mppi.py:531
+            a.U[j] = un;
+            a.A[j] = an;
+            if (j < a.upc * nu) a.action_out[j] = an;                                      // mppi.py:533-537
+        }
+    } else {
+        __syncthreads();
+        for (int j = tid; j < R; j += BD) {
+            const real tn = O::add(ths[j], (real)(numd[2 + j] * inv_eta));              // mppi.py:681
+            ths[j] = tn;
+            a.theta[j] = tn;
+        }
+        __syncthreads();
+        const int S = a.S;
+        for (int j = tid; j < TN; j += BD) {                                               // mppi.py:682  U = W theta
+            const int t = j / nu, n = j - t * nu;
+            real acc = O::mul(Ws[t * S], ths[n]);
+            for (int s = 1; s < S; ++s) acc = O::add(acc, O::mul(Ws[t * S + s], ths[s * nu + n]));
+            a.U[j] = acc;
+            if (j < a.upc * nu) a.action_out[j] = acc;
+        }
+    }
+}
+
+// ---- tail: publish the CTA partial; the last CTA combines, exchanges, updates ----------------------
+template <typename real, int VARIANT, int NU>
+__device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real beta_run, real eta_run) {
+    typedef Ops<real> O;
+    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
+    const int R = a.R, TN = a.TN;
+    const real nfl = a.nm.neg_inv_lambda;
+    __shared__ int s_is_last;
+    const int b = blockIdx.x;
+    if (tid == 0) {
+        a.betaP[b] = beta_run;
+        a.etaP[b] = eta_run;
+    }
+    for (int j = tid; j < R; j += BD) a.VP[(size_t)b * R + j] = sm.Vrun[j];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        s_is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+
+    const int nb = gridDim.x;
+    const volatile real* betaP = a.betaP;
+    const volatile real* etaP = a.etaP;
+    const volatile real* VP = a.VP;
+    real bmin = O::inf();
+    for (int q = tid; q < nb; q += BD) {
+        const real bq = betaP[q];
+        bmin = bq < bmin ? bq : bmin;
+    }
+    const real beta = block_min<real>(bmin, sm.red);
+    double eta_loc = 0.0;
+    for (int q = tid; q < nb; q += BD) {
+        const real s = O::exp_(nfl * (betaP[q] - beta));
+        sm.sS[q] = s;
+        eta_loc += (double)s * (double)etaP[q];
+    }
+    const double eta = block_sum<double>(eta_loc, sm.redd);   // barriers also publish sS
+    for (int j = lane; j < R; j += 32) {
+        double acc = 0.0;
+        for (int q = warp; q < nb; q += nw) acc += (double)sm.sS[q] * (double)VP[(size_t)q * R + j];
+        sm.part2[warp * R + j] = acc;
+    }
+    __syncthreads();
+    for (int j = tid; j < R; j += BD) {
+        double s = sm.part2[j];
+        for (int q = 1; q < nw; ++q) s += sm.part2[q * R + j];
+        sm.numd[2 + j] = s;
+    }
+    if (tid == 0) {
+        sm.numd[0] = (double)beta;
+        sm.numd[1] = eta;
+        *a.ticket = 0u;   // self-reset: the next launch needs no memset
+    }
+    __syncthreads();
+
+    if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
+        for (int j = tid; j < R + 2; j += BD) a.partial_out[j] = sm.numd[j];
+        for (int j = tid; j < TN; j += BD) {
+            a.nominal_used[j] = sm.Us[j];
+            if (VARIANT == V_SMPPI) a.nominal_used[TN + j] = sm.As[j];
+        }
+        if (VARIANT == V_KMPPI)
+            for (int j = tid; j < R; j += BD) a.nominal_used[2 * TN + j] = sm.ths[j];
+        if (tid == 0) {
+            a.stats[0] = sm.numd[0];
+            a.stats[1] = sm.numd[1];
+            a.stats[3] = 0.0;
+        }
+        return;
+    }
+    if (a.world > 1) {
+        double* scratch = reinterpret_cast<double*>(sm.rows);   // the tile is free now
+        if (exchange_partials<real>(a, sm.numd, scratch, (double)nfl)) {
+            if (tid == 0) a.stats[3] = -6.0;   // MPPI_ERR_TIMEOUT
+            return;
+        }
+    }
+    finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);
+    if (tid == 0) a.stats[3] = 0.0;
+}
+
+// =================================================================================================
+// The fused command kernel
+// =================================================================================================
+template <class Model, typename real, int VARIANT>
+__global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a, const typename Model::template P<real> mp) {
+    typedef Ops<real> O;
+    constexpr int NX = Model::NX, NU = Model::NU;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, gridDim.x, 0);
+    Smem<real> sm(smem, L);
+    const NoiseModel<real>& nm = a.nm;
+    const int T = a.T;
+
+    stage_nominal<real, VARIANT, NU>(a, sm);
+
+    real beta_run = O::inf(), eta_run = (real)0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int k = tile * BD + tid;
+        const bool active = k < a.K;
+        const int nvalid = min(BD, a.K - tile * BD);
+        const unsigned long long kg = (unsigned long long)(a.k_offset + k);
+
+        fill_normals<real>(a, sm, tile, active, kg, nvalid);
+
+        real c_tot = O::inf();
+        if (active) {
+            transform_column<real, VARIANT, NU>(a, sm, kg);
+
+            // C. rollout (mppi.py:297-332) + action cost (mppi.py:409,415) [+ smoothness :559-562]
+            real x[NX];
+            if (a.state_dev != nullptr) {
+                const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
+#pragma unroll
+                for (int i = 0; i < NX; ++i) x[i] = sp[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) x[i] = a.x0[i];
+            }
+            real roll = (real)0, pert = (real)0, smooth = (real)0;
+            real vprev[NU];
+#pragma unroll
+            for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
+            for (int t = 0; t < T; ++t) {
+                real v[NU], u[NU], eps[NU];
+                action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+                noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+#pragma unroll
+                for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
+                Model::template step<real>(mp, x, u);                                     // mppi.py:314
+                roll = O::add(roll, Model::template cost<real>(mp, x, u));                // mppi.py:318-319
+                pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
+                if (VARIANT == V_SMPPI) {
+                    if (t > 0) {
+#pragma unroll
+                        for (int n = 0; n < NU; ++n) {
+                            const real d = O::mul(nm.u_scale, O::sub(v[n], vprev[n]));    // mppi.py:559
+                            smooth = O::add(smooth, O::mul(d, d));
+                        }
+                    }
+#pragma unroll
+                    for (int n = 0; n < NU; ++n) vprev[n] = v[n];
+                }
+            }
+            if (Model::template has_terminal<real>(mp)) roll = O::add(roll, Model::template terminal<real>(mp, x));
+            c_tot = O::add(roll, pert);                                                   // mppi.py:416
+            if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569
+            a.cost_total[k] = c_tot;
+        }
+        real w_unused;
+        fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+    }
+    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+}
+
+// =================================================================================================
+// Generic path, part 1: sample + perturb with coalesced write-out (mppi.py:375-385, 409, 415;
+// SMPPI :539-562; KMPPI :657-670).  Also used to materialise noise/perturbed_action lazily.
+// =================================================================================================
+template <typename real, int VARIANT, int NU>
+__global__ void __launch_bounds__(512) sample_kernel(const KArgs<real> a) {
+    typedef Ops<real> O;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, 1, VARIANT == V_KMPPI);
+    Smem<real> sm(smem, L);
+    const NoiseModel<real>& nm = a.nm;
+    const int T = a.T, R = a.R, TN = a.TN, LD = sm.LD;
+
+    stage_nominal<real, VARIANT, NU>(a, sm);
+    if (blockIdx.x == 0 && a.nominal_used != nullptr) {
+        for (int j = tid; j < TN; j += BD) {
+            a.nominal_used[j] = sm.Us[j];
+            if (VARIANT == V_SMPPI) a.nominal_used[TN + j] = sm.As[j];
+        }
+        if (VARIANT == V_KMPPI)
+            for (int j = tid; j < R; j += BD) a.nominal_used[2 * TN + j] = sm.ths[j];
+    }
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int k = tile * BD + tid;
+        const bool active = k < a.K;
+        const int nvalid = min(BD, a.K - tile * BD);
+        const unsigned long long kg = (unsigned long long)(a.k_offset + k);
+        fill_normals<real>(a, sm, tile, active, kg, nvalid);
+        if (active) {
+            transform_column<real, VARIANT, NU>(a, sm, kg);
+            real pert = (real)0, smooth = (real)0;
+            real vprev[NU];
+#pragma unroll
+            for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
+            for (int t = 0; t < T; ++t) {
+                real v[NU], eps[NU];
+                action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+                noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+                pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
+                if (VARIANT == V_KMPPI) {
+#pragma unroll
+                    for (int n = 0; n < NU; ++n) sm.rows2[(t * NU + n) * LD + tid] = v[n];
+                }
+                if (VARIANT == V_SMPPI) {
+                    if (t > 0) {
+#pragma unroll
+                        for (int n = 0; n < NU; ++n) {
+                            const real d = O::mul(nm.u_scale, O::sub(v[n], vprev[n]));
+                            smooth = O::add(smooth, O::mul(d, d));
+                        }
+                    }
+#pragma unroll
+                    for (int n = 0; n < NU; ++n) vprev[n] = v[n];
+                }
+            }
+            if (a.out_cost_init != nullptr) {
+                real c0 = pert;
+                if (VARIANT == V_SMPPI) c0 = O::add(c0, O::mul(smooth, nm.w_smooth));
+                a.out_cost_init[k] = c0;
+            }
+        }
+        __syncthreads();
+        // coalesced write-out of the tile: (K,T,nu) row-major == [sample][j]
+        {
+            const real* vt = (VARIANT == V_KMPPI) ? sm.rows2 : sm.rows;
+            const size_t base = (size_t)tile * BD * TN;
+            const int count = nvalid * TN;
+            for (int e = tid; e < count; e += BD) {
+                const int s = e / TN, j = e - s * TN;
+                const real val = vt[j * LD + s];
+                if (a.out_pa != nullptr) a.out_pa[base + e] = val;
+                if (a.out_noise != nullptr) {
+                    real ep;
+                    if (VARIANT == V_SMPPI) ep = O::sub(O::div(O::sub(val, sm.As[j]), nm.delta_t), sm.Us[j]);
+                    else ep = O::sub(val, sm.Us[j]);
+                    a.out_noise[base + e] = ep;
+                }
+            }
+            if (VARIANT == V_KMPPI && a.out_noise_theta != nullptr) {
+                const size_t base2 = (size_t)tile * BD * R;
+                const int count2 = nvalid * R;
+                for (int e = tid; e < count2; e += BD) {
+                    const int s = e / R, j = e - s * R;
+                    a.out_noise_theta[base2 + e] = O::sub(sm.rows[j * LD + s], sm.ths[j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// states along the rollout of given perturbed actions (mppi.py:307-322), for registered models
+template <class Model, typename real>
+__global__ void states_kernel(const real* __restrict__ pa, real* __restrict__ states, const KArgs<real> a,
+                              const typename Model::template P<real> mp) {
+    typedef Ops<real> O;
+    constexpr int NX = Model::NX, NU = Model::NU;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    real x[NX];
+    if (a.state_dev != nullptr) {
+        const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
+        for (int i = 0; i < NX; ++i) x[i] = sp[i];
+    } else {
+        for (int i = 0; i < NX; ++i) x[i] = a.x0[i];
+    }
+    for (int t = 0; t < a.T; ++t) {
+        real u[NU];
+        for (int n = 0; n < NU; ++n) u[n] = O::mul(a.nm.u_scale, pa[((size_t)k * a.T + t) * NU + n]);
+        Model::template step<real>(mp, x, u);
+        for (int i = 0; i < NX; ++i) states[((size_t)k * a.T + t) * NX + i] = x[i];
+    }
+}
+
+// =================================================================================================
+// Generic path, part 2: softmin + weighted update from materialised cost_total (K) and eps (K,R)
+// (mppi.py:254-259, 268-270).  HBM-bound: reads 4*K*(R+1) bytes once, coalesced.
+// =================================================================================================
+template <typename real, int VARIANT, int NU>
+__global__ void __launch_bounds__(512) softmin_update_kernel(const KArgs<real> a) {
+    typedef Ops<real> O;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, gridDim.x, 0);
+    Smem<real> sm(smem, L);
+    const int R = a.R, TN = a.TN, LD = sm.LD;
+    // post-shift nominal comes from nominal_used (written by sample_kernel)
+    for (int j = tid; j < TN; j += BD) {
+        sm.Us[j] = a.nominal_used[j];
+        if (VARIANT == V_SMPPI) sm.As[j] = a.nominal_used[TN + j];
+    }
+    if (VARIANT == V_KMPPI) {
+        for (int j = tid; j < R; j += BD) sm.ths[j] = a.nominal_used[2 * TN + j];
+        for (int j = tid; j < a.T * a.S; j += BD) sm.Ws[j] = a.W[j];
+    }
+    for (int j = tid; j < R; j += BD) sm.Vrun[j] = (real)0;
+    __syncthreads();
+    real beta_run = O::inf(), eta_run = (real)0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int k = tile * BD + tid;
+        const bool active = k < a.K;
+        const int nvalid = min(BD, a.K - tile * BD);
+        const size_t base = (size_t)tile * BD * R;
+        const int count = nvalid * R;
+        for (int e = tid; e < count; e += BD) {
+            const int s = e / R, j = e - s * R;
+            sm.rows[j * LD + s] = a.in_eps[base + e];
+        }
+        const real c = active ? a.in_cost[k] : O::inf();
+        real w;
+        fold_tile<real, VARIANT, true>(a, sm, c, active, nvalid, beta_run, eta_run, w);   // first barrier inside publishes rows
+    }
+    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+}
+
+// omega_k = exp(-(c_k - beta)/lambda) / eta from the stats a command left behind (mppi.py:256-258)
+template <typename real>
+__global__ void omega_kernel(const real* __restrict__ cost, real* __restrict__ omega, const double* __restrict__ stats,
+                             real neg_inv_lambda, int K) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const real beta = (real)stats[0];
+    const real inv_eta = (real)(1.0 / stats[1]);
+    omega[k] = inv_eta * Ops<real>::exp_(neg_inv_lambda * (cost[k] - beta));
+}
+
+// cost[m,k] += c[m,k]  (mppi.py:319 / 363); M>1: var_acc[k] += var_m(c[:,k]) * discount (mppi.py:364)
+template <typename real>
+__global__ void cost_accumulate_kernel(real* __restrict__ cost, const real* __restrict__ c, real* __restrict__ var_acc,
+                                       int M, int K, real discount) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    real mean = (real)0;
+    for (int m = 0; m < M; ++m) {
+        const real v = c[(size_t)m * K + k];
+        cost[(size_t)m * K + k] += v;
+        mean += v;
+    }
+    if (var_acc != nullptr && M > 1) {
+        mean /= (real)M;
+        real ss = (real)0;
+        for (int m = 0; m < M; ++m) {
+            const real d = c[(size_t)m * K + k] - mean;
+            ss += d * d;
+        }
+        var_acc[k] += ss / (real)(M - 1) * discount;
+    }
+}
+
+// ---- finish from all-gathered partials (library-collective route) --------------------------------
+template <typename real, int VARIANT>
+__global__ void apply_partials_kernel(const KArgs<real> a, const double* partials, int nu) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const int TN = a.TN, R = a.R, T = a.T, S = a.S;
+    real* Us = reinterpret_cast<real*>(smem);
+    real* As = Us + TN;
+    real* ths = As + TN;
+    real* Ws = ths + R;
+    double* numd = reinterpret_cast<double*>(smem + align_up((2 * TN + R + T * S) * (int)sizeof(real), 16));
+    for (int j = tid; j < TN; j += BD) {
+        Us[j] = a.nominal_used[j];
+        As[j] = (VARIANT == V_SMPPI) ? a.nominal_used[TN + j] : (real)0;
+    }
+    if (VARIANT == V_KMPPI) {
+        for (int j = tid; j < R; j += BD) ths[j] = a.nominal_used[2 * TN + j];
+        for (int j = tid; j < T * S; j += BD) Ws[j] = a.W[j];
+    }
+    const double nfl = (double)a.nm.neg_inv_lambda;
+    double beta = partials[0];
+    for (int g = 1; g < a.world; ++g) beta = fmin(beta, partials[(size_t)g * (R + 2)]);
+    for (int j = tid; j < R + 1; j += BD) {
+        double acc = 0.0;
+        for (int g = 0; g < a.world; ++g) {
+            const double* rec = partials + (size_t)g * (R + 2);
+            acc += exp(nfl * (rec[0] - beta)) * rec[1 + j];
+        }
+        numd[1 + j] = acc;
+    }
+    if (tid == 0) numd[0] = beta;
+    __syncthreads();
+    finish_update<real, VARIANT>(a, numd, Us, As, ths, Ws, nu);
+    if (tid == 0) a.stats[3] = 0.0;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace mppi

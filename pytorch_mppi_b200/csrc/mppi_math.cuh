@@ -1,0 +1,379 @@
+// mppi_math.cuh — per-sample arithmetic of the MPPI engine: counter-based RNG, noise colouring,
+// the registered analytic models, and the action-cost term.  Everything here is a pure function of
+// its arguments (no memory traffic), written once for float and double.
+//
+// Parity rule (SURVEY.md §7 "hard parts"): the reference's fp32 run is only reproducible to ~1e-6
+// if the per-sample cost is built from the SAME sequence of individually-rounded IEEE operations as
+// the reference's ATen elementwise kernels.  So every operation that feeds a sample's cost goes
+// through Ops<real>::{add,sub,mul,div} which map to the explicitly-rounded, never-contracted
+// intrinsics (__fmul_rn ...); nvcc may not fuse those into FMAs.  The reductions over samples, which
+// the reference does in library-defined order anyway, are free to use FMAs / wider accumulators.
+//
+// Host compilation (MPPI_HD functions under g++) exists only for tests/emu — the product never
+// runs this code on the CPU.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MPPI_HD __host__ __device__ __forceinline__
+#else
+#define MPPI_HD inline
+#endif
+
+namespace mppi {
+
+// ------------------------------------------------------------------------------------------------
+// Explicitly rounded scalar ops
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Ops;
+
+template <> struct Ops<float> {
+    typedef float real;
+    static MPPI_HD float add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    static MPPI_HD float sub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fsub_rn(a, b);
+#else
+        return a - b;
+#endif
+    }
+    static MPPI_HD float mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    static MPPI_HD float div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        return __fdiv_rn(a, b);
+#else
+        return a / b;
+#endif
+    }
+    static MPPI_HD float sin_(float x) { return sinf(x); }
+    static MPPI_HD float exp_(float x) { return expf(x); }
+    static MPPI_HD float fmod_(float a, float b) { return fmodf(a, b); }
+    static MPPI_HD float abs_(float x) { return fabsf(x); }
+    static MPPI_HD float min_(float a, float b) { return fminf(a, b); }
+    static MPPI_HD float max_(float a, float b) { return fmaxf(a, b); }
+    static MPPI_HD float inf() { return INFINITY; }
+};
+
+template <> struct Ops<double> {
+    typedef double real;
+    static MPPI_HD double add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dadd_rn(a, b);
+#else
+        return a + b;
+#endif
+    }
+    static MPPI_HD double sub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dsub_rn(a, b);
+#else
+        return a - b;
+#endif
+    }
+    static MPPI_HD double mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __dmul_rn(a, b);
+#else
+        return a * b;
+#endif
+    }
+    static MPPI_HD double div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+        return __ddiv_rn(a, b);
+#else
+        return a / b;
+#endif
+    }
+    static MPPI_HD double sin_(double x) { return sin(x); }
+    static MPPI_HD double exp_(double x) { return exp(x); }
+    static MPPI_HD double fmod_(double a, double b) { return fmod(a, b); }
+    static MPPI_HD double abs_(double x) { return fabs(x); }
+    static MPPI_HD double min_(double a, double b) { return fmin(a, b); }
+    static MPPI_HD double max_(double a, double b) { return fmax(a, b); }
+    static MPPI_HD double inf() { return (double)INFINITY; }
+};
+
+// torch.clamp(x, lo, hi) = min(max(x, lo), hi)   (mppi.py:419-420)
+template <typename real> MPPI_HD real clamp(real x, real lo, real hi) {
+    return Ops<real>::min_(Ops<real>::max_(x, lo), hi);
+}
+
+// torch.remainder for floating types (result takes the sign of the divisor); used by `%` in
+// tests/pendulum.py:52.
+template <typename real> MPPI_HD real remainder(real a, real b) {
+    real m = Ops<real>::fmod_(a, b);
+    if (m != (real)0 && ((b < (real)0) != (m < (real)0))) m = Ops<real>::add(m, b);
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (offset_lo, offset_hi, subseq_lo, subseq_hi),
+// key = (seed_lo, seed_hi): subsequence = GLOBAL sample index, offset = per-command counter base +
+// chunk index, so the draw for sample k does not depend on how K is sharded over blocks or GPUs.
+// ------------------------------------------------------------------------------------------------
+struct U4 { uint32_t x, y, z, w; };
+
+MPPI_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+MPPI_HD U4 philox4x32_10(uint64_t seed, uint64_t subseq, uint64_t offset) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    U4 c;
+    c.x = (uint32_t)offset; c.y = (uint32_t)(offset >> 32);
+    c.z = (uint32_t)subseq; c.w = (uint32_t)(subseq >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(0xD2511F53u, c.x, hi0, lo0);
+        mulhilo32(0xCD9E8D57u, c.z, hi1, lo1);
+        U4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Standard normals per Philox call: 4 (float, two Box-Muller pairs) or 2 (double, one pair of
+// 53-bit uniforms).  u in (0,1]: x*2^-32 + 2^-33 (float) — never 0, so log is finite.
+template <typename real> struct Normals;
+
+template <> struct Normals<float> {
+    static const int PER_CALL = 4;
+    static MPPI_HD void pair(uint32_t a, uint32_t b, float& n0, float& n1) {
+        float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // 2^-32, 2^-33
+        float u2 = (float)b * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+        float r = sqrtf(-2.0f * logf(u1));
+        float s, c;
+#if defined(__CUDA_ARCH__)
+        sincospif(2.0f * u2, &s, &c);
+#else
+        s = (float)sin(6.283185307179586 * (double)u2);
+        c = (float)cos(6.283185307179586 * (double)u2);
+#endif
+        n0 = r * s;
+        n1 = r * c;
+    }
+    static MPPI_HD void draw(uint64_t seed, uint64_t subseq, uint64_t offset, float* out) {
+        U4 v = philox4x32_10(seed, subseq, offset);
+        pair(v.x, v.y, out[0], out[1]);
+        pair(v.z, v.w, out[2], out[3]);
+    }
+};
+
+template <> struct Normals<double> {
+    static const int PER_CALL = 2;
+    static MPPI_HD void draw(uint64_t seed, uint64_t subseq, uint64_t offset, double* out) {
+        U4 v = philox4x32_10(seed, subseq, offset);
+        uint64_t a = ((uint64_t)v.y << 32) | v.x;
+        uint64_t b = ((uint64_t)v.w << 32) | v.z;
+        double u1 = (double)(a >> 11) * 1.1102230246251565e-16 + 5.551115123125783e-17;  // 2^-53, 2^-54
+        double u2 = (double)(b >> 11) * 1.1102230246251565e-16 + 5.551115123125783e-17;
+        double r = sqrt(-2.0 * log(u1));
+        double s, c;
+#if defined(__CUDA_ARCH__)
+        sincospi(2.0 * u2, &s, &c);
+#else
+        s = sin(6.283185307179586 * u2);
+        c = cos(6.283185307179586 * u2);
+#endif
+        out[0] = r * s;
+        out[1] = r * c;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Noise model: colouring, bounds, action cost (device-side mirror of MppiFusedParams, pre-cast)
+// ------------------------------------------------------------------------------------------------
+#ifndef MPPI_MAX_NU
+#define MPPI_MAX_NU 4
+#endif
+#ifndef MPPI_MAX_NX
+#define MPPI_MAX_NX 8
+#endif
+
+template <typename real> struct NoiseModel {
+    real mu[MPPI_MAX_NU];
+    real L[MPPI_MAX_NU * MPPI_MAX_NU];      // lower Cholesky, row-major (diag: sqrt on the diagonal)
+    real Sinv[MPPI_MAX_NU * MPPI_MAX_NU];   // inverse covariance, row-major
+    real u_min[MPPI_MAX_NU], u_max[MPPI_MAX_NU];
+    real a_min[MPPI_MAX_NU], a_max[MPPI_MAX_NU];
+    real lambda_, neg_inv_lambda, u_scale, w_smooth, delta_t;
+    int diag, abs_cost;
+};
+
+// mppi.py:204-206: diag: z*sqrt(diag)+mu ; full: z @ L^T + mu  (row n: sum_m z_m L[n][m])
+template <typename real, int NU>
+MPPI_HD void colour(const NoiseModel<real>& nm, const real* z, real* e) {
+    typedef Ops<real> O;
+    if (nm.diag) {
+#pragma unroll
+        for (int n = 0; n < NU; ++n) e[n] = O::add(O::mul(z[n], nm.L[n * MPPI_MAX_NU + n]), nm.mu[n]);
+    } else {
+#pragma unroll
+        for (int n = 0; n < NU; ++n) {
+            real acc = O::mul(z[0], nm.L[n * MPPI_MAX_NU + 0]);
+#pragma unroll
+            for (int m = 1; m < NU; ++m) acc = O::add(acc, O::mul(z[m], nm.L[n * MPPI_MAX_NU + m]));
+            e[n] = O::add(acc, nm.mu[n]);
+        }
+    }
+}
+
+// mppi.py:186-199 and :415 for one (k,t): sum_n U_n * (lambda * g(eps) Sigma^-1)_n
+template <typename real, int NU>
+MPPI_HD real action_cost_term(const NoiseModel<real>& nm, const real* eps, const real* Urow) {
+    typedef Ops<real> O;
+    real g[NU];
+#pragma unroll
+    for (int n = 0; n < NU; ++n) g[n] = O::mul(nm.lambda_, nm.abs_cost ? O::abs_(eps[n]) : eps[n]);
+    real tot = (real)0;
+#pragma unroll
+    for (int n = 0; n < NU; ++n) {
+        real ac;
+        if (nm.diag) {
+            ac = O::mul(g[n], nm.Sinv[n * MPPI_MAX_NU + n]);
+        } else {
+            ac = O::mul(g[0], nm.Sinv[0 * MPPI_MAX_NU + n]);
+#pragma unroll
+            for (int m = 1; m < NU; ++m) ac = O::add(ac, O::mul(g[m], nm.Sinv[m * MPPI_MAX_NU + n]));
+        }
+        tot = O::add(tot, O::mul(Urow[n], ac));
+    }
+    return tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Registered analytic models.  Interface:
+//   NX, NU ; P<real> (parameters) ; load(P&, const double* blob)
+//   step(P, x[NX] inout, u[NU])          — one dynamics step (u already multiplied by u_scale)
+//   cost(P, x[NX], u[NU])                — running cost on the POST-step state (mppi.py:314-319)
+//   has_terminal(P) / terminal(P, xT)    — terminal cost on the last state (mppi.py:324-328)
+// ------------------------------------------------------------------------------------------------
+struct PendulumModel {
+    static const int NX = 2, NU = 1;
+    template <typename real> struct P {
+        real c_sin, c_u, dt, max_torque, max_speed, pi, two_pi, w_thdot;
+    };
+    template <typename real> static void load(P<real>& p, const double* b) {
+        double g = b[0], m = b[1], l = b[2];
+        p.c_sin = (real)(3 * g / (2 * l));          // tests/pendulum.py:43, python-float literal
+        p.c_u = (real)(3.0 / (m * l * l));
+        p.dt = (real)b[3];
+        p.max_torque = (real)b[4];
+        p.max_speed = (real)b[5];
+        p.w_thdot = (real)b[6];
+        p.pi = (real)3.141592653589793;
+        p.two_pi = (real)(2 * 3.141592653589793);
+    }
+    // tests/pendulum.py:30-48
+    template <typename real> static MPPI_HD void step(const P<real>& p, real* x, const real* u) {
+        typedef Ops<real> O;
+        real uc = clamp<real>(u[0], -p.max_torque, p.max_torque);
+        real acc = O::add(O::mul(p.c_sin, O::sin_(x[0])), O::mul(p.c_u, uc));
+        real thd = O::add(x[1], O::mul(acc, p.dt));
+        thd = clamp<real>(thd, -p.max_speed, p.max_speed);
+        x[0] = O::add(x[0], O::mul(thd, p.dt));
+        x[1] = thd;
+    }
+    // tests/pendulum.py:51-60
+    template <typename real> static MPPI_HD real cost(const P<real>& p, const real* x, const real* u) {
+        typedef Ops<real> O;
+        real an = O::sub(remainder<real>(O::add(x[0], p.pi), p.two_pi), p.pi);
+        return O::add(O::mul(an, an), O::mul(p.w_thdot, O::mul(x[1], x[1])));
+    }
+    template <typename real> static MPPI_HD bool has_terminal(const P<real>&) { return false; }
+    template <typename real> static MPPI_HD real terminal(const P<real>&, const real*) { return (real)0; }
+};
+
+struct LinearPointModel {
+    static const int NX = 2, NU = 2;
+    static const int MAX_HILLS = 3;
+    template <typename real> struct P {
+        real B[4], goal[2], Q[4], R[4];
+        real hQ[MAX_HILLS][4], hc[MAX_HILLS][2], hh[MAX_HILLS];
+        real terminal_scale;
+        int has_R, n_hills;
+    };
+    template <typename real> static void load(P<real>& p, const double* b) {
+        for (int i = 0; i < 4; ++i) p.B[i] = (real)b[i];
+        p.goal[0] = (real)b[4]; p.goal[1] = (real)b[5];
+        for (int i = 0; i < 4; ++i) p.Q[i] = (real)b[6 + i];
+        p.has_R = b[10] != 0.0;
+        for (int i = 0; i < 4; ++i) p.R[i] = (real)b[11 + i];
+        p.terminal_scale = (real)b[15];
+        p.n_hills = (int)b[16];
+        if (p.n_hills > MAX_HILLS) p.n_hills = MAX_HILLS;
+        for (int h = 0; h < MAX_HILLS; ++h) {
+            for (int i = 0; i < 4; ++i) p.hQ[h][i] = (real)b[17 + 7 * h + i];
+            p.hc[h][0] = (real)b[17 + 7 * h + 4];
+            p.hc[h][1] = (real)b[17 + 7 * h + 5];
+            p.hh[h] = (real)b[17 + 7 * h + 6];
+        }
+    }
+    // d^T Q d as sum_i d_i * (sum_j d_j Q[i][j])
+    template <typename real> static MPPI_HD real quad(const real* d, const real* Q) {
+        typedef Ops<real> O;
+        real q0 = O::add(O::mul(d[0], Q[0]), O::mul(d[1], Q[1]));
+        real q1 = O::add(O::mul(d[0], Q[2]), O::mul(d[1], Q[3]));
+        return O::add(O::mul(d[0], q0), O::mul(d[1], q1));
+    }
+    // x + u @ B^T   (tests/test_mppi.py:24-29, tests/smooth_mppi.py:29-36)
+    template <typename real> static MPPI_HD void step(const P<real>& p, real* x, const real* u) {
+        typedef Ops<real> O;
+        real d0 = O::add(O::mul(u[0], p.B[0]), O::mul(u[1], p.B[1]));
+        real d1 = O::add(O::mul(u[0], p.B[2]), O::mul(u[1], p.B[3]));
+        x[0] = O::add(x[0], d0);
+        x[1] = O::add(x[1], d1);
+    }
+    template <typename real> static MPPI_HD real state_cost(const P<real>& p, const real* x) {
+        typedef Ops<real> O;
+        real d[2] = {O::sub(p.goal[0], x[0]), O::sub(p.goal[1], x[1])};
+        real c = quad<real>(d, p.Q);
+        for (int h = 0; h < p.n_hills; ++h) {
+            real e[2] = {O::sub(p.hc[h][0], x[0]), O::sub(p.hc[h][1], x[1])};
+            c = O::add(c, O::mul(p.hh[h], O::exp_(-quad<real>(e, p.hQ[h]))));
+        }
+        return c;
+    }
+    // tests/test_mppi.py:37-41 ; tests/smooth_mppi.py:50-76,105-111
+    template <typename real> static MPPI_HD real cost(const P<real>& p, const real* x, const real* u) {
+        typedef Ops<real> O;
+        real c = state_cost<real>(p, x);
+        if (p.has_R) c = O::add(c, quad<real>(u, p.R));
+        return c;
+    }
+    template <typename real> static MPPI_HD bool has_terminal(const P<real>& p) { return p.terminal_scale != (real)0; }
+    // tests/test_mppi.py:49-51 ; tests/smooth_mppi.py:102-103
+    template <typename real> static MPPI_HD real terminal(const P<real>& p, const real* xT) {
+        return Ops<real>::mul(p.terminal_scale, state_cost<real>(p, xT));
+    }
+};
+
+}  // namespace mppi

@@ -1,0 +1,182 @@
+"""Registry of analytic models whose dynamics + running cost are compiled into the fused kernel.
+
+The reference's plugin surface is a pair of Python callables ``dynamics(state, action)`` /
+``running_cost(state, action)`` (mppi.py:63-64, README.md:53-58).  Arbitrary callables cannot be
+inlined into CUDA, so the fused path recognises callables that are *bound methods of a registered
+model object*: pass ``model.dynamics`` / ``model.running_cost`` (and optionally
+``model.terminal_cost``) to the controller exactly as you would pass your own functions, and the
+controller launches the fused sm_100a kernel.  The same bound methods are ordinary torch functions
+(any device, any dtype), so they also serve as the simulator you step your real system with and as
+the callables of the per-step path.
+
+Anything else (a torch MLP, a lambda, a step-dependent function) takes the per-step path:
+the T-loop stays in Python with sampling / accumulation / softmin in CUDA kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+
+
+class AnalyticModel:
+    """Base class: a model known to the CUDA registry (include/mppi_b200.h `MppiModel`)."""
+    model_id: int = 0
+    nx: int = 0
+    nu: int = 0
+
+    def param_blob(self) -> list:
+        """The `model_params` doubles of MppiFusedParams for this instance."""
+        raise NotImplementedError
+
+    @property
+    def has_terminal(self) -> bool:
+        return False
+
+    # -- recognition of bound methods --------------------------------------------------------
+    @staticmethod
+    def owner_of(fn) -> Optional["AnalyticModel"]:
+        owner = getattr(fn, "__self__", None)
+        return owner if isinstance(owner, AnalyticModel) else None
+
+
+class Pendulum(AnalyticModel):
+    """Gym pendulum swing-up, the model of BASELINE configs 1/2/5
+    (/root/reference/tests/pendulum.py:30-60): state (theta, theta_dot), one torque input.
+
+        u      <- clamp(u, +-max_torque)
+        thdot' =  clip(thdot + (3g/(2l) sin(theta) + 3/(m l^2) u) dt, +-max_speed)
+        theta' =  theta + thdot' dt
+        cost   =  angle_normalize(theta')^2 + w_thdot thdot'^2
+    """
+    model_id = _cabi.MODEL_PENDULUM
+    nx, nu = 2, 1
+
+    def __init__(self, g=10.0, m=1.0, l=1.0, dt=0.05, max_torque=2.0, max_speed=8.0, w_thdot=0.1):
+        self.g, self.m, self.l, self.dt = float(g), float(m), float(l), float(dt)
+        self.max_torque, self.max_speed, self.w_thdot = float(max_torque), float(max_speed), float(w_thdot)
+
+    def param_blob(self):
+        return [self.g, self.m, self.l, self.dt, self.max_torque, self.max_speed, self.w_thdot]
+
+    def dynamics(self, state, action):
+        th = state[:, 0:1]
+        thdot = state[:, 1:2]
+        u = torch.clamp(action[:, 0:1], -self.max_torque, self.max_torque)
+        acc = (3 * self.g / (2 * self.l)) * torch.sin(th) + (3.0 / (self.m * self.l ** 2)) * u
+        new_thdot = torch.clamp(thdot + acc * self.dt, -self.max_speed, self.max_speed)
+        new_th = th + new_thdot * self.dt
+        return torch.cat((new_th, new_thdot), dim=1)
+
+    @staticmethod
+    def angle_normalize(x):
+        return ((x + math.pi) % (2 * math.pi)) - math.pi
+
+    def running_cost(self, state, action):
+        return self.angle_normalize(state[:, 0]) ** 2 + self.w_thdot * state[:, 1] ** 2
+
+
+class LinearPoint(AnalyticModel):
+    """2-D point mass with linear-delta dynamics ``x + u @ B.T``, a quadratic goal cost
+    ``(g-x)^T Q (g-x)``, optional action cost ``u^T R u``, up to three Gaussian hill costs
+    ``h exp(-(c-x)^T Q_h (c-x))`` and an optional terminal cost ``terminal_scale * state_cost(x_T)``.
+
+    `LinearPoint.unit_test_env()` is the fixture of the reference's test-suite
+    (/root/reference/tests/test_mppi.py:24-51); `LinearPoint.toy2d_nav()` is the Toy2D navigation
+    environment of /root/reference/tests/smooth_mppi.py:79-142 (BASELINE config 3).
+    """
+    model_id = _cabi.MODEL_LINEAR_POINT
+    nx, nu = 2, 2
+    MAX_HILLS = 3
+
+    def __init__(self, B, goal, Q=None, R=None, hills: Sequence = (), terminal_scale: float = 0.0):
+        self.B = [[float(v) for v in row] for row in B]
+        self.goal = [float(v) for v in goal]
+        self.Q = [[1.0, 0.0], [0.0, 1.0]] if Q is None else [[float(v) for v in row] for row in Q]
+        self.R = None if R is None else [[float(v) for v in row] for row in R]
+        self.hills = [([[float(v) for v in row] for row in q], [float(v) for v in c], float(h)) for q, c, h in hills]
+        if len(self.hills) > self.MAX_HILLS:
+            raise ValueError(f"at most {self.MAX_HILLS} hills are compiled into the fused kernel")
+        self.terminal_scale = float(terminal_scale)
+        self._cache = {}
+
+    @classmethod
+    def unit_test_env(cls, terminal_scale=0.0):
+        return cls(B=[[1.0, 0.0], [0.0, -1.0]], goal=[2.0, 2.0], terminal_scale=terminal_scale)
+
+    @classmethod
+    def toy2d_nav(cls, terminal_scale=10.0, r=0.01):
+        return cls(B=[[0.5, 0.0], [0.0, -0.5]], goal=[2.0, 2.0], R=[[r, 0.0], [0.0, r]],
+                   hills=[([[0.25, 0.125], [0.125, 0.25]], [-0.5, -1.0], 200.0)], terminal_scale=terminal_scale)
+
+    @property
+    def has_terminal(self):
+        return self.terminal_scale != 0.0
+
+    def param_blob(self):
+        flat = lambda m: [m[0][0], m[0][1], m[1][0], m[1][1]]
+        b = flat(self.B) + self.goal + flat(self.Q)
+        b += [1.0 if self.R is not None else 0.0] + (flat(self.R) if self.R is not None else [0.0] * 4)
+        b += [self.terminal_scale, float(len(self.hills))]
+        for q, c, h in self.hills:
+            b += flat(q) + c + [h]
+        b += [0.0] * (7 * (self.MAX_HILLS - len(self.hills)))
+        return b
+
+    # ---- torch implementations (any device/dtype) ---------------------------------------------
+    def _t(self, name, like):
+        key = (name, like.device, like.dtype)
+        if key not in self._cache:
+            src = {"B": self.B, "goal": self.goal, "Q": self.Q, "R": self.R}.get(name)
+            if src is None and name.startswith("hq"):
+                src = self.hills[int(name[2:])][0]
+            if src is None and name.startswith("hc"):
+                src = self.hills[int(name[2:])][1]
+            self._cache[key] = torch.tensor(src, device=like.device, dtype=like.dtype)
+        return self._cache[key]
+
+    @staticmethod
+    def _quad(d, Q):
+        return (d * (d @ Q.transpose(0, 1))).sum(dim=-1)
+
+    def dynamics(self, state, action):
+        return state + action @ self._t("B", state).transpose(0, 1)
+
+    def state_cost(self, state):
+        c = self._quad(self._t("goal", state) - state, self._t("Q", state))
+        for i, (_, _, h) in enumerate(self.hills):
+            c = c + h * torch.exp(-self._quad(self._t(f"hc{i}", state) - state, self._t(f"hq{i}", state)))
+        return c
+
+    def running_cost(self, state, action):
+        c = self.state_cost(state)
+        if self.R is not None:
+            c = c + self._quad(action, self._t("R", state))
+        return c
+
+    def terminal_cost(self, states, actions):
+        return self.terminal_scale * self.state_cost(states[..., -1, :])
+
+
+def resolve_fused_model(dynamics, running_cost, terminal_state_cost) -> Optional[AnalyticModel]:
+    """The registered model these plugins belong to, or None if they are not (all) bound methods of
+    one registered model — in which case the controller uses the per-step path."""
+    m = AnalyticModel.owner_of(dynamics)
+    if m is None or AnalyticModel.owner_of(running_cost) is not m:
+        return None
+    if getattr(dynamics, "__func__", None) is not type(m).dynamics:
+        return None
+    if getattr(running_cost, "__func__", None) is not type(m).running_cost:
+        return None
+    if terminal_state_cost is None:
+        # the kernel adds the model's terminal cost iff terminal_scale != 0; without the plugin the
+        # reference adds none, so only models whose terminal term is off qualify
+        return m if not m.has_terminal else None
+    if AnalyticModel.owner_of(terminal_state_cost) is not m or not m.has_terminal:
+        return None
+    if getattr(terminal_state_cost, "__func__", None) is not getattr(type(m), "terminal_cost", None):
+        return None
+    return m

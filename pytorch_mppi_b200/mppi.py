@@ -1,0 +1,1031 @@
+"""MPPI / SMPPI / KMPPI controllers with the reference's constructor + ``command()`` API
+(/root/reference/src/pytorch_mppi/mppi.py:35-688), executing on hand-written sm_100a kernels.
+
+Two execution routes, chosen at construction:
+
+* fused  — dynamics / running_cost (/ terminal cost) are bound methods of one registered analytic
+           model (pytorch_mppi_b200.models): ONE kernel launch per ``command()`` does sampling,
+           rollout, softmin and the nominal update (csrc/mppi_fused.cuh `fused_command_kernel`).
+* stepped — arbitrary Python callables (a torch MLP, step-dependent functions, M>1 rollouts, a
+           SpecificActionSampler): the T-loop stays in Python exactly like mppi.py:312-322, with the
+           sampling (`mppi_sample_perturb`), cost accumulation (`mppi_cost_accumulate`) and softmin
+           update (`mppi_softmin_update`) as kernels.
+
+There is no CPU / eager-PyTorch fallback: a missing CUDA library or a non-CUDA device raises.
+PyTorch is used for device memory, streams and (multi-GPU) torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import time
+import typing
+
+import torch
+
+from . import _cabi
+from .models import AnalyticModel, resolve_fused_model
+
+logger = logging.getLogger(__name__)
+
+_DT = {torch.float32: _cabi.F32, torch.float64: _cabi.F64}
+_ES = {torch.float32: 4, torch.float64: 8}
+
+
+class SpecificActionSampler:
+    """Same hook as the reference's (mppi.py:16-32)."""
+
+    def __init__(self):
+        self.start_idx = 0
+        self.end_idx = 0
+        self.slice = slice(0, 0)
+
+    def sample_trajectories(self, state, info):
+        raise NotImplementedError
+
+    def specific_dynamics(self, next_state, state, action, t):
+        return next_state
+
+    def register_sample_start_end(self, start_idx, end_idx):
+        self.start_idx = start_idx
+        self.end_idx = end_idx
+        self.slice = slice(start_idx, end_idx)
+
+
+def _vec(x, n, name):
+    """nu-vector of python floats from a float / 0-dim / (n,) tensor."""
+    if x is None:
+        return None
+    t = torch.as_tensor(x).detach().to("cpu", torch.float64).reshape(-1)
+    if t.numel() == 1:
+        t = t.repeat(n)
+    if t.numel() != n:
+        raise ValueError(f"{name} must have {n} entries, got {t.numel()}")
+    return t.tolist()
+
+
+def _pad16(n_elems, es):
+    return (n_elems * es + 15) // 16 * 16 // es
+
+
+class MPPI:
+    """Model Predictive Path Integral control (Williams et al. 2017, alg. 2), B200 engine.
+    Constructor and methods mirror the reference (mppi.py:45-61, 208-290, 425-448)."""
+
+    _VARIANT = _cabi.VARIANT_MPPI
+
+    def __init__(self, dynamics, running_cost, nx, noise_sigma, num_samples=100, horizon=15, device="cuda",
+                 terminal_state_cost=None,
+                 lambda_=1.,
+                 noise_mu=None,
+                 u_min=None,
+                 u_max=None,
+                 u_init=None,
+                 U_init=None,
+                 u_scale=1,
+                 u_per_command=1,
+                 step_dependent_dynamics=False,
+                 rollout_samples=1,
+                 rollout_var_cost=0,
+                 rollout_var_discount=0.95,
+                 sample_null_action=False,
+                 specific_action_sampler: typing.Optional[SpecificActionSampler] = None,
+                 noise_abs_cost=False,
+                 *,
+                 rng_seed: typing.Optional[int] = None,
+                 block_threads: int = 0,
+                 process_group=None,
+                 exchange: str = "p2p"):
+        self._lib = _cabi.load()          # raises if the CUDA library is not built
+        self.d = torch.device(device)
+        if self.d.type != "cuda":
+            raise ValueError("pytorch_mppi_b200 runs on CUDA devices only (pass device='cuda'); "
+                             "there is no CPU fallback")
+        if self.d.index is None:
+            self.d = torch.device("cuda", torch.cuda.current_device())
+        if not torch.is_tensor(noise_sigma):
+            noise_sigma = torch.tensor(noise_sigma)
+        self.dtype = noise_sigma.dtype                                         # mppi.py:88
+        if self.dtype not in _DT:
+            raise ValueError(f"dtype {self.dtype} is not supported (float32 / float64)")
+        self.K = int(num_samples)
+        self.T = int(horizon)
+        self.nx = int(nx)
+        self.nu = 1 if noise_sigma.dim() == 0 else noise_sigma.shape[0]        # mppi.py:94
+        if self.nu > _cabi.MPPI_MAX_NU:
+            raise ValueError(f"nu={self.nu} exceeds the engine's MPPI_MAX_NU={_cabi.MPPI_MAX_NU}")
+        self._dirty = True
+        self._lambda = float(lambda_)
+        if noise_mu is None:
+            noise_mu = torch.zeros(self.nu, dtype=self.dtype)
+        if u_init is None:
+            u_init = torch.zeros_like(torch.as_tensor(noise_mu))
+        noise_mu = torch.as_tensor(noise_mu)
+        if self.nu == 1:                                                       # mppi.py:104-106
+            noise_mu = noise_mu.reshape(-1)
+            noise_sigma = noise_sigma.reshape(-1, 1)
+        self._u_scale = u_scale
+        self.u_per_command = int(u_per_command)
+        # bounds (mppi.py:112-126)
+        if u_max is not None and u_min is None:
+            u_max = torch.as_tensor(u_max)
+            u_min = -u_max
+        if u_min is not None and u_max is None:
+            u_min = torch.as_tensor(u_min)
+            u_max = -u_min
+        if u_min is not None:
+            self._u_min = torch.as_tensor(u_min).to(self.d)
+            self._u_max = torch.as_tensor(u_max).to(self.d)
+        else:
+            self._u_min = torch.tensor(float("-inf"), device=self.d)
+            self._u_max = torch.tensor(float("inf"), device=self.d)
+        self._noise_mu = noise_mu.to(self.d, self.dtype)
+        self._set_sigma(noise_sigma.to(self.d, self.dtype))
+        self._u_init = torch.as_tensor(u_init).to(self.d, self.dtype).reshape(-1)
+
+        # plugins (mppi.py:147-163)
+        self.step_dependency = step_dependent_dynamics
+        if step_dependent_dynamics:
+            self._dynamics_fn = dynamics
+            self._running_cost_fn = running_cost
+        else:
+            self._dynamics_fn = lambda state, u, t: dynamics(state, u)
+            self._running_cost_fn = lambda state, u, t: running_cost(state, u)
+        self.F = dynamics
+        self.running_cost = running_cost
+        self.terminal_state_cost = terminal_state_cost
+        self.sample_null_action = sample_null_action
+        self.specific_action_sampler = specific_action_sampler
+        self.noise_abs_cost = noise_abs_cost
+        self.state = None
+        self.info = None
+        self.M = int(rollout_samples)
+        self.rollout_var_cost = rollout_var_cost
+        self.rollout_var_discount = rollout_var_discount
+
+        # route selection
+        self._model: typing.Optional[AnalyticModel] = None
+        if (self.M == 1 and specific_action_sampler is None and not step_dependent_dynamics):
+            m = resolve_fused_model(dynamics, running_cost, terminal_state_cost)
+            if m is not None and m.nx == self.nx and m.nu == self.nu:
+                self._model = m
+        self._block_threads = int(block_threads)
+
+        # multi-GPU: K is the GLOBAL sample count, sharded over the group
+        self._pg = process_group
+        self._exchange = exchange
+        self._rank, self._world = 0, 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self._rank = dist.get_rank(process_group)
+            self._world = dist.get_world_size(process_group)
+        from .distributed import shard_bounds
+        self._k_offset, self._K_local = shard_bounds(self.K, self._rank, self._world)
+        self._epoch = 0
+        self._mailboxes = None
+
+        # RNG: own (seed, counter) if rng_seed is given, else the torch CUDA generator protocol
+        self._rng_seed = None if rng_seed is None else int(rng_seed) & 0xFFFFFFFFFFFFFFFF
+        self._rng_counter = 0
+        if self._world > 1 and self._rng_seed is None:
+            import torch.distributed as dist
+            s = torch.empty(1, dtype=torch.int64, device=self.d)
+            if self._rank == 0:
+                s.fill_(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+            dist.broadcast(s, src=dist.get_global_rank(process_group, 0) if hasattr(dist, "get_global_rank") else 0,
+                           group=process_group)
+            self._rng_seed = int(s.item())
+        self._z_inject = None
+        self._z_out = None
+
+        # device state
+        self._alloc_nominal(U_init)
+        self._alloc_results()
+        self._p = _cabi.MppiFusedParams()
+        self._cmd_count = 0
+        self._materialized_at = {}
+
+        # sampled results from last command (mppi.py:179-184)
+        self.cost_total = None
+        self._states = None
+        self._actions = None
+
+    # ------------------------------------------------------------------------------------------
+    # configuration that feeds kernel constants; setters mark the packed struct dirty
+    # (fixes the reference's stale-cache gotcha when autotune mutates these: SURVEY.md §5)
+    # ------------------------------------------------------------------------------------------
+    def _set_sigma(self, sigma):
+        self._noise_sigma = sigma
+        self._diagonal_sigma = bool(torch.equal(sigma, torch.diag(torch.diag(sigma))))     # mppi.py:131
+        if self._diagonal_sigma:
+            diag = torch.diag(sigma)
+            self._noise_sigma_inv_diag = 1.0 / diag
+            self._noise_sigma_sqrt_diag = torch.sqrt(diag)
+            self._noise_sigma_inv = torch.diag(self._noise_sigma_inv_diag)
+            self._chol = torch.diag(self._noise_sigma_sqrt_diag)
+        else:
+            self._noise_sigma_inv = torch.linalg.inv(sigma)                                  # mppi.py:138-139
+            self._chol = torch.linalg.cholesky(sigma)
+        self._dirty = True
+
+    noise_sigma = property(lambda self: self._noise_sigma, lambda self, v: self._set_sigma(torch.as_tensor(v).to(self.d, self.dtype).reshape(self.nu, self.nu)))
+
+    @property
+    def noise_sigma_inv(self):
+        return self._noise_sigma_inv
+
+    @noise_sigma_inv.setter
+    def noise_sigma_inv(self, v):   # autotune writes it next to noise_sigma (autotune.py:160-162); derived here
+        pass
+
+    def _mk(name):   # noqa: N805  (tiny property factory)
+        def get(self):
+            return getattr(self, "_" + name)
+
+        def set_(self, v):
+            setattr(self, "_" + name, v)
+            self._dirty = True
+        return property(get, set_)
+
+    lambda_ = _mk("lambda")
+    u_scale = _mk("u_scale")
+    u_min = _mk("u_min")
+    u_max = _mk("u_max")
+    noise_mu = _mk("noise_mu")
+    u_init = _mk("u_init")
+    del _mk
+
+    # ------------------------------------------------------------------------------------------
+    # buffers
+    # ------------------------------------------------------------------------------------------
+    def _rows(self):
+        return self.T * self.nu
+
+    def _alloc_nominal(self, U_init):
+        es = _ES[self.dtype]
+        tn = self.T * self.nu
+        self._Ubuf = torch.zeros(_pad16(tn, es), device=self.d, dtype=self.dtype)
+        if U_init is None:
+            self.U = self._sample_noise((self.T,))                                          # mppi.py:144-145
+        else:
+            self.U = U_init
+
+    def _alloc_results(self):
+        K, tn = self._K_local, self.T * self.nu
+        self._cost_buf = torch.empty(K, device=self.d, dtype=self.dtype)
+        self._nominal_used = torch.zeros(3 * tn + 4, device=self.d, dtype=self.dtype)
+        self._stats = torch.zeros(4, device=self.d, dtype=torch.float64)
+        self._workspace = None
+        self._partial = None
+
+    @property
+    def U(self):
+        return self._Ubuf[: self.T * self.nu].view(self.T, self.nu)
+
+    @U.setter
+    def U(self, value):
+        value = torch.as_tensor(value).to(self.d, self.dtype).reshape(-1, self.nu)
+        if value.shape[0] != self.T:
+            raise ValueError(f"U must have T={self.T} rows, got {value.shape[0]}")
+        self._Ubuf[: self.T * self.nu].copy_(value.reshape(-1))
+
+    def _sample_noise(self, shape):
+        """N(noise_mu, noise_sigma) draws for U initialisation / reset (mppi.py:201-206).  Off the hot
+        path: plain torch on the device."""
+        z = torch.randn(*shape, self.nu, device=self.d, dtype=self.dtype)
+        if self._diagonal_sigma:
+            return z * self._noise_sigma_sqrt_diag + self._noise_mu
+        return z @ self._chol.T + self._noise_mu
+
+    # ------------------------------------------------------------------------------------------
+    # packing the C-ABI struct
+    # ------------------------------------------------------------------------------------------
+    def _variant_pack(self, p):
+        pass
+
+    def _pack(self):
+        p = self._p
+        nu = self.nu
+        p.struct_size = C.sizeof(_cabi.MppiFusedParams)
+        p.variant = self._VARIANT
+        p.model = self._model.model_id if self._model is not None else 0
+        p.dtype = _DT[self.dtype]
+        p.K, p.T, p.nx, p.nu = self._K_local, self.T, self.nx, nu
+        p.S = 0
+        p.u_per_command = self.u_per_command
+        p.block_threads = self._block_threads
+        p.grid_blocks = 0
+        p.k_offset = self._k_offset
+        p.lambda_ = float(self._lambda)
+        p.u_scale = float(self._u_scale)
+        mu = _vec(self._noise_mu, nu, "noise_mu")
+        umin = _vec(self._u_min, nu, "u_min")
+        umax = _vec(self._u_max, nu, "u_max")
+        uinit = _vec(self._u_init, nu, "u_init")
+        L = self._chol.detach().to("cpu", torch.float64)
+        Si = self._noise_sigma_inv.detach().to("cpu", torch.float64)
+        for i in range(_cabi.MPPI_MAX_NU):
+            p.noise_mu[i] = mu[i] if i < nu else 0.0
+            p.u_min[i] = umin[i] if i < nu else 0.0
+            p.u_max[i] = umax[i] if i < nu else 0.0
+            p.u_init[i] = uinit[i] if i < nu else 0.0
+            p.action_min[i] = -math.inf
+            p.action_max[i] = math.inf
+            for j in range(_cabi.MPPI_MAX_NU):
+                inside = i < nu and j < nu
+                p.chol[i * _cabi.MPPI_MAX_NU + j] = float(L[i, j]) if inside else 0.0
+                p.sigma_inv[i * _cabi.MPPI_MAX_NU + j] = float(Si[i, j]) if inside else 0.0
+        p.w_action_seq_cost = 0.0
+        p.delta_t = 1.0
+        blob = self._model.param_blob() if self._model is not None else []
+        for i in range(_cabi.MPPI_MODEL_PARAM_DOUBLES):
+            p.model_params[i] = float(blob[i]) if i < len(blob) else 0.0
+        self._base_flags = ((_cabi.FLAG_NULL_ACTION if self.sample_null_action else 0)
+                            | (_cabi.FLAG_ABS_COST if self.noise_abs_cost else 0)
+                            | (_cabi.FLAG_DIAG_SIGMA if self._diagonal_sigma else 0)
+                            | _cabi.FLAG_NOMINAL_PADDED)
+        p.U = self._Ubuf.data_ptr()
+        p.A = None
+        p.theta = None
+        p.W = None
+        p.Wshift = None
+        p.cost_total = self._cost_buf.data_ptr()
+        p.nominal_used = self._nominal_used.data_ptr()
+        p.stats = self._stats.data_ptr()
+        p.z = None
+        p.z_out = None
+        p.rank, p.world = self._rank, self._world
+        for g in range(_cabi.MPPI_MAX_RANKS):
+            p.peer_slots[g] = None
+        p.partial_out = None
+        self._variant_pack(p)
+        # workspace sized for the worst-case geometry of these dimensions
+        if self._model is not None:
+            info = _cabi.MppiLaunchInfo()
+            p.flags = self._base_flags
+            _cabi.check(self._lib.mppi_fused_query(C.byref(p), C.byref(info)), "mppi_fused_query")
+            self.launch_info = info
+            need = int(info.workspace_bytes)
+        else:
+            need = 16 + 148 * 16 * (2 + self._noise_rows()) * 8 + 64
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.zeros(need, device=self.d, dtype=torch.uint8)
+        p.workspace = self._workspace.data_ptr()
+        p.workspace_bytes = self._workspace.numel()
+        if self._world > 1:
+            self._setup_exchange(p)
+        self._dirty = False
+
+    def _noise_rows(self):
+        return self.T * self.nu
+
+    def _setup_exchange(self, p):
+        from . import distributed as D
+        if self._exchange == "p2p":
+            if self._mailboxes is None:
+                self._mailboxes = D.PeerMailboxes(self._lib, self._pg, self.d)
+            for g in range(self._world):
+                p.peer_slots[g] = self._mailboxes.ptrs[g]
+        else:
+            rows = self._noise_rows()
+            if self._partial is None:
+                self._partial = torch.zeros(rows + 2, device=self.d, dtype=torch.float64)
+                self._gathered = torch.zeros(self._world * (rows + 2), device=self.d, dtype=torch.float64)
+            p.partial_out = self._partial.data_ptr()
+
+    # ------------------------------------------------------------------------------------------
+    # RNG stream
+    # ------------------------------------------------------------------------------------------
+    def _next_rng(self):
+        """(seed, counter base) for this command; the counter advances by the Philox calls one
+        sample makes.  With rng_seed=None the stream is the torch CUDA generator's
+        (torch.manual_seed reseeds it), consumed with the same (seed, offset) protocol ATen ops use."""
+        per = 4 if self.dtype == torch.float32 else 2
+        chunks = (self._noise_rows() + per - 1) // per
+        if self._rng_seed is not None:
+            base = self._rng_counter
+            self._rng_counter += chunks
+            return self._rng_seed, base
+        gen = torch.cuda.default_generators[self.d.index]
+        seed = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        try:
+            off = gen.get_offset()
+            gen.set_offset(off + 4 * chunks)
+        except (AttributeError, RuntimeError):   # very old torch: private counter keyed by the seed
+            if getattr(self, "_rng_last_seed", None) != seed:
+                self._rng_last_seed, self._rng_counter = seed, 0
+            off = 4 * self._rng_counter
+            self._rng_counter += chunks
+        return seed, off // 4
+
+    def inject_noise(self, z):
+        """Parity hook: the next command consumes these standard normals — shape (K,T,nu)
+        (KMPPI: (K,S,nu)) — instead of drawing from Philox.  This is how the engine and the
+        reference/oracle are fed identical draws."""
+        rows = self._noise_rows()
+        z = torch.as_tensor(z).to(self.d, self.dtype).contiguous()
+        if z.numel() != self._K_local * rows:
+            if z.numel() == self.K * rows:   # global tensor given to a shard
+                z = z.reshape(self.K, rows)[self._k_offset:self._k_offset + self._K_local].contiguous()
+            else:
+                raise ValueError(f"injected noise must have {self._K_local * rows} elements, got {z.numel()}")
+        self._z_inject = z
+
+    def record_noise(self, enable=True):
+        """Keep the standard normals each command actually used in `self.z_used`."""
+        self._z_out = torch.empty(self._K_local * self._noise_rows(), device=self.d, dtype=self.dtype) if enable else None
+
+    @property
+    def z_used(self):
+        return None if self._z_out is None else self._z_out.view(self._K_local, -1, self.nu)
+
+    # ------------------------------------------------------------------------------------------
+    # public API (mppi.py:208-290)
+    # ------------------------------------------------------------------------------------------
+    def compile(self, **kwargs):
+        """API compatibility (mppi.py:208-215).  The fused route is already one kernel; on the stepped
+        route the user's callables run as given.  No tracing compiler is involved."""
+        self._compile_kwargs = kwargs
+
+    def get_params(self):
+        return f"K={self.K} T={self.T} M={self.M} lambda={self.lambda_} noise_mu={self.noise_mu.cpu().numpy()} noise_sigma={self.noise_sigma.cpu().numpy()}".replace(
+            "\n", ",")
+
+    def get_action_sequence(self):
+        return self.U
+
+    def shift_nominal_trajectory(self):
+        """mppi.py:232-238.  (command() folds the shift into the kernel; this explicit form is for
+        callers that shift by hand.)"""
+        U = torch.roll(self.U, -1, dims=0)
+        U[-1] = self._u_init
+        self.U = U
+
+    def reset(self):
+        """mppi.py:286-290"""
+        self.U = self._sample_noise((self.T,))
+
+    def change_horizon(self, horizon):
+        """mppi.py:277-284"""
+        U = self.U.clone()
+        if horizon < U.shape[0]:
+            U = U[:horizon]
+        elif horizon > U.shape[0]:
+            U = torch.cat((U, self._u_init.repeat(horizon - U.shape[0], 1)))
+        self._resize_horizon(horizon, U)
+
+    def _resize_horizon(self, horizon, U):
+        self.T = int(horizon)
+        self._alloc_nominal(U)
+        self._alloc_results()
+        self._dirty = True
+
+    def command(self, state, shift_nominal_trajectory=True, info=None):
+        """mppi.py:240-252: returns the first `u_per_command` actions of the updated sequence."""
+        self.info = info
+        if self._dirty:
+            self._pack()
+        if self._model is not None:
+            return self._command_fused(state, shift_nominal_trajectory)
+        return self._command_stepped(state, shift_nominal_trajectory)
+
+    # ------------------------------------------------------------------------------------------
+    # fused route
+    # ------------------------------------------------------------------------------------------
+    def _set_state(self, p, state, flags):
+        """State by value in the parameter struct when it lives on the host (no H2D copy);
+        device pointer when it is already a CUDA tensor or one state per sample."""
+        if torch.is_tensor(state) and state.is_cuda:
+            st = state.to(self.dtype)
+            if st.dim() == 2 and st.shape == (self.K, self.nx) and self.K != 1:
+                st = st[self._k_offset:self._k_offset + self._K_local].contiguous()
+                flags |= _cabi.FLAG_STATE_DEVICE | _cabi.FLAG_STATE_PER_SAMPLE
+            else:
+                st = st.reshape(-1).contiguous()
+                flags |= _cabi.FLAG_STATE_DEVICE
+            self.state = st
+            p.state_dev = st.data_ptr()
+            return flags
+        vals = state.tolist() if hasattr(state, "tolist") else list(state)
+        if len(vals) and isinstance(vals[0], (list, tuple)):
+            if len(vals) == self.K and self.K != 1:   # (K,nx) host states -> upload once
+                return self._set_state(p, torch.as_tensor(state).to(self.d), flags)
+            vals = vals[0]
+        if len(vals) < self.nx:
+            raise ValueError(f"state has {len(vals)} entries, nx={self.nx}")
+        for i in range(self.nx):
+            p.state[i] = vals[i]
+        self.state = state
+        p.state_dev = None
+        return flags
+
+    def _begin_command(self, state, shift):
+        p = self._p
+        flags = self._base_flags | (_cabi.FLAG_SHIFT if shift else 0)
+        flags = self._set_state(p, state, flags)
+        if self._z_inject is not None:
+            p.z = self._z_inject.data_ptr()
+            self._z_keep = self._z_inject      # stays alive for lazy materialisation
+            self._z_inject = None
+            p.seed, p.offset = 0, 0
+        else:
+            p.z = None
+            self._z_keep = None
+            p.seed, p.offset = self._next_rng()
+        p.z_out = None if self._z_out is None else self._z_out.data_ptr()
+        if self._world > 1:
+            self._epoch += 1
+            p.epoch = self._epoch
+            if self._exchange != "p2p":
+                flags |= _cabi.FLAG_EXPORT_PARTIAL
+        p.flags = flags
+        action = torch.empty((self.u_per_command, self.nu), device=self.d, dtype=self.dtype)
+        p.action_out = action.data_ptr()
+        self._cmd_count += 1
+        return p, action
+
+    def _finish_command(self, p, action, stream):
+        if self._world > 1 and self._exchange != "p2p":
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._gathered, self._partial, group=self._pg)
+            p.flags &= ~_cabi.FLAG_EXPORT_PARTIAL
+            _cabi.check(self._lib.mppi_apply_partials(C.byref(p), self._gathered.data_ptr(), stream), "mppi_apply_partials")
+        self.cost_total = self._cost_buf
+        self._states = None
+        self._actions = None
+        if self.u_per_command == 1:                                                        # mppi.py:273-274
+            return action[0]
+        return action
+
+    def _command_fused(self, state, shift):
+        p, action = self._begin_command(state, shift)
+        stream = torch.cuda.current_stream(self.d).cuda_stream
+        rc = self._lib.mppi_fused_command(C.byref(p), stream)
+        if rc != 0:
+            _cabi.check(rc, "mppi_fused_command")
+        return self._finish_command(p, action, stream)
+
+    # ------------------------------------------------------------------------------------------
+    # stepped route (arbitrary callables): mppi.py:297-373 with kernels around the T-loop
+    # ------------------------------------------------------------------------------------------
+    def _ensure_step_buffers(self):
+        K, T, nu = self._K_local, self.T, self.nu
+        if getattr(self, "_pa_buf", None) is None or self._pa_buf.shape != (K, T, nu):
+            self._pa_buf = torch.empty(K, T, nu, device=self.d, dtype=self.dtype)
+            self._noise_buf = torch.empty(K, T, nu, device=self.d, dtype=self.dtype)
+            self._cost_init = torch.empty(K, device=self.d, dtype=self.dtype)
+            self._noise_theta_buf = None
+
+    def _eps_for_update(self):
+        return self._noise_buf
+
+    def _command_stepped(self, state, shift):
+        lib = self._lib
+        self._ensure_step_buffers()
+        if not torch.is_tensor(state):
+            state = torch.tensor(state)
+        st = state.to(dtype=self.dtype, device=self.d)                                     # mppi.py:262-264
+        p, action = self._begin_command(st if st.dim() == 1 else st.reshape(-1)[: self.nx], shift)
+        self.state = st
+        stream = torch.cuda.current_stream(self.d).cuda_stream
+        K, T, nu = self._K_local, self.T, self.nu
+
+        ovr_ptr, n_ovr, ovr_start = None, 0, 0
+        if self.specific_action_sampler is not None:                                       # mppi.py:393-399
+            acts = self.specific_action_sampler.sample_trajectories(self.state, self.info)
+            acts = acts.reshape(-1, T, nu).to(self.d, self.dtype).contiguous()
+            ovr_start = 1 if self.sample_null_action else 0
+            n_ovr = acts.shape[0]
+            self.specific_action_sampler.register_sample_start_end(ovr_start, ovr_start + n_ovr)
+            self._ovr_keep = acts
+            ovr_ptr = acts.data_ptr()
+        nth = None if self._noise_theta_buf is None else self._noise_theta_buf.data_ptr()
+        _cabi.check(lib.mppi_sample_perturb(C.byref(p), self._pa_buf.data_ptr(), self._noise_buf.data_ptr(), nth,
+                                            self._cost_init.data_ptr(), ovr_ptr, n_ovr, ovr_start, stream),
+                    "mppi_sample_perturb")
+        self._materialized_at["noise"] = self._cmd_count
+
+        if self.M == 1:
+            rollout, states, actions = self._rollout_single(self._pa_buf, stream)
+        else:
+            rollout, states, actions = self._rollout_multi(self._pa_buf, stream)
+        # cost_total = rollout + perturbation (+ smoothness), mppi.py:416 / :569
+        _cabi.check(lib.mppi_cost_accumulate(rollout.data_ptr(), self._cost_init.data_ptr(), None, 1, K, 1.0,
+                                             _DT[self.dtype], stream), "mppi_cost_accumulate")
+        self._cost_buf = rollout
+        p.cost_total = rollout.data_ptr()
+        _cabi.check(lib.mppi_softmin_update(C.byref(p), rollout.data_ptr(), self._eps_for_update().data_ptr(), stream),
+                    "mppi_softmin_update")
+        out = self._finish_command(p, action, stream)
+        self._states = states
+        self._actions = actions / self._u_scale if actions is not None else None         # mppi.py:412
+        return out
+
+    def _rollout_single(self, perturbed_actions, stream):
+        """mppi.py:297-332"""
+        lib = self._lib
+        K, T, nu = perturbed_actions.shape
+        cost_total = torch.zeros(K, device=self.d, dtype=self.dtype)
+        if self.state.shape == (self.K, self.nx) and self.K != 1:
+            state = self.state[self._k_offset:self._k_offset + K].clone()
+        else:
+            state = self.state.view(1, -1).expand(K, -1)
+        need_storage = self.terminal_state_cost is not None
+        states = actions = None
+        if need_storage:
+            states = torch.empty(1, K, T, self.nx, device=self.d, dtype=self.dtype)
+            actions = torch.empty(1, K, T, nu, device=self.d, dtype=self.dtype)
+        dt = _DT[self.dtype]
+        for t in range(T):
+            u = self._u_scale * perturbed_actions[:, t]
+            state = self._dynamics_fn(state, u, t)
+            if self.specific_action_sampler is not None:
+                state = self.specific_action_sampler.specific_dynamics(
+                    state.unsqueeze(0), state.unsqueeze(0), u.unsqueeze(0), t).squeeze(0)
+            c = self._running_cost_fn(state, u, t).reshape(K)
+            if c.dtype != self.dtype or not c.is_contiguous():
+                c = c.to(self.dtype).contiguous()
+            rc = lib.mppi_cost_accumulate(cost_total.data_ptr(), c.data_ptr(), None, 1, K, 1.0, dt, stream)
+            if rc != 0:
+                _cabi.check(rc, "mppi_cost_accumulate")
+            if need_storage:
+                states[0, :, t] = state[:, :self.nx]
+                actions[0, :, t] = u
+        if need_storage:
+            c = self.terminal_state_cost(states, actions)
+            if torch.is_tensor(c) and c.dim() > 1:
+                c = c.squeeze(0)
+            if torch.is_tensor(c):
+                c = c.to(self.dtype).reshape(K).contiguous()
+                _cabi.check(lib.mppi_cost_accumulate(cost_total.data_ptr(), c.data_ptr(), None, 1, K, 1.0, dt, stream),
+                            "mppi_cost_accumulate")
+            else:
+                cost_total += c
+        return cost_total, states, actions
+
+    def _rollout_multi(self, perturbed_actions, stream):
+        """mppi.py:334-373 (M>1: stochastic dynamics with a discounted variance cost)"""
+        lib = self._lib
+        K, T, nu = perturbed_actions.shape
+        M = self.M
+        dt = _DT[self.dtype]
+        cost_samples = torch.zeros(M, K, device=self.d, dtype=self.dtype)
+        cost_var = torch.zeros(K, device=self.d, dtype=self.dtype)
+        if self.state.shape == (self.K, self.nx) and self.K != 1:
+            state = self.state[self._k_offset:self._k_offset + K]
+        else:
+            state = self.state.view(1, -1).expand(K, -1)
+        state = state.repeat(M, 1, 1)
+        states = torch.empty(M, K, T, self.nx, device=self.d, dtype=self.dtype)
+        actions = torch.empty(M, K, T, nu, device=self.d, dtype=self.dtype)
+        MK = M * K
+        state_flat = state.reshape(MK, self.nx)
+        for t in range(T):
+            u = self._u_scale * perturbed_actions[:, t].expand(M, -1, -1)
+            u_flat = u.reshape(MK, nu)
+            state_flat = self._dynamics_fn(state_flat, u_flat, t)
+            if self.specific_action_sampler is not None:
+                s3 = state_flat.reshape(M, K, -1)
+                s3 = self.specific_action_sampler.specific_dynamics(s3, state.reshape(M, K, -1), u, t)
+                state_flat = s3.reshape(MK, -1)
+            c = self._running_cost_fn(state_flat, u_flat, t).reshape(MK).to(self.dtype).contiguous()
+            _cabi.check(lib.mppi_cost_accumulate(cost_samples.data_ptr(), c.data_ptr(), cost_var.data_ptr(), M, K,
+                                                 float(self.rollout_var_discount) ** t, dt, stream), "mppi_cost_accumulate")
+            states[:, :, t] = state_flat.reshape(M, K, -1)[:, :, :self.nx]
+            actions[:, :, t] = u
+        if self.terminal_state_cost is not None:
+            cost_samples = cost_samples + self.terminal_state_cost(states, actions)
+        cost_total = cost_samples.mean(dim=0) + cost_var * self.rollout_var_cost
+        return cost_total.contiguous(), states, actions
+
+    # ------------------------------------------------------------------------------------------
+    # API-visible intermediates, materialised on demand (mppi.py:180-184, 383-385)
+    # ------------------------------------------------------------------------------------------
+    def _materialize(self, want_states=False):
+        if self.cost_total is None:
+            return False
+        key = "states" if want_states else "noise"
+        if self._materialized_at.get(key) == self._cmd_count:
+            return True
+        self._ensure_step_buffers()
+        p = self._p
+        stream = torch.cuda.current_stream(self.d).cuda_stream
+        nth = None if self._noise_theta_buf is None else self._noise_theta_buf.data_ptr()
+        st_ptr = None
+        if want_states:
+            self._states_buf = torch.empty(self._K_local, self.T, self.nx, device=self.d, dtype=self.dtype)
+            st_ptr = self._states_buf.data_ptr()
+        _cabi.check(self._lib.mppi_materialize(C.byref(p), self._pa_buf.data_ptr(), self._noise_buf.data_ptr(), nth,
+                                               st_ptr, stream), "mppi_materialize")
+        self._materialized_at["noise"] = self._cmd_count
+        if want_states:
+            self._materialized_at["states"] = self._cmd_count
+        return True
+
+    @property
+    def noise(self):
+        return self._noise_buf if self._materialize() else None
+
+    @property
+    def perturbed_action(self):
+        return self._pa_buf if self._materialize() else None
+
+    @property
+    def omega(self):
+        """mppi.py:258"""
+        if self.cost_total is None:
+            return None
+        if self._materialized_at.get("omega") != self._cmd_count:
+            self._omega_buf = torch.empty_like(self.cost_total)
+            stream = torch.cuda.current_stream(self.d).cuda_stream
+            _cabi.check(self._lib.mppi_omega(self.cost_total.data_ptr(), self._omega_buf.data_ptr(), self._stats.data_ptr(),
+                                             float(self._lambda), self._K_local, _DT[self.dtype], stream), "mppi_omega")
+            self._materialized_at["omega"] = self._cmd_count
+        return self._omega_buf
+
+    @property
+    def cost_total_non_zero(self):
+        """mppi.py:256: exp(-(c-beta)/lambda) = omega * eta"""
+        om = self.omega
+        return None if om is None else om * self._stats[1].to(self.dtype)
+
+    @property
+    def states(self):
+        """(1,K,T,nx) iff a terminal cost is set (mppi.py:307-310, test_mppi.py:241-260)"""
+        if self.cost_total is None or self.terminal_state_cost is None:
+            return None
+        if self._model is None:
+            return self._states
+        self._materialize(want_states=True)
+        return self._states_buf.unsqueeze(0)
+
+    @property
+    def actions(self):
+        if self.cost_total is None or self.terminal_state_cost is None:
+            return None
+        if self._model is None:
+            return self._actions
+        self._materialize()
+        return self._pa_buf.unsqueeze(0)          # (u_scale * pa) / u_scale, mppi.py:412
+
+    @property
+    def beta(self):
+        return None if self.cost_total is None else self._stats[0]
+
+    @property
+    def eta(self):
+        return None if self.cost_total is None else self._stats[1]
+
+    def get_rollouts(self, state, num_rollouts=1, U=None):
+        """mppi.py:425-448: open-loop replay of one control sequence through the dynamics plugin."""
+        state = torch.as_tensor(state).to(self.d, self.dtype).view(-1, self.nx)
+        if state.size(0) == 1:
+            state = state.expand(num_rollouts, -1)
+        if U is None:
+            U = self.get_action_sequence()
+        T = U.shape[0]
+        states = torch.zeros((num_rollouts, T + 1, self.nx), dtype=U.dtype, device=U.device)
+        states[:, 0] = state
+        for t in range(T):
+            nxt = self._dynamics_fn(states[:, t].view(num_rollouts, -1), self._u_scale * U[t].expand(num_rollouts, -1), t)
+            states[:, t + 1] = nxt[:, :self.nx]
+        return states[:, 1:]
+
+
+class SMPPI(MPPI):
+    """Smooth MPPI: noise is sampled on the control derivative, actions are its integral, and the
+    change between consecutive actions is penalised (mppi.py:451-570, arXiv:2112.09988)."""
+
+    _VARIANT = _cabi.VARIANT_SMPPI
+
+    def __init__(self, *args, w_action_seq_cost=1., delta_t=1., U_init=None, action_min=None, action_max=None, **kwargs):
+        self.w_action_seq_cost = w_action_seq_cost
+        self.delta_t = delta_t
+        self._Abuf = None
+        super().__init__(*args, U_init=U_init, **kwargs)
+        if action_min is not None and action_max is None:                                  # mppi.py:464-477
+            action_min = torch.as_tensor(action_min)
+            action_max = -action_min
+        if action_max is not None and action_min is None:
+            action_max = torch.as_tensor(action_max)
+            action_min = -action_max
+        if action_min is not None:
+            self.action_min = torch.as_tensor(action_min).to(self.d)
+            self.action_max = torch.as_tensor(action_max).to(self.d)
+        else:
+            self.action_min = torch.tensor(float("-inf"), device=self.d)
+            self.action_max = torch.tensor(float("inf"), device=self.d)
+        # the lifted formulation starts from zero controls (mppi.py:480-484)
+        if U_init is None:
+            self.action_sequence = torch.zeros_like(self.U)
+        else:
+            self.action_sequence = U_init
+        self.U = torch.zeros_like(self.U)
+        self._dirty = True
+
+    def _alloc_nominal(self, U_init):
+        super()._alloc_nominal(U_init)
+        old = self._Abuf
+        self._Abuf = torch.zeros_like(self._Ubuf)
+        if old is not None:
+            n = min(old.numel(), self._Abuf.numel())
+            self._Abuf[:n].copy_(old[:n])
+
+    @property
+    def action_sequence(self):
+        return self._Abuf[: self.T * self.nu].view(self.T, self.nu)
+
+    @action_sequence.setter
+    def action_sequence(self, value):
+        value = torch.as_tensor(value).to(self.d, self.dtype).reshape(-1, self.nu)
+        self._Abuf[: self.T * self.nu].copy_(value.reshape(-1))
+
+    def _variant_pack(self, p):
+        p.A = self._Abuf.data_ptr()
+        p.w_action_seq_cost = float(self.w_action_seq_cost)
+        p.delta_t = float(self.delta_t)
+        amin = _vec(self.action_min, self.nu, "action_min")
+        amax = _vec(self.action_max, self.nu, "action_max")
+        for i in range(self.nu):
+            p.action_min[i] = amin[i]
+            p.action_max[i] = amax[i]
+
+    def get_params(self):
+        return f"{super().get_params()} w={self.w_action_seq_cost} t={self.delta_t}"
+
+    def shift_nominal_trajectory(self):
+        """mppi.py:489-493"""
+        super().shift_nominal_trajectory()
+        A = torch.roll(self.action_sequence, -1, dims=0)
+        A[-1] = A[-2]
+        self.action_sequence = A
+
+    def get_action_sequence(self):
+        return self.action_sequence
+
+    def reset(self):
+        """mppi.py:498-500"""
+        self._Ubuf.zero_()
+        self._Abuf.zero_()
+
+    def change_horizon(self, horizon):
+        """mppi.py:502-512"""
+        U = self.U.clone()
+        A = self.action_sequence.clone()
+        if horizon < U.shape[0]:
+            U, A = U[:horizon], A[:horizon]
+        elif horizon > U.shape[0]:
+            ext = horizon - U.shape[0]
+            U = torch.cat((U, self._u_init.repeat(ext, 1)))
+            A = torch.cat((A, A[-1].repeat(ext, 1)))
+        self._Abuf = None
+        self._resize_horizon(horizon, U)
+        self.action_sequence = A
+
+    @property
+    def perturbed_control(self):
+        """mppi.py:546 (clamped, unused by the algorithm itself): U + coloured noise, bounded."""
+        n = self.noise
+        if n is None:
+            return None
+        tn = self.T * self.nu
+        Uu = self._nominal_used[:tn].view(self.T, self.nu)
+        return torch.clamp(Uu + n, self._u_min, self._u_max)
+
+
+class TimeKernel:
+    """Kernel acting on the time dimension of trajectories (mppi.py:573-577)."""
+
+    def __call__(self, t, tk):
+        raise NotImplementedError
+
+
+class RBFKernel(TimeKernel):
+    """mppi.py:580-590"""
+
+    def __init__(self, sigma=1):
+        self.sigma = sigma
+
+    def __repr__(self):
+        return f"RBFKernel(sigma={self.sigma})"
+
+    def __call__(self, t, tk):
+        d = torch.sum((t[:, None] - tk) ** 2, dim=-1)
+        return torch.exp(-d / (1e-8 + 2 * self.sigma ** 2))
+
+
+class KMPPI(MPPI):
+    """MPPI with kernel interpolation of control points for smoothing (mppi.py:593-688).
+
+    The reference solves a (S x S) system per sample through torch.vmap; the interpolation operator
+    ``W = k(Hs,Tk) k(Tk,Tk)^-1`` is sample-independent, so it is computed once here and staged in
+    shared memory by the kernel."""
+
+    _VARIANT = _cabi.VARIANT_KMPPI
+
+    def __init__(self, *args, num_support_pts=None, kernel: TimeKernel = RBFKernel(), **kwargs):
+        self.num_support_pts = None
+        self.interpolation_kernel = kernel
+        self._theta = None
+        super().__init__(*args, **kwargs)
+        self.num_support_pts = int(num_support_pts or self.T // 2)                         # mppi.py:598
+        self._theta = torch.zeros((self.num_support_pts, self.nu), dtype=self.dtype, device=self.d)
+        self.prepare_vmap_interpolation()
+        self._alloc_results()
+        self._dirty = True
+
+    @property
+    def theta(self):
+        return self._theta
+
+    @theta.setter
+    def theta(self, v):
+        self._theta.copy_(torch.as_tensor(v).to(self.d, self.dtype).reshape(self.num_support_pts, self.nu))
+
+    def _noise_rows(self):
+        S = self.num_support_pts if self.num_support_pts else self.T
+        return S * self.nu
+
+    def get_params(self):
+        return f"{super().get_params()} num_support_pts={self.num_support_pts} kernel={self.interpolation_kernel}"
+
+    def prepare_vmap_interpolation(self):
+        """mppi.py:636-648 reduced to its sample-independent content: Tk, Hs and the two operators."""
+        S, T = self.num_support_pts, self.T
+        self.Tk = torch.linspace(0, T - 1, int(S), device=self.d, dtype=self.dtype).unsqueeze(0)
+        self.Hs = torch.linspace(0, T - 1, int(T), device=self.d, dtype=self.dtype).unsqueeze(0)
+        tk = self.Tk[0]
+        G = self.interpolation_kernel(tk.unsqueeze(-1), tk.unsqueeze(-1))
+        self._W = torch.linalg.solve(G, self.interpolation_kernel(self.Hs[0].unsqueeze(-1), tk.unsqueeze(-1)), left=False).contiguous()
+        self._Wshift = torch.linalg.solve(G, self.interpolation_kernel((tk + 1).unsqueeze(-1), tk.unsqueeze(-1)), left=False).contiguous()
+
+    def do_kernel_interpolation(self, t, tk, c):
+        """mppi.py:621-627"""
+        K = self.interpolation_kernel(t.unsqueeze(-1), tk.unsqueeze(-1))
+        Ktktk = self.interpolation_kernel(tk.unsqueeze(-1), tk.unsqueeze(-1))
+        KK = torch.linalg.solve(Ktktk, K, left=False)
+        return torch.matmul(KK, c), K
+
+    def deparameterize_to_trajectory_single(self, theta):
+        return self.do_kernel_interpolation(self.Hs[0], self.Tk[0], theta)
+
+    def deparameterize_to_trajectory_batch(self, theta):
+        assert theta.shape == (self.K, self.num_support_pts, self.nu)
+        return torch.matmul(self._W, theta), None
+
+    def _variant_pack(self, p):
+        p.S = self.num_support_pts
+        p.theta = self._theta.data_ptr()
+        p.W = self._W.data_ptr()
+        p.Wshift = self._Wshift.data_ptr()
+
+    def reset(self):
+        """mppi.py:613-615"""
+        super().reset()
+        self._theta.zero_()
+
+    def shift_nominal_trajectory(self):
+        """mppi.py:617-619"""
+        super().shift_nominal_trajectory()
+        self._theta.copy_(self._Wshift @ self._theta)
+
+    def _ensure_step_buffers(self):
+        super()._ensure_step_buffers()
+        shape = (self._K_local, self.num_support_pts, self.nu)
+        if self._noise_theta_buf is None or self._noise_theta_buf.shape != shape:
+            self._noise_theta_buf = torch.empty(*shape, device=self.d, dtype=self.dtype)
+
+    def _eps_for_update(self):
+        return self._noise_theta_buf
+
+    @property
+    def noise_theta(self):
+        return self._noise_theta_buf if self._materialize() else None
+
+
+def run_mppi(mppi, env, retrain_dynamics, retrain_after_iter=50, iter=1000, render=True):
+    """Closed-loop driver with the reference's signature (mppi.py:876-898): command -> env.step ->
+    log (state, action) rows, calling `retrain_dynamics(dataset)` every `retrain_after_iter` steps.
+    Host glue only; nothing here is on the measured path."""
+    width = mppi.nx + mppi.nu
+    dataset = torch.zeros((retrain_after_iter, width), dtype=mppi.dtype, device=mppi.d)
+    total_reward = 0
+    for step in range(iter):
+        obs = env.unwrapped.state.copy()
+        t0 = time.perf_counter()
+        action = mppi.command(obs)
+        dt_cmd = time.perf_counter() - t0
+        out = env.step(action.cpu().numpy())
+        reward = out[1]
+        total_reward += reward
+        logger.debug("step %d: cost %.4f, command() %.5fs", step, -reward, dt_cmd)
+        if render:
+            env.render()
+        row = step % retrain_after_iter
+        if row == 0 and step > 0:
+            retrain_dynamics(dataset)
+            dataset.zero_()
+        dataset[row, :mppi.nx] = torch.as_tensor(obs, dtype=mppi.dtype)
+        dataset[row, mppi.nx:] = action
+    return total_reward, dataset

@@ -1,0 +1,140 @@
+"""CPU: host-side logic — model registry resolution, torch model definitions vs the oracle,
+K-sharding arithmetic, cross-rank combination (incl. a world_size-2 gloo run), Philox oracle KATs."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_mppi_b200 as eng
+from oracle import mppi_oracle as orc
+from oracle import philox_oracle as po
+from pytorch_mppi_b200.distributed import combine_partials, shard_bounds
+from pytorch_mppi_b200.models import resolve_fused_model
+
+
+def test_registry_resolution():
+    pend = eng.Pendulum()
+    assert resolve_fused_model(pend.dynamics, pend.running_cost, None) is pend
+    assert resolve_fused_model(lambda s, a: pend.dynamics(s, a), pend.running_cost, None) is None
+    other = eng.Pendulum()
+    assert resolve_fused_model(pend.dynamics, other.running_cost, None) is None
+    nav = eng.LinearPoint.toy2d_nav()
+    assert resolve_fused_model(nav.dynamics, nav.running_cost, nav.terminal_cost) is nav
+    assert resolve_fused_model(nav.dynamics, nav.running_cost, None) is None          # terminal term would differ
+    lin = eng.LinearPoint.unit_test_env()
+    assert resolve_fused_model(lin.dynamics, lin.running_cost, None) is lin
+    assert resolve_fused_model(lin.dynamics, lin.running_cost, lambda s, a: 0) is None
+    assert len(nav.param_blob()) <= 48 and len(pend.param_blob()) == 7
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_torch_models_equal_oracle_models(dtype):
+    g = torch.Generator().manual_seed(0)
+    s = torch.randn(64, 2, generator=g, dtype=dtype) * 2
+    a1 = torch.randn(64, 1, generator=g, dtype=dtype) * 3
+    a2 = torch.randn(64, 2, generator=g, dtype=dtype)
+    pe, po_ = eng.Pendulum(), orc.PendulumModel(numpy_sin=False)
+    assert torch.equal(pe.dynamics(s, a1), po_.dynamics(s, a1))
+    assert torch.equal(pe.running_cost(s, a1), po_.running_cost(s, a1))
+    ne = eng.LinearPoint.toy2d_nav()
+    no = orc.LinearPointModel(B=ne.B, goal=ne.goal, R=ne.R, hills=ne.hills, terminal_scale=10.0, dtype=dtype)
+    assert torch.equal(ne.dynamics(s, a2), no.dynamics(s, a2))
+    assert torch.allclose(ne.running_cost(s, a2), no.running_cost(s, a2), rtol=1e-6)
+    st = s.view(1, 8, 8, 2)
+    assert torch.allclose(ne.terminal_cost(st, None), no.terminal_cost(st, None), rtol=1e-6)
+
+
+def test_shard_bounds_partition_exactly():
+    for K in (8, 100, 16384, 2 ** 20, 1000003):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(K, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == K
+            for (o0, n0), (o1, _) in zip(spans, spans[1:]):
+                assert o0 + n0 == o1
+    with pytest.raises(ValueError):
+        shard_bounds(2, 3, 4)
+
+
+def test_combine_partials_equals_unsharded_softmin():
+    g = torch.Generator().manual_seed(1)
+    K, R, lam = 1000, 12, 0.7
+    cost = torch.rand(K, generator=g, dtype=torch.float64) * 50
+    eps = torch.randn(K, R, generator=g, dtype=torch.float64)
+    beta, w, eta, omega = orc.softmin_weights(cost, lam)
+    want = (omega[:, None] * eps).sum(0)
+    recs = []
+    for r in range(4):
+        o, n = shard_bounds(K, r, 4)
+        c, e = cost[o:o + n], eps[o:o + n]
+        b = c.min()
+        ww = torch.exp(-(c - b) / lam)
+        recs.append(torch.cat([b.view(1), ww.sum().view(1), (ww[:, None] * e).sum(0)]))
+    b2, eta2, delta = combine_partials(torch.stack(recs), lam)
+    assert torch.allclose(delta, want, atol=1e-12) and abs(b2 - beta) < 1e-15 and abs(eta2 - eta) < 1e-9
+
+
+def _gloo_worker(rank, world, port, K, R, lam, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    cost = torch.rand(K, generator=g, dtype=torch.float64) * 30
+    eps = torch.randn(K, R, generator=g, dtype=torch.float64)
+    o, n = shard_bounds(K, rank, world)
+    c, e = cost[o:o + n], eps[o:o + n]
+    b = c.min()
+    w = torch.exp(-(c - b) / lam)
+    rec = torch.cat([b.view(1), w.sum().view(1), (w[:, None] * e).sum(0)])
+    gathered = torch.zeros(world * (R + 2), dtype=torch.float64)
+    dist.all_gather_into_tensor(gathered, rec)                # the collective the nccl route issues
+    _, _, delta = combine_partials(gathered.view(world, R + 2), lam)
+    _, _, _, omega = orc.softmin_weights(cost, lam)
+    want = (omega[:, None] * eps).sum(0)
+    out[rank] = float((delta - want).abs().max())
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_exchange_matches_single_process():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, 999, 10, 1.3, out), nprocs=2, join=True)
+    assert len(out) == 2 and max(out.values()) < 1e-12
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors: philox4x32_10
+    v = po.philox4x32_10(np.zeros((1, 4), dtype=np.uint32), (0, 0))[0]
+    assert [int(x) for x in v] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    v = po.philox4x32_10(np.full((1, 4), 0xFFFFFFFF, dtype=np.uint32), (0xFFFFFFFF, 0xFFFFFFFF))[0]
+    assert [int(x) for x in v] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    v = po.philox4x32_10(np.array([[0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344]], dtype=np.uint32), (0xa4093822, 0x299f31d0))[0]
+    assert [int(x) for x in v] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_normals_shard_invariant_and_gaussian():
+    full = po.normals(99, 5, 0, 4096, 30, np.float32)
+    part = po.normals(99, 5, 1024, 512, 30, np.float32)
+    assert np.array_equal(full[1024:1536], part)             # keyed by the global sample index
+    assert abs(full.mean()) < 0.01 and abs(full.std() - 1) < 0.01
+    d = po.normals(99, 5, 0, 4096, 7, np.float64)
+    assert d.shape == (4096, 7) and abs(d.std() - 1) < 0.02
+
+
+def test_kernel_matrices_identities():
+    # W theta interpolates: at support times the interpolation reproduces theta (SURVEY.md App. A probe)
+    T, S = 20, 5
+    W, Wsh = orc.kernel_matrices(T, S, lambda a, b: orc.rbf_kernel(a, b, 2.0), torch.float64)
+    assert W.shape == (T, S) and Wsh.shape == (S, S)
+    Tk = torch.linspace(0, T - 1, S)
+    idx = [int(round(float(t))) for t in Tk if abs(float(t) - round(float(t))) < 1e-9]
+    theta = torch.randn(S, 2, dtype=torch.float64)
+    full = W @ theta
+    for s, t in enumerate(Tk):
+        if abs(float(t) - round(float(t))) < 1e-9:
+            assert torch.allclose(full[int(round(float(t)))], theta[s], atol=1e-9)
+    assert len(idx) >= 2
