@@ -90,9 +90,9 @@ typedef struct MppiFusedParams {
     int32_t S;                   /* KMPPI: number of support points (else 0)                            */
     int32_t u_per_command;       /* rows of the action sequence copied to action_out                    */
     uint32_t flags;              /* MPPI_FLAG_*                                                         */
-    int32_t block_threads;       /* 0 = library default                                                 */
+    int32_t block_threads;       /* samples per CTA tile (multiple of 32, <= 512); 0 = library default  */
     int32_t grid_blocks;         /* 0 = library default (<= SMs * resident CTAs)                        */
-    int32_t _pad0;
+    int32_t threads_per_sample;  /* 1/2/4 threads share one sample's sampling work; 0 = library default */
     int64_t k_offset;            /* global index of this rank's first sample (keys the RNG, null action)*/
     uint64_t seed, offset;       /* Philox4x32-10 key / counter base (see oracle/philox_oracle.py)      */
     double lambda_;              /* temperature                                                         */
@@ -135,7 +135,7 @@ typedef struct MppiLaunchInfo {
     int32_t max_blocks_per_sm, sm_count;
     uint64_t workspace_bytes;    /* minimum workspace for these dimensions                               */
     int32_t tma_staging;         /* 1 if the nominal sequence is staged with cp.async.bulk (TMA)         */
-    int32_t _pad;
+    int32_t threads_per_sample;
 } MppiLaunchInfo;
 
 int mppi_b200_abi_version(void);

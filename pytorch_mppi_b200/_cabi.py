@@ -51,7 +51,7 @@ class MppiFusedParams(C.Structure):
         ("flags", C.c_uint32),
         ("block_threads", C.c_int32),
         ("grid_blocks", C.c_int32),
-        ("_pad0", C.c_int32),
+        ("threads_per_sample", C.c_int32),
         ("k_offset", C.c_int64),
         ("seed", C.c_uint64),
         ("offset", C.c_uint64),
@@ -101,7 +101,7 @@ class MppiLaunchInfo(C.Structure):
         ("sm_count", C.c_int32),
         ("workspace_bytes", C.c_uint64),
         ("tma_staging", C.c_int32),
-        ("_pad", C.c_int32),
+        ("threads_per_sample", C.c_int32),
     ]
 
 

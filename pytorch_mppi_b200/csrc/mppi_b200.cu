@@ -84,7 +84,7 @@ inline uint64_t ws_bytes(int nb, int R, int es) {
     return 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
 }
 
-template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BD, int nb) {
+template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BS, int nb, int tps = 1) {
     memset(&a, 0, sizeof(a));
     fill_noise_model<real>(p, a.nm);
     for (int i = 0; i < MPPI_MAX_NU; ++i) a.u_init[i] = (real)p->u_init[i];
@@ -108,7 +108,8 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     a.R = rows_of(p);
     a.TN = p->T * p->nu;
     a.upc = p->u_per_command;
-    a.n_tiles = (p->K + BD - 1) / BD;
+    a.n_tiles = (p->K + BS - 1) / BS;
+    a.tps = tps;
     a.k_offset = p->k_offset;
     a.seed = p->seed;
     a.offset = p->offset;
@@ -139,16 +140,28 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     return MPPI_OK;
 }
 
+template <typename... Args>
+int launch_kernel(void (*kernel)(Args...), int nb, int BD, int smem, cudaStream_t stream, Args... args) {
+    void* argv[] = {(void*)&args...};
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(nb), dim3(BD), argv, (size_t)smem, stream);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "launch grid=%d block=%d smem=%d: %s (%s)", nb, BD, smem,
+                 cudaGetErrorName(e), cudaGetErrorString(e));
+        return MPPI_ERR_CUDA;
+    }
+    return MPPI_OK;
+}
+
 struct Geometry {
-    int BD, nb, smem, occ, regs;
+    int BD, BS, tps, nb, smem, occ, regs;   // BD = BS * tps threads per CTA, BS samples per tile
 };
 
 struct GeomKey {
     const void* kernel;
-    int dev, variant, K, T, nu, S, bt, gb, r2, single;
+    int dev, variant, K, T, nu, S, bt, tp, gb, r2, single;
     bool operator==(const GeomKey& o) const {
         return kernel == o.kernel && dev == o.dev && variant == o.variant && K == o.K && T == o.T && nu == o.nu && S == o.S &&
-               bt == o.bt && gb == o.gb && r2 == o.r2 && single == o.single;
+               bt == o.bt && tp == o.tp && gb == o.gb && r2 == o.r2 && single == o.single;
     }
 };
 
@@ -156,14 +169,14 @@ struct GeomKey {
 // the last few results are cached per thread: a steady-state command() pays only the lookup.
 template <typename KernelT>
 int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_rows2, bool single_partial_grid, Geometry& g,
-                  SmemLayout (*layout)(int, int, int, int, int, int, int, int)) {
+                  SmemLayout (*layout)(int, int, int, int, int, int, int, int, int)) {
     static thread_local GeomKey keys[8];
     static thread_local Geometry vals[8];
     static thread_local int n_cached = 0, next_slot = 0;
     int dev = 0;
     CK(cudaGetDevice(&dev));
-    const GeomKey key{(const void*)kernel, dev, p->variant, p->K, p->T, p->nu, p->S, p->block_threads, p->grid_blocks,
-                      need_rows2, single_partial_grid ? 1 : 0};
+    const GeomKey key{(const void*)kernel, dev, p->variant, p->K, p->T, p->nu, p->S, p->block_threads, p->threads_per_sample,
+                      p->grid_blocks, need_rows2, single_partial_grid ? 1 : 0};
     for (int i = 0; i < n_cached; ++i)
         if (keys[i] == key) {
             g = vals[i];
@@ -173,23 +186,36 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     int rc = get_dev_info(di);
     if (rc) return rc;
     const int R = rows_of(p);
-    int BD = p->block_threads;
-    if (BD <= 0) BD = (p->K <= di.sm_count * 128 * 2) ? 128 : 256;
-    if (BD % 32 != 0 || BD < 32 || BD > 512) return MPPI_ERR_BAD_ARG;
-    const int n_tiles = (p->K + BD - 1) / BD;
+    // BS samples per tile; tps threads share one sample's sampling/transform work.  Small problems
+    // (fewer tiles than SMs) cannot fill the machine with one thread per sample, so they get
+    // 4 (or 2) threads per sample; large ones already have the thread-level parallelism.
+    int BS = p->block_threads;
+    if (BS <= 0) BS = (p->K <= di.sm_count * 128 * 2) ? 128 : 256;
+    if (BS % 32 != 0 || BS < 32 || BS > 512) return MPPI_ERR_BAD_ARG;
+    const int n_tiles = (p->K + BS - 1) / BS;
+    int tps = p->threads_per_sample;
+    if (tps <= 0) tps = (n_tiles <= di.sm_count) ? 4 : (n_tiles <= 2 * di.sm_count ? 2 : 1);
+    while (tps > 1 && BS * tps > 512) tps >>= 1;
+    if (tps != 1 && tps != 2 && tps != 4) return MPPI_ERR_BAD_ARG;
+    const int BD = BS * tps;
     const int cap = di.sm_count * 16;
-    SmemLayout L = layout(p->variant, p->T, p->nu, p->S, R, BD, single_partial_grid ? 1 : cap, need_rows2);
-    if (L.total > di.max_smem_optin) return MPPI_ERR_UNSUPPORTED;
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    SmemLayout L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : cap, need_rows2);
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kernel));
+    const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;   // static + dynamic <= opt-in maximum
+    if (L.total > dyn_limit) return MPPI_ERR_UNSUPPORTED;
+    // The attribute is a per-kernel LIMIT (setting a smaller value later lowers it), so raise it
+    // once to the device maximum; the carve-out actually used follows each launch's request.
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
     if (occ < 1) return MPPI_ERR_UNSUPPORTED;
     int nb = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
     if (nb > cap) nb = cap;
     if (p->grid_blocks > 0 && p->grid_blocks < nb) nb = p->grid_blocks;
-    L = layout(p->variant, p->T, p->nu, p->S, R, BD, single_partial_grid ? 1 : nb, need_rows2);
-    cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, kernel));
+    L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : nb, need_rows2);
+    g.BS = BS;
+    g.tps = tps;
     g.BD = BD;
     g.nb = nb;
     g.smem = L.total;
@@ -203,8 +229,8 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     return MPPI_OK;
 }
 
-template <typename real> SmemLayout layout_fn(int v, int T, int nu, int S, int R, int BD, int nb, int r2) {
-    return make_layout<real>(v, T, nu, S, R, BD, nb, r2);
+template <typename real> SmemLayout layout_fn(int v, int T, int nu, int S, int R, int BD, int BS, int nb, int r2) {
+    return make_layout<real>(v, T, nu, S, R, BD, BS, nb, r2);
 }
 
 // ---- fused command ----------------------------------------------------------------------------
@@ -217,11 +243,12 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (rc) return rc;
     const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
     KArgs<real> a;
-    fill_kargs<real>(p, a, g.BD, g.nb);
+    fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
     if (info != nullptr) {
         DevInfo di;
         get_dev_info(di);
         info->block_threads = g.BD;
+        info->threads_per_sample = g.tps;
         info->grid_blocks = g.nb;
         info->smem_bytes = g.smem;
         info->regs_per_thread = g.regs;
@@ -240,9 +267,7 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params);
-    kernel<<<g.nb, g.BD, g.smem, stream>>>(a, mp);
-    CK(cudaGetLastError());
-    return MPPI_OK;
+    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a, mp);
 }
 
 template <class Model, typename real>
@@ -277,7 +302,7 @@ int run_sample(const MppiFusedParams* p, KArgs<real>& a_extra, cudaStream_t stre
     int rc = plan_geometry(kernel, p, (int)sizeof(real), V == V_KMPPI, true, g, layout_fn<real>);
     if (rc) return rc;
     KArgs<real> a;
-    fill_kargs<real>(p, a, g.BD, g.nb);
+    fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
     a.out_pa = a_extra.out_pa;
     a.out_noise = a_extra.out_noise;
     a.out_noise_theta = a_extra.out_noise_theta;
@@ -293,9 +318,7 @@ int run_sample(const MppiFusedParams* p, KArgs<real>& a_extra, cudaStream_t stre
         a.tma_ok = 0;
         a.nominal_used = nullptr;
     }
-    kernel<<<g.nb, g.BD, g.smem, stream>>>(a);
-    CK(cudaGetLastError());
-    return MPPI_OK;
+    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a);
 }
 
 template <typename real, int V> int run_sample_nu(const MppiFusedParams* p, KArgs<real>& e, cudaStream_t s) {
@@ -337,13 +360,11 @@ int run_softmin(const MppiFusedParams* p, const void* cost, const void* eps, cud
     if (rc) return rc;
     if (p->workspace == nullptr || p->workspace_bytes < ws_bytes(g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
     KArgs<real> a;
-    fill_kargs<real>(p, a, g.BD, g.nb);
+    fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
     a.in_cost = (const real*)cost;
     a.in_eps = (const real*)eps;
     if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
-    kernel<<<g.nb, g.BD, g.smem, stream>>>(a);
-    CK(cudaGetLastError());
-    return MPPI_OK;
+    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a);
 }
 
 template <typename real, int V> int run_softmin_nu(const MppiFusedParams* p, const void* c, const void* e, cudaStream_t s) {

@@ -58,6 +58,7 @@ template <typename real> struct KArgs {
     long long k_offset;
     unsigned long long seed, offset;
     int shift, null_action, tma_ok, state_per_sample;
+    int tps;   // threads cooperating on one sample's sampling/transform phases (1, 2 or 4)
     // generic-path extras (sample_kernel / softmin_update_kernel)
     real* out_pa;
     real* out_noise;
@@ -80,8 +81,9 @@ struct SmemLayout {
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
 // rows2 (a second TN-row tile) is only used by sample_kernel for KMPPI
+// BD = threads per CTA, BS = samples per tile (BD / threads-per-sample)
 template <typename real>
-__host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int nb, int need_rows2) {
+__host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int BS, int nb, int need_rows2) {
     SmemLayout L;
     const int es = (int)sizeof(real);
     const int TN = T * nu, SN = S * nu, nw = BD / 32;
@@ -95,10 +97,10 @@ __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, in
     L.off_w = o; o = align_up(o + (variant == V_KMPPI ? T * S : 0) * es, 16);
     L.off_wsh = o; o = align_up(o + (variant == V_KMPPI ? S * S : 0) * es, 16);
     L.off_vrun = o; o = align_up(o + R * es, 16);
-    L.off_ws = o; o = align_up(o + BD * es, 16);
+    L.off_ws = o; o = align_up(o + BS * es, 16);
     L.off_red = o; o = align_up(o + 64 * es, 16);
     L.off_part = o; o = align_up(o + nw * R * es, 16);
-    L.LD = BD + 1;
+    L.LD = BS + 1;
     L.off_rows = o; o = align_up(o + R * L.LD * es, 16);
     L.off_rows2 = o; o = align_up(o + (need_rows2 ? TN * L.LD : 0) * es, 16);
     L.off_ss = o; o = align_up(o + nb * es, 16);
@@ -260,11 +262,14 @@ __device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
 }
 
 // ---- stage A: standard normals into the tile ------------------------------------------------------
+// (thread -> sample s = tid % BS, chunk lane g = tid / BS: the tps threads of a sample split its
+// Philox chunks)
 template <typename real>
 __device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, bool active, unsigned long long kg, int nvalid) {
     const int tid = threadIdx.x, BD = blockDim.x, R = a.R, LD = sm.LD;
+    const int BS = BD / a.tps, s_ = tid % BS, g_ = tid / BS;
     if (a.z != nullptr) {
-        const size_t base = (size_t)tile * BD * R;
+        const size_t base = (size_t)tile * BS * R;
         const int count = nvalid * R;
         for (int e = tid; e < count; e += BD) {
             const int s = e / R, j = e - s * R;
@@ -273,8 +278,8 @@ __device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, boo
         __syncthreads();
     } else if (active) {
         constexpr int PER = Normals<real>::PER_CALL;
-        real* col = sm.rows + tid;
-        for (int c = 0; c * PER < R; ++c) {
+        real* col = sm.rows + s_;
+        for (int c = g_; c * PER < R; c += a.tps) {
             real tmp[PER];
             Normals<real>::draw(a.seed, kg, a.offset + (unsigned long long)c, tmp);
 #pragma unroll
@@ -284,7 +289,7 @@ __device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, boo
     }
     if (a.z_out != nullptr) {
         __syncthreads();
-        const size_t base = (size_t)tile * BD * R;
+        const size_t base = (size_t)tile * BS * R;
         const int count = nvalid * R;
         for (int e = tid; e < count; e += BD) {
             const int s = e / R, j = e - s * R;
@@ -312,9 +317,10 @@ __device__ __forceinline__ void transform_column(const KArgs<real>& a, Smem<real
     typedef Ops<real> O;
     const NoiseModel<real>& nm = a.nm;
     const int LD = sm.LD;
-    real* col = sm.rows + threadIdx.x;
+    const int BS = blockDim.x / a.tps, s_ = threadIdx.x % BS, g_ = threadIdx.x / BS;
+    real* col = sm.rows + s_;
     if (VARIANT == V_KMPPI) {
-        for (int s = 0; s < a.S; ++s) {                                                   // mppi.py:660-664
+        for (int s = g_; s < a.S; s += a.tps) {                                           // mppi.py:660-664
             real zr[NU], e[NU];
 #pragma unroll
             for (int n = 0; n < NU; ++n) zr[n] = col[(s * NU + n) * LD];
@@ -324,7 +330,7 @@ __device__ __forceinline__ void transform_column(const KArgs<real>& a, Smem<real
                 col[(s * NU + n) * LD] = clamp<real>(O::add(sm.ths[s * NU + n], e[n]), nm.u_min[n], nm.u_max[n]);
         }
     } else {
-        for (int t = 0; t < a.T; ++t) {
+        for (int t = g_; t < a.T; t += a.tps) {
             real zr[NU], e[NU];
 #pragma unroll
             for (int n = 0; n < NU; ++n) zr[n] = col[(t * NU + n) * LD];
@@ -351,7 +357,7 @@ template <typename real, int VARIANT, int NU>
 __device__ __forceinline__ void action_at(const KArgs<real>& a, const Smem<real>& sm, unsigned long long kg, int t, real* v) {
     typedef Ops<real> O;
     const int LD = sm.LD;
-    const real* col = sm.rows + threadIdx.x;
+    const real* col = sm.rows + (threadIdx.x % (blockDim.x / a.tps));
     if (VARIANT == V_KMPPI) {
         const int S = a.S;
 #pragma unroll
@@ -395,32 +401,36 @@ template <typename real, int VARIANT, bool EPS_DIRECT>
 __device__ void fold_tile(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool active, int nvalid, real& beta_run,
                           real& eta_run, real& w_out) {
     typedef Ops<real> O;
-    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
+    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int BS = BD / a.tps, ng = BS >> 5;          // sample groups of 32 in the tile
     const int R = a.R, LD = sm.LD;
     const real nfl = a.nm.neg_inv_lambda;
+    // only the rollout threads (tid < BS) carry a cost; the helper threads contribute +inf / 0
     const real tile_min = block_min<real>(c_tot, sm.red);
     const real beta_new = tile_min < beta_run ? tile_min : beta_run;
     const real w = active ? O::exp_(nfl * (c_tot - beta_new)) : (real)0;                  // mppi.py:12-13, 256
     const real resc = (beta_run == O::inf()) ? (real)0 : O::exp_(nfl * (beta_run - beta_new));
-    sm.w_s[tid] = w;
+    if (tid < BS) sm.w_s[tid] = w;
     w_out = w;
     const real eta_tile = block_sum<real>(w, sm.red);   // (its barriers also publish w_s)
-    for (int j = lane; j < R; j += 32) {
+    // warp -> (sample group gi, row slice ri): every (gi, j) is produced by exactly one warp
+    const int gi = warp % ng, ri = warp / ng;
+    for (int j = lane + 32 * ri; j < R; j += 32 * a.tps) {
         const real us = (VARIANT == V_KMPPI || EPS_DIRECT) ? (real)0 : sm.Us[j];
         const real a2 = EPS_DIRECT ? (real)0 : (VARIANT == V_SMPPI ? sm.As[j] : (VARIANT == V_KMPPI ? sm.ths[j] : (real)0));
         real acc = (real)0;
-        const int i0 = warp * 32;
+        const int i0 = gi * 32;
         const int i1 = min(i0 + 32, nvalid);
         for (int i = i0; i < i1; ++i) {
             const real val = sm.rows[j * LD + i];
             acc += sm.w_s[i] * (EPS_DIRECT ? val : eps_of<real, VARIANT>(a.nm, val, us, a2));   // mppi.py:268
         }
-        sm.part[warp * R + j] = acc;
+        sm.part[gi * R + j] = acc;
     }
     __syncthreads();
     for (int j = tid; j < R; j += BD) {
         real s = sm.part[j];
-        for (int q = 1; q < nw; ++q) s += sm.part[q * R + j];
+        for (int q = 1; q < ng; ++q) s += sm.part[q * R + j];
         sm.Vrun[j] = sm.Vrun[j] * resc + s;
     }
     eta_run = eta_run * resc + eta_tile;
@@ -563,26 +573,37 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
     if (!s_is_last) return;
     __threadfence();
 
+    // The partials were written by other SMs before their ticket increments; this CTA has not
+    // touched those lines during this launch, and __ldcg reads them from L2.  Loads are issued in
+    // batches of 8 so their ~300-cycle L2 latencies overlap instead of serialising.
     const int nb = gridDim.x;
-    const volatile real* betaP = a.betaP;
-    const volatile real* etaP = a.etaP;
-    const volatile real* VP = a.VP;
+    const real* betaP = a.betaP;
+    const real* etaP = a.etaP;
+    const real* VP = a.VP;
     real bmin = O::inf();
     for (int q = tid; q < nb; q += BD) {
-        const real bq = betaP[q];
+        const real bq = __ldcg(betaP + q);
         bmin = bq < bmin ? bq : bmin;
     }
     const real beta = block_min<real>(bmin, sm.red);
     double eta_loc = 0.0;
     for (int q = tid; q < nb; q += BD) {
-        const real s = O::exp_(nfl * (betaP[q] - beta));
+        const real s = O::exp_(nfl * (__ldcg(betaP + q) - beta));
         sm.sS[q] = s;
-        eta_loc += (double)s * (double)etaP[q];
+        eta_loc += (double)s * (double)__ldcg(etaP + q);
     }
     const double eta = block_sum<double>(eta_loc, sm.redd);   // barriers also publish sS
     for (int j = lane; j < R; j += 32) {
         double acc = 0.0;
-        for (int q = warp; q < nb; q += nw) acc += (double)sm.sS[q] * (double)VP[(size_t)q * R + j];
+        int q = warp;
+        for (; q + 7 * nw < nb; q += 8 * nw) {
+            real v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(VP + (size_t)(q + u * nw) * R + j);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += (double)sm.sS[q + u * nw] * (double)v[u];
+        }
+        for (; q < nb; q += nw) acc += (double)sm.sS[q] * (double)__ldcg(VP + (size_t)q * R + j);
         sm.part2[warp * R + j] = acc;
     }
     __syncthreads();
@@ -633,7 +654,8 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
     constexpr int NX = Model::NX, NU = Model::NU;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, BD = blockDim.x;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, gridDim.x, 0);
+    const int BS = BD / a.tps;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, 0);
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
@@ -642,16 +664,19 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
 
     real beta_run = O::inf(), eta_run = (real)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int k = tile * BD + tid;
-        const bool active = k < a.K;
-        const int nvalid = min(BD, a.K - tile * BD);
+        const int k = tile * BS + (tid % BS);
+        const bool in_range = k < a.K;
+        const bool active = in_range && tid < BS;      // the rollout thread of sample k
+        const int nvalid = min(BS, a.K - tile * BS);
         const unsigned long long kg = (unsigned long long)(a.k_offset + k);
 
-        fill_normals<real>(a, sm, tile, active, kg, nvalid);
+        fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
+        if (a.tps > 1) __syncthreads();
+        if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
+        if (a.tps > 1) __syncthreads();
 
         real c_tot = O::inf();
         if (active) {
-            transform_column<real, VARIANT, NU>(a, sm, kg);
 
             // C. rollout (mppi.py:297-332) + action cost (mppi.py:409,415) [+ smoothness :559-562]
             real x[NX];
@@ -667,6 +692,7 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
             real vprev[NU];
 #pragma unroll
             for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
+#pragma unroll 2
             for (int t = 0; t < T; ++t) {
                 real v[NU], u[NU], eps[NU];
                 action_at<real, VARIANT, NU>(a, sm, kg, t, v);
@@ -708,7 +734,8 @@ __global__ void __launch_bounds__(512) sample_kernel(const KArgs<real> a) {
     typedef Ops<real> O;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, BD = blockDim.x;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, 1, VARIANT == V_KMPPI);
+    const int BS = BD / a.tps;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1, VARIANT == V_KMPPI);
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T, R = a.R, TN = a.TN, LD = sm.LD;
@@ -724,13 +751,16 @@ __global__ void __launch_bounds__(512) sample_kernel(const KArgs<real> a) {
     }
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int k = tile * BD + tid;
-        const bool active = k < a.K;
-        const int nvalid = min(BD, a.K - tile * BD);
+        const int k = tile * BS + (tid % BS);
+        const bool in_range = k < a.K;
+        const bool active = in_range && tid < BS;
+        const int nvalid = min(BS, a.K - tile * BS);
         const unsigned long long kg = (unsigned long long)(a.k_offset + k);
-        fill_normals<real>(a, sm, tile, active, kg, nvalid);
+        fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
+        if (a.tps > 1) __syncthreads();
+        if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
+        if (a.tps > 1) __syncthreads();
         if (active) {
-            transform_column<real, VARIANT, NU>(a, sm, kg);
             real pert = (real)0, smooth = (real)0;
             real vprev[NU];
 #pragma unroll
@@ -766,7 +796,7 @@ __global__ void __launch_bounds__(512) sample_kernel(const KArgs<real> a) {
         // coalesced write-out of the tile: (K,T,nu) row-major == [sample][j]
         {
             const real* vt = (VARIANT == V_KMPPI) ? sm.rows2 : sm.rows;
-            const size_t base = (size_t)tile * BD * TN;
+            const size_t base = (size_t)tile * BS * TN;
             const int count = nvalid * TN;
             for (int e = tid; e < count; e += BD) {
                 const int s = e / TN, j = e - s * TN;
@@ -780,7 +810,7 @@ __global__ void __launch_bounds__(512) sample_kernel(const KArgs<real> a) {
                 }
             }
             if (VARIANT == V_KMPPI && a.out_noise_theta != nullptr) {
-                const size_t base2 = (size_t)tile * BD * R;
+                const size_t base2 = (size_t)tile * BS * R;
                 const int count2 = nvalid * R;
                 for (int e = tid; e < count2; e += BD) {
                     const int s = e / R, j = e - s * R;
@@ -824,7 +854,8 @@ __global__ void __launch_bounds__(512) softmin_update_kernel(const KArgs<real> a
     typedef Ops<real> O;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, BD = blockDim.x;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, gridDim.x, 0);
+    const int BS = BD / a.tps;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, 0);
     Smem<real> sm(smem, L);
     const int R = a.R, TN = a.TN, LD = sm.LD;
     // post-shift nominal comes from nominal_used (written by sample_kernel)
@@ -840,10 +871,10 @@ __global__ void __launch_bounds__(512) softmin_update_kernel(const KArgs<real> a
     __syncthreads();
     real beta_run = O::inf(), eta_run = (real)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int k = tile * BD + tid;
-        const bool active = k < a.K;
-        const int nvalid = min(BD, a.K - tile * BD);
-        const size_t base = (size_t)tile * BD * R;
+        const int k = tile * BS + tid;
+        const bool active = tid < BS && k < a.K;
+        const int nvalid = min(BS, a.K - tile * BS);
+        const size_t base = (size_t)tile * BS * R;
         const int count = nvalid * R;
         for (int e = tid; e < count; e += BD) {
             const int s = e / R, j = e - s * R;

@@ -61,7 +61,30 @@ template <> struct Ops<float> {
     }
     static MPPI_HD float sin_(float x) { return sinf(x); }
     static MPPI_HD float exp_(float x) { return expf(x); }
-    static MPPI_HD float fmod_(float a, float b) { return fmodf(a, b); }
+    // Exact fmodf(a, b) for b > 0 without the library's long-division loop: q ~ trunc(|a|/b) from one
+    // multiply by 1/b (off by at most one for quotients < 2^21), remainder by ONE fma — which is
+    // exact, because |a| - q*b is a multiple of ulp(b) smaller than 2b — and a +-1 correction of q
+    // (re-evaluating the fma so the returned value is never a rounded intermediate).  Larger
+    // quotients, b <= 0 and non-finite inputs take fmodf.
+    static MPPI_HD float fmod_(float a, float b) {
+#if defined(__CUDA_ARCH__)
+        const float fa = fabsf(a);
+        const float qf = fa * __frcp_rn(b);
+        if (!(b > 0.0f) || !(qf < 2097152.0f)) return fmodf(a, b);
+        float q = truncf(qf);
+        float r = __fmaf_rn(-q, b, fa);
+        if (r < 0.0f) {
+            q -= 1.0f;
+            r = __fmaf_rn(-q, b, fa);
+        } else if (r >= b) {
+            q += 1.0f;
+            r = __fmaf_rn(-q, b, fa);
+        }
+        return copysignf(r, a);
+#else
+        return fmodf(a, b);
+#endif
+    }
     static MPPI_HD float abs_(float x) { return fabsf(x); }
     static MPPI_HD float min_(float a, float b) { return fminf(a, b); }
     static MPPI_HD float max_(float a, float b) { return fmaxf(a, b); }
@@ -166,19 +189,26 @@ template <typename real> struct Normals;
 
 template <> struct Normals<float> {
     static const int PER_CALL = 4;
+    // Stream definition (oracle/philox_oracle.py): u = v*2^-32 + 2^-33, r = sqrt(-2 ln u1),
+    // n0 = r sin(2 pi u2), n1 = r cos(2 pi u2).  The device evaluates it on the SFU (MUFU.LG2 /
+    // MUFU.SQRT / MUFU.SIN / MUFU.COS): the angle is shifted into [-pi, pi) where the hardware
+    // sine/cosine are accurate to 2^-21 absolute (sin(x - pi) = -sin x), so |z_device - z_spec| is a
+    // few 1e-6 — the engine is then checked against the oracle on the z it actually used.
     static MPPI_HD void pair(uint32_t a, uint32_t b, float& n0, float& n1) {
         float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // 2^-32, 2^-33
+#if defined(__CUDA_ARCH__)
+        float ang = fmaf((float)b, 1.4629180792671596e-09f, 7.314590396335798e-10f - 3.14159265358979f);  // 2 pi u2 - pi
+        float m2l = -2.0f * __logf(u1);
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m2l));
+        n0 = -r * __sinf(ang);
+        n1 = -r * __cosf(ang);
+#else
         float u2 = (float)b * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
         float r = sqrtf(-2.0f * logf(u1));
-        float s, c;
-#if defined(__CUDA_ARCH__)
-        sincospif(2.0f * u2, &s, &c);
-#else
-        s = (float)sin(6.283185307179586 * (double)u2);
-        c = (float)cos(6.283185307179586 * (double)u2);
+        n0 = r * (float)sin(6.283185307179586 * (double)u2);
+        n1 = r * (float)cos(6.283185307179586 * (double)u2);
 #endif
-        n0 = r * s;
-        n1 = r * c;
     }
     static MPPI_HD void draw(uint64_t seed, uint64_t subseq, uint64_t offset, float* out) {
         U4 v = philox4x32_10(seed, subseq, offset);

@@ -95,6 +95,7 @@ class MPPI:
                  *,
                  rng_seed: typing.Optional[int] = None,
                  block_threads: int = 0,
+                 threads_per_sample: int = 0,
                  process_group=None,
                  exchange: str = "p2p"):
         self._lib = _cabi.load()          # raises if the CUDA library is not built
@@ -171,6 +172,7 @@ class MPPI:
             if m is not None and m.nx == self.nx and m.nu == self.nu:
                 self._model = m
         self._block_threads = int(block_threads)
+        self._threads_per_sample = int(threads_per_sample)
 
         # multi-GPU: K is the GLOBAL sample count, sharded over the group
         self._pg = process_group
@@ -315,6 +317,7 @@ class MPPI:
         p.S = 0
         p.u_per_command = self.u_per_command
         p.block_threads = self._block_threads
+        p.threads_per_sample = self._threads_per_sample
         p.grid_blocks = 0
         p.k_offset = self._k_offset
         p.lambda_ = float(self._lambda)

@@ -71,10 +71,11 @@ except Exception:
 # timing
 import pytorch_mppi_b200 as eng  # noqa: E402
 pend = eng.Pendulum()
-for K, T, bt in ((16384, 30, 0), (16384, 30, 64), (16384, 30, 128), (16384, 30, 256), (16384, 30, 512), (131072, 50, 0), (131072, 50, 128), (131072, 50, 512), (1 << 20, 50, 0), (1 << 20, 50, 128), (1 << 20, 50, 512)):
+for K, T, bt, tps in ((16384, 30, 0, 0), (16384, 30, 128, 1), (16384, 30, 128, 2), (16384, 30, 128, 4), (16384, 30, 64, 4), (16384, 30, 64, 2), (16384, 30, 32, 4), (16384, 30, 256, 2),
+                      (131072, 50, 0, 0), (131072, 50, 128, 2), (131072, 50, 256, 1), (131072, 50, 512, 1), (1 << 20, 50, 0, 0), (1 << 20, 50, 128, 1), (1 << 20, 50, 512, 1)):
     try:
         ctrl = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=K, horizon=T,
-                        u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=1, block_threads=bt)
+                        u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=1, block_threads=bt, threads_per_sample=tps)
         x = [math.pi, 1.0] if False else [3.14159, 1.0]
         for _ in range(20):
             ctrl.command(x)
@@ -90,7 +91,7 @@ for K, T, bt in ((16384, 30, 0), (16384, 30, 64), (16384, 30, 128), (16384, 30, 
         wall = (time.perf_counter() - t0) / n * 1e6
         dev = e0.elapsed_time(e1) / n * 1e3
         info = ctrl.launch_info
-        P(f"time K={K} T={T} bt={bt}: device {dev:.2f} us/command, wall {wall:.2f} us/command, grid={info.grid_blocks} block={info.block_threads} occ={info.max_blocks_per_sm} -> {K*T/dev:.1f} M rollout-steps/s")
+        P(f"time K={K} T={T} bt={bt} tps={tps}->{info.threads_per_sample}: device {dev:.2f} us/command, wall {wall:.2f} us/command, grid={info.grid_blocks} block={info.block_threads} occ={info.max_blocks_per_sm} -> {K*T/dev:.1f} M rollout-steps/s")
         # e2e: host state in, action to host
         t0 = time.perf_counter()
         for _ in range(n):
