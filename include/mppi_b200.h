@@ -127,6 +127,12 @@ typedef struct MppiFusedParams {
     void* peer_slots[MPPI_MAX_RANKS];   /* in-kernel exchange: pointer to every rank's mailbox (own included),
                                            from mppi_xchg_*; all NULL = no in-kernel exchange            */
     void* partial_out;           /* MPPI_FLAG_EXPORT_PARTIAL: (2 + R) doubles out                        */
+    void* host_mailbox;          /* optional PINNED HOST memory (device-visible under UVA), >= 16 + u_per_command*nu
+                                    elements: the kernel stores the action at byte 16.. and then host_epoch
+                                    at byte 0, so the host can spin on the flag instead of issuing a D2H copy */
+    uint64_t host_epoch;
+    void* debug_clocks;          /* optional profiling aid: (grid_blocks, 16) uint64 %globaltimer stamps (ns) at
+                                    phase boundaries of each CTA's first tile; NULL on the product path   */
 } MppiFusedParams;
 
 typedef struct MppiLaunchInfo {

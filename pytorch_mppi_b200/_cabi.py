@@ -88,6 +88,9 @@ class MppiFusedParams(C.Structure):
         ("epoch", C.c_uint64),
         ("peer_slots", C.c_void_p * MPPI_MAX_RANKS),
         ("partial_out", C.c_void_p),
+        ("host_mailbox", C.c_void_p),
+        ("host_epoch", C.c_uint64),
+        ("debug_clocks", C.c_void_p),
     ]
 
 

@@ -131,6 +131,9 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     a.epoch = p->epoch;
     a.export_partial = (p->flags & MPPI_FLAG_EXPORT_PARTIAL) ? 1 : 0;
     a.partial_out = (double*)p->partial_out;
+    a.dbg = (unsigned long long*)p->debug_clocks;
+    a.host_mailbox = (unsigned long long*)p->host_mailbox;
+    a.host_epoch = p->host_epoch;
     bool any_peer = false;
     for (int g = 0; g < MPPI_MAX_RANKS; ++g) {
         a.peers[g] = (unsigned long long*)p->peer_slots[g];

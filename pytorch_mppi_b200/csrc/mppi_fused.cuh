@@ -59,6 +59,9 @@ template <typename real> struct KArgs {
     unsigned long long seed, offset;
     int shift, null_action, tma_ok, state_per_sample;
     int tps;   // threads cooperating on one sample's sampling/transform phases (1, 2 or 4)
+    unsigned long long* dbg;   // optional (grid,16) globaltimer stamps
+    unsigned long long* host_mailbox;   // optional pinned host memory: [0]=epoch flag, [2..]=action values
+    unsigned long long host_epoch;
     // generic-path extras (sample_kernel / softmin_update_kernel)
     real* out_pa;
     real* out_noise;
@@ -103,7 +106,7 @@ __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, in
     L.LD = BS + 1;
     L.off_rows = o; o = align_up(o + R * L.LD * es, 16);
     L.off_rows2 = o; o = align_up(o + (need_rows2 ? TN * L.LD : 0) * es, 16);
-    L.off_ss = o; o = align_up(o + nb * es, 16);
+    L.off_ss = o; o = align_up(o + 2 * nb * es, 16);
     L.off_part2 = o; o = align_up(o + nw * R * 8, 16);
     L.off_numd = o; o = align_up(o + (R + 2) * 8, 16);
     L.off_redd = o; o = align_up(o + 64 * 8, 16);
@@ -142,6 +145,14 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t phase) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(phase)
             : "memory");
+    }
+}
+
+__device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
+    if (dbg != nullptr && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[(size_t)blockIdx.x * 16 + slot] = t;
     }
 }
 
@@ -212,9 +223,10 @@ template <typename real> struct Smem {
 };
 
 // ---- stage 0: nominal sequence(s) into shared memory, shift folded in ----------------------------
+// stage_issue starts the (asynchronous) TMA bulk copy; stage_finish waits for it and builds the
+// shifted nominal.  The first tile's Philox draws run in between, hiding the global-memory latency.
 template <typename real, int VARIANT, int NU>
-__device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
-    typedef Ops<real> O;
+__device__ void stage_issue(const KArgs<real>& a, Smem<real>& sm) {
     const int tid = threadIdx.x, BD = blockDim.x;
     const int T = a.T, S = a.S, R = a.R, TN = a.TN;
     if (tid == 0) mbar_init(sm.bar, 1);
@@ -239,6 +251,13 @@ __device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
         if (a.shift)
             for (int j = tid; j < S * S; j += BD) sm.Wsh[j] = a.Wshift[j];
     }
+}
+
+template <typename real, int VARIANT, int NU>
+__device__ void stage_finish(const KArgs<real>& a, Smem<real>& sm) {
+    typedef Ops<real> O;
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const int T = a.T, S = a.S, R = a.R, TN = a.TN;
     if (a.tma_ok) mbar_wait(sm.bar, 0);
     __syncthreads();
     for (int j = tid; j < TN; j += BD) {
@@ -259,6 +278,12 @@ __device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
         }
     }
     __syncthreads();
+}
+
+template <typename real, int VARIANT, int NU>
+__device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
+    stage_issue<real, VARIANT, NU>(a, sm);
+    stage_finish<real, VARIANT, NU>(a, sm);
 }
 
 // ---- stage A: standard normals into the tile ------------------------------------------------------
@@ -412,9 +437,15 @@ __device__ void fold_tile(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool
     const real resc = (beta_run == O::inf()) ? (real)0 : O::exp_(nfl * (beta_run - beta_new));
     if (tid < BS) sm.w_s[tid] = w;
     w_out = w;
-    const real eta_tile = block_sum<real>(w, sm.red);   // (its barriers also publish w_s)
-    // warp -> (sample group gi, row slice ri): every (gi, j) is produced by exactly one warp
+    __syncthreads();
+    // warp -> (sample group gi, row slice ri): every (gi, j) is produced by exactly one warp;
+    // the ri == 0 warps also reduce their group's 32 weights (the eta partial)
     const int gi = warp % ng, ri = warp / ng;
+    if (ri == 0) {
+        const int i = gi * 32 + lane;
+        const real wsum = warp_sum<real>(i < nvalid ? sm.w_s[i] : (real)0);
+        if (lane == 0) sm.red[32 + gi] = wsum;
+    }
     for (int j = lane + 32 * ri; j < R; j += 32 * a.tps) {
         const real us = (VARIANT == V_KMPPI || EPS_DIRECT) ? (real)0 : sm.Us[j];
         const real a2 = EPS_DIRECT ? (real)0 : (VARIANT == V_SMPPI ? sm.As[j] : (VARIANT == V_KMPPI ? sm.ths[j] : (real)0));
@@ -433,6 +464,8 @@ __device__ void fold_tile(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool
         for (int q = 1; q < ng; ++q) s += sm.part[q * R + j];
         sm.Vrun[j] = sm.Vrun[j] * resc + s;
     }
+    real eta_tile = sm.red[32];
+    for (int q = 1; q < ng; ++q) eta_tile += sm.red[32 + q];
     eta_run = eta_run * resc + eta_tile;
     beta_run = beta_new;
     __syncthreads();
@@ -516,11 +549,15 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
         a.stats[0] = numd[0];
         a.stats[1] = eta;
     }
+    real* hact = a.host_mailbox != nullptr ? reinterpret_cast<real*>(a.host_mailbox + 2) : nullptr;
     if (VARIANT == V_MPPI) {
         for (int j = tid; j < TN; j += BD) {
             const real un = O::add(Us[j], (real)(numd[2 + j] * inv_eta));                // mppi.py:270
             a.U[j] = un;
-            if (j < a.upc * nu) a.action_out[j] = un;                                      // mppi.py:271-275
+            if (j < a.upc * nu) {                                                          // mppi.py:271-275
+                a.action_out[j] = un;
+                if (hact != nullptr) hact[j] = un;
+            }
         }
     } else if (VARIANT == V_SMPPI) {
         for (int j = tid; j < TN; j += BD) {
@@ -528,7 +565,10 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
             const real an = O::add(As[j], O::mul(un, a.nm.delta_t));                       // mppi.py:531
             a.U[j] = un;
             a.A[j] = an;
-            if (j < a.upc * nu) a.action_out[j] = an;                                      // mppi.py:533-537
+            if (j < a.upc * nu) {                                                          // mppi.py:533-537
+                a.action_out[j] = an;
+                if (hact != nullptr) hact[j] = an;
+            }
         }
     } else {
         __syncthreads();
@@ -544,7 +584,19 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
             real acc = O::mul(Ws[t * S], ths[n]);
             for (int s = 1; s < S; ++s) acc = O::add(acc, O::mul(Ws[t * S + s], ths[s * nu + n]));
             a.U[j] = acc;
-            if (j < a.upc * nu) a.action_out[j] = acc;
+            if (j < a.upc * nu) {
+                a.action_out[j] = acc;
+                if (hact != nullptr) hact[j] = acc;
+            }
+        }
+    }
+    if (a.host_mailbox != nullptr) {
+        // zero-copy result delivery: action words first, then the epoch flag the host spins on
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            *reinterpret_cast<volatile unsigned long long*>(a.host_mailbox) = a.host_epoch;
+            __threadfence_system();
         }
     }
 }
@@ -570,54 +622,82 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
         s_is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
+    stamp(a.dbg, 6);
     if (!s_is_last) return;
     __threadfence();
+    stamp(a.dbg, 8);
 
     // The partials were written by other SMs before their ticket increments; this CTA has not
-    // touched those lines during this launch, and __ldcg reads them from L2.  Loads are issued in
-    // batches of 8 so their ~300-cycle L2 latencies overlap instead of serialising.
+    // touched those lines during this launch, and __ldcg reads them from L2.  Every load whose
+    // address does not depend on beta is issued up front (one L2 round trip for the common case),
+    // the scalar part (beta, eta, rescale factors) is done by warp 0 with shuffles only, and three
+    // barriers separate the remaining stages.
     const int nb = gridDim.x;
     const real* betaP = a.betaP;
     const real* etaP = a.etaP;
     const real* VP = a.VP;
-    real bmin = O::inf();
-    for (int q = tid; q < nb; q += BD) {
-        const real bq = __ldcg(betaP + q);
-        bmin = bq < bmin ? bq : bmin;
+    real* sB = sm.sS;            // [nb] beta_q, then rescale factors s_q
+    real* sE = sm.sS + nb;       // [nb] eta_q
+    real vpre[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int q = warp + u * nw;
+        vpre[u] = (lane < R && q < nb) ? __ldcg(VP + (size_t)q * R + lane) : (real)0;
     }
-    const real beta = block_min<real>(bmin, sm.red);
-    double eta_loc = 0.0;
-    for (int q = tid; q < nb; q += BD) {
-        const real s = O::exp_(nfl * (__ldcg(betaP + q) - beta));
-        sm.sS[q] = s;
-        eta_loc += (double)s * (double)__ldcg(etaP + q);
+    if (warp == 0) {
+        real bl = O::inf();
+        for (int q = lane; q < nb; q += 32) {
+            const real bq = __ldcg(betaP + q);
+            sB[q] = bq;
+            sE[q] = __ldcg(etaP + q);
+            bl = bq < bl ? bq : bl;
+        }
+        const real beta = warp_min<real>(bl);
+        __syncwarp();
+        double el = 0.0;
+        for (int q = lane; q < nb; q += 32) {
+            const real sq = O::exp_(nfl * (sB[q] - beta));
+            sB[q] = sq;
+            el += (double)sq * (double)sE[q];
+        }
+        const double eta = warp_sum<double>(el);
+        if (lane == 0) {
+            sm.numd[0] = (double)beta;
+            sm.numd[1] = eta;
+            *a.ticket = 0u;   // self-reset: the next launch needs no memset
+        }
     }
-    const double eta = block_sum<double>(eta_loc, sm.redd);   // barriers also publish sS
+    __syncthreads();
+    stamp(a.dbg, 10);
     for (int j = lane; j < R; j += 32) {
         double acc = 0.0;
         int q = warp;
+        if (j == lane) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int qq = warp + u * nw;
+                if (qq < nb) acc += (double)sB[qq] * (double)vpre[u];
+            }
+            q = warp + 8 * nw;
+        }
         for (; q + 7 * nw < nb; q += 8 * nw) {
             real v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = __ldcg(VP + (size_t)(q + u * nw) * R + j);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += (double)sm.sS[q + u * nw] * (double)v[u];
+            for (int u = 0; u < 8; ++u) acc += (double)sB[q + u * nw] * (double)v[u];
         }
-        for (; q < nb; q += nw) acc += (double)sm.sS[q] * (double)__ldcg(VP + (size_t)q * R + j);
+        for (; q < nb; q += nw) acc += (double)sB[q] * (double)__ldcg(VP + (size_t)q * R + j);
         sm.part2[warp * R + j] = acc;
     }
     __syncthreads();
     for (int j = tid; j < R; j += BD) {
-        double s = sm.part2[j];
-        for (int q = 1; q < nw; ++q) s += sm.part2[q * R + j];
-        sm.numd[2 + j] = s;
-    }
-    if (tid == 0) {
-        sm.numd[0] = (double)beta;
-        sm.numd[1] = eta;
-        *a.ticket = 0u;   // self-reset: the next launch needs no memset
+        double s2 = sm.part2[j];
+        for (int q = 1; q < nw; ++q) s2 += sm.part2[q * R + j];
+        sm.numd[2 + j] = s2;
     }
     __syncthreads();
+    stamp(a.dbg, 11);
 
     if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
         for (int j = tid; j < R + 2; j += BD) a.partial_out[j] = sm.numd[j];
@@ -660,7 +740,10 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
 
-    stage_nominal<real, VARIANT, NU>(a, sm);
+    stamp(a.dbg, 0);
+    stage_issue<real, VARIANT, NU>(a, sm);
+    stamp(a.dbg, 1);
+    bool staged = false;
 
     real beta_run = O::inf(), eta_run = (real)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -671,9 +754,16 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
         const unsigned long long kg = (unsigned long long)(a.k_offset + k);
 
         fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
-        if (a.tps > 1) __syncthreads();
+        if (!staged) {   // the nominal sequence is first needed now; its TMA copy flew during the draws
+            stage_finish<real, VARIANT, NU>(a, sm);
+            staged = true;
+        } else if (a.tps > 1) {
+            __syncthreads();
+        }
+        if (tile == blockIdx.x) stamp(a.dbg, 2);
         if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
         if (a.tps > 1) __syncthreads();
+        if (tile == blockIdx.x) stamp(a.dbg, 3);
 
         real c_tot = O::inf();
         if (active) {
@@ -688,19 +778,25 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
 #pragma unroll
                 for (int i = 0; i < NX; ++i) x[i] = a.x0[i];
             }
+            // Software-pipelined T-loop: the running cost of the state reached at step t-1 and the
+            // dynamics of step t both depend only on x_t, so issuing them back to back gives the
+            // single resident warp two independent dependency chains.  The arithmetic and the
+            // order of every accumulation are exactly the reference's (cost summed t = 0..T-1).
             real roll = (real)0, pert = (real)0, smooth = (real)0;
-            real vprev[NU];
+            real vprev[NU], uprev[NU];
 #pragma unroll
-            for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
+            for (int n = 0; n < NU; ++n) { vprev[n] = (real)0; uprev[n] = (real)0; }
 #pragma unroll 2
             for (int t = 0; t < T; ++t) {
-                real v[NU], u[NU], eps[NU];
+                real v[NU], u[NU], eps[NU], xs[NX];
                 action_at<real, VARIANT, NU>(a, sm, kg, t, v);
                 noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
 #pragma unroll
                 for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
+#pragma unroll
+                for (int i = 0; i < NX; ++i) xs[i] = x[i];
                 Model::template step<real>(mp, x, u);                                     // mppi.py:314
-                roll = O::add(roll, Model::template cost<real>(mp, x, u));                // mppi.py:318-319
+                if (t > 0) roll = O::add(roll, Model::template cost<real>(mp, xs, uprev));   // mppi.py:318-319 (step t-1)
                 pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
                 if (VARIANT == V_SMPPI) {
                     if (t > 0) {
@@ -713,16 +809,23 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
 #pragma unroll
                     for (int n = 0; n < NU; ++n) vprev[n] = v[n];
                 }
+#pragma unroll
+                for (int n = 0; n < NU; ++n) uprev[n] = u[n];
             }
+            roll = O::add(roll, Model::template cost<real>(mp, x, uprev));                // step T-1
             if (Model::template has_terminal<real>(mp)) roll = O::add(roll, Model::template terminal<real>(mp, x));
             c_tot = O::add(roll, pert);                                                   // mppi.py:416
             if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569
             a.cost_total[k] = c_tot;
         }
         real w_unused;
+        if (tile == blockIdx.x) stamp(a.dbg, 4);
         fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+        if (tile == blockIdx.x) stamp(a.dbg, 5);
     }
+    if (!staged) stage_finish<real, VARIANT, NU>(a, sm);
     publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+    stamp(a.dbg, 7);
 }
 
 // =================================================================================================

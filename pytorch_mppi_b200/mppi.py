@@ -200,6 +200,8 @@ class MPPI:
             self._rng_seed = int(s.item())
         self._z_inject = None
         self._z_out = None
+        self._host_box = None
+        self._host_epoch = 0
 
         # device state
         self._alloc_nominal(U_init)
@@ -362,6 +364,9 @@ class MPPI:
         for g in range(_cabi.MPPI_MAX_RANKS):
             p.peer_slots[g] = None
         p.partial_out = None
+        p.debug_clocks = None
+        p.host_mailbox = None
+        p.host_epoch = 0
         self._variant_pack(p)
         # workspace sized for the worst-case geometry of these dimensions
         if self._model is not None:
@@ -568,6 +573,36 @@ class MPPI:
         if rc != 0:
             _cabi.check(rc, "mppi_fused_command")
         return self._finish_command(p, action, stream)
+
+    def command_host(self, state, shift_nominal_trajectory=True, info=None):
+        """`command()` for a control loop that lives on the host: the start state travels in the
+        kernel's parameter block (no H2D copy) and the kernel stores the action straight into pinned
+        host memory, then an epoch flag the host spins on — no D2H memcpy call, no stream
+        synchronise.  Returns a CPU tensor ((nu,) or (u_per_command, nu)); the device-side state
+        (U, cost_total, ...) is exactly what `command()` leaves."""
+        if self._host_box is None:
+            words = 2 + (self.u_per_command * self.nu * _ES[self.dtype] + 7) // 8
+            self._host_box = torch.zeros(words, dtype=torch.int64).pin_memory()
+            self._host_flag = self._host_box.numpy()[:1]
+            self._host_vals = self._host_box[2:].view(self.dtype)[: self.u_per_command * self.nu].view(self.u_per_command, self.nu)
+        self._host_epoch += 1
+        p = self._p
+        p.host_mailbox = self._host_box.data_ptr()
+        p.host_epoch = self._host_epoch
+        try:
+            self.command(state, shift_nominal_trajectory, info)
+        finally:
+            p.host_mailbox = None
+        flag, want = self._host_flag, self._host_epoch
+        spins = 0
+        while flag[0] != want:
+            spins += 1
+            if spins > 50_000_000:
+                torch.cuda.synchronize(self.d)
+                if flag[0] != want:
+                    raise RuntimeError("command_host: the kernel never published its result")
+        out = self._host_vals.clone()
+        return out[0] if self.u_per_command == 1 else out
 
     # ------------------------------------------------------------------------------------------
     # stepped route (arbitrary callables): mppi.py:297-373 with kernels around the T-loop

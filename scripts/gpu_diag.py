@@ -98,6 +98,11 @@ for K, T, bt, tps in ((16384, 30, 0, 0), (16384, 30, 128, 1), (16384, 30, 128, 2
             a = ctrl.command(x).cpu()
         wall = (time.perf_counter() - t0) / n * 1e6
         P(f"     e2e (host state -> action.cpu()): {wall:.2f} us/command")
+        t0 = time.perf_counter()
+        for _ in range(n):
+            a = ctrl.command_host(x)
+        wall = (time.perf_counter() - t0) / n * 1e6
+        P(f"     e2e (command_host, pinned mailbox):  {wall:.2f} us/command")
     except Exception:
         P(f"time K={K} EXCEPTION\n{traceback.format_exc()}")
 out.close()

@@ -1,0 +1,36 @@
+"""Phase timeline of the fused kernel from %globaltimer stamps (debug aid). usage: phase_clocks.py K T [bt] [tps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pytorch_mppi_b200 as eng  # noqa: E402
+
+K, T = int(sys.argv[1]), int(sys.argv[2])
+bt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+tps = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+pend = eng.Pendulum()
+ctrl = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=K, horizon=T,
+                u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=1, block_threads=bt, threads_per_sample=tps)
+x = [3.14159, 1.0]
+for _ in range(5):
+    ctrl.command(x)
+nb = ctrl.launch_info.grid_blocks
+dbg = torch.zeros(nb, 16, dtype=torch.int64, device="cuda")
+ctrl._p.debug_clocks = dbg.data_ptr()
+names = ["start", "staged", "filled", "transformed", "rolled", "folded", "published", "end(last)", "L:fence", "L:beta", "L:eta", "L:numer"]
+for rep in range(3):
+    dbg.zero_()
+    torch.cuda.synchronize()
+    ctrl.command(x)
+    torch.cuda.synchronize()
+    d = dbg.cpu().numpy().astype(np.int64)
+    t0 = d[:, 0].min()
+    print(f"rep {rep}: grid={nb} block={ctrl.launch_info.block_threads} tps={ctrl.launch_info.threads_per_sample}")
+    for i, n in enumerate(names):
+        col = d[:, i]
+        col = col[col > 0]
+        if len(col):
+            print(f"  {n:12s} min {(col.min()-t0)/1e3:7.2f} us  median {(np.median(col)-t0)/1e3:7.2f}  max {(col.max()-t0)/1e3:7.2f}")

@@ -183,3 +183,23 @@ def test_large_k_grid_stride_and_block_sizes():
     floor = (res[torch.float32] - res[torch.float64]).abs().max().item()
     err = (outs[1].double() - res[torch.float64]).abs().max().item()
     assert err <= 2 * floor + 1e-5, (err, floor)
+
+
+def test_command_host_zero_copy_equals_command():
+    """The pinned-mailbox delivery returns exactly the action `command()` leaves on the device."""
+    import pytorch_mppi_b200 as eng
+    nav = eng.LinearPoint.toy2d_nav()
+    for cls, kw in ((eng.MPPI, {}), (eng.SMPPI, dict(w_action_seq_cost=10.0, action_max=torch.tensor([1.0, 1.0]))),
+                    (eng.KMPPI, dict(num_support_pts=5, kernel=eng.RBFKernel(sigma=2)))):
+        outs = []
+        for host in (False, True):
+            c = cls(nav.dynamics, nav.running_cost, 2, torch.eye(2), num_samples=1024, horizon=20, device="cuda",
+                    terminal_state_cost=nav.terminal_cost, u_max=torch.tensor([1.0, 1.0]), rng_seed=7, u_per_command=2, **kw)
+            acts = []
+            x = [-3.0, -2.0]
+            for _ in range(3):
+                a = c.command_host(x) if host else c.command(x).cpu()
+                assert a.shape == (2, 2) and a.device.type == "cpu"
+                acts.append(a.clone())
+            outs.append(torch.stack(acts))
+        assert torch.equal(outs[0], outs[1])
