@@ -586,6 +586,8 @@ class MPPI:
             self._host_flag = self._host_box.numpy()[:1]
             self._host_vals = self._host_box[2:].view(self.dtype)[: self.u_per_command * self.nu].view(self.u_per_command, self.nu)
         self._host_epoch += 1
+        if self._dirty:
+            self._pack()          # (re)packing clears the mailbox fields, so do it first
         p = self._p
         p.host_mailbox = self._host_box.data_ptr()
         p.host_epoch = self._host_epoch
