@@ -156,6 +156,24 @@ int mppi_fused_query(const MppiFusedParams* p, MppiLaunchInfo* out);
 /* The fused command (see struct comment).  `stream` is a cudaStream_t. */
 int mppi_fused_command(const MppiFusedParams* p, void* stream);
 
+/* ---- Plans: the steady-state fast path ----------------------------------------------------------
+ * A plan freezes everything `mppi_fused_command` derives from an MppiFusedParams (kernel selection,
+ * launch geometry, the pre-cast kernel argument block) so that one command costs one short call.
+ * Per command only the start state, the RNG counter / injected-noise pointer, the flags that vary
+ * (SHIFT, STATE_DEVICE, STATE_PER_SAMPLE) and the action destination change.  The multi-GPU epoch is
+ * advanced inside the plan (every rank issues the same sequence of commands). */
+int mppi_plan_create(const MppiFusedParams* p, void** plan_out);
+int mppi_plan_destroy(void* plan);
+/* One command(); `state` = nx host doubles (by value into the launch) or NULL with `state_dev` set. */
+int mppi_plan_command(void* plan, const double* state, const void* state_dev, uint32_t flags, uint64_t seed,
+                      uint64_t offset, const void* z, void* action_out, void* stream);
+/* One command() for a host-resident control loop: launches, then spins (in C) on the pinned-host
+ * mailbox the kernel stores the action + epoch flag into, and returns the action as doubles in
+ * `action_host_out` (u_per_command*nu).  No D2H memcpy call, no stream synchronise.
+ * `host_mailbox`: >= 16 + u_per_command*nu*sizeof(dtype) bytes of pinned host memory. */
+int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset,
+                           const void* z, void* action_out_dev, void* host_mailbox, double* action_host_out, void* stream);
+
 /* Multi-GPU, library-collective route: after every rank exported its partial and the caller
  * all-gathered them (NCCL), finish the update on each rank: beta=min, rescale, U += sum/eta
  * (mppi.py:254-259, 268-270 across shards).  `partials` is (world, 2+R) doubles on device. */

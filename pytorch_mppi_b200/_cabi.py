@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libmppi_b200.so")
+LIB_PATH = os.environ.get("MPPI_B200_LIB") or os.path.join(HERE, "csrc", "libmppi_b200.so")
 
 MPPI_MAX_NU = 4
 MPPI_MAX_NX = 8
@@ -117,6 +117,12 @@ SYMBOLS = [
     ("mppi_abi_layout", C.c_uint64, [C.c_int]),
     ("mppi_fused_query", C.c_int, [_P, C.POINTER(MppiLaunchInfo)]),
     ("mppi_fused_command", C.c_int, [_P, C.c_void_p]),
+    ("mppi_plan_create", C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    ("mppi_plan_destroy", C.c_int, [C.c_void_p]),
+    ("mppi_plan_command", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    ("mppi_plan_command_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     ("mppi_apply_partials", C.c_int, [_P, C.c_void_p, C.c_void_p]),
     ("mppi_xchg_create", C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
     ("mppi_xchg_open", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

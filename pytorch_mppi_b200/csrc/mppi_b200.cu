@@ -2,6 +2,7 @@
 // Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
 // No torch types cross this boundary; the Python side binds it with ctypes.
 #include <cuda_runtime.h>
+#include <new>
 #include <stdio.h>
 #include <string.h>
 
@@ -287,6 +288,82 @@ template <class Model> int run_fused_dtype(const MppiFusedParams* p, cudaStream_
     return p->dtype == MPPI_F32 ? run_fused_variant<Model, float>(p, s, info) : run_fused_variant<Model, double>(p, s, info);
 }
 
+// ---- plans ---------------------------------------------------------------------------------------
+struct Plan {
+    MppiFusedParams p;
+    const void* kernel;
+    Geometry g;
+    int is_double, nx, upc_nu;
+    unsigned long long epoch, host_epoch;
+    alignas(16) unsigned char kargs[sizeof(KArgs<double>)];
+    alignas(16) unsigned char mparams[1024];
+};
+
+template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    auto kernel = fused_command_kernel<Model, real, V>;
+    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
+    if (rc) return rc;
+    if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
+    static_assert(sizeof(typename Model::template P<real>) <= sizeof(pl->mparams), "model parameter block too large");
+    KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
+    fill_kargs<real>(p, *a, pl->g.BS, pl->g.nb, pl->g.tps);
+    if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
+    typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
+    Model::template load<real>(*mp, p->model_params);
+    pl->kernel = (const void*)kernel;
+    pl->is_double = sizeof(real) == 8;
+    pl->nx = Model::NX;
+    pl->upc_nu = p->u_per_command * p->nu;
+    pl->epoch = p->epoch;
+    pl->host_epoch = 0;
+    pl->p = *p;
+    return MPPI_OK;
+}
+
+template <class Model, typename real> int build_plan_variant(const MppiFusedParams* p, Plan* pl) {
+    switch (p->variant) {
+        case MPPI_VARIANT_MPPI: return build_plan<Model, real, V_MPPI>(p, pl);
+        case MPPI_VARIANT_SMPPI: return build_plan<Model, real, V_SMPPI>(p, pl);
+        case MPPI_VARIANT_KMPPI: return build_plan<Model, real, V_KMPPI>(p, pl);
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+template <class Model> int build_plan_dtype(const MppiFusedParams* p, Plan* pl) {
+    return p->dtype == MPPI_F32 ? build_plan_variant<Model, float>(p, pl) : build_plan_variant<Model, double>(p, pl);
+}
+
+template <typename real>
+inline void plan_update(Plan* pl, const double* state, const void* state_dev, uint32_t flags, uint64_t seed, uint64_t offset,
+                        const void* z, void* action_out, void* host_mailbox) {
+    KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
+    if (state != nullptr)
+        for (int i = 0; i < pl->nx; ++i) a->x0[i] = (real)state[i];
+    a->state_dev = (flags & MPPI_FLAG_STATE_DEVICE) ? (const real*)state_dev : nullptr;
+    a->state_per_sample = (flags & MPPI_FLAG_STATE_PER_SAMPLE) ? 1 : 0;
+    a->shift = (flags & MPPI_FLAG_SHIFT) ? 1 : 0;
+    a->seed = seed;
+    a->offset = offset;
+    a->z = (const real*)z;
+    a->action_out = (real*)action_out;
+    if (a->world > 1 || a->export_partial) a->epoch = ++pl->epoch;
+    a->host_mailbox = (unsigned long long*)host_mailbox;
+    if (host_mailbox != nullptr) a->host_epoch = ++pl->host_epoch;
+}
+
+inline int plan_launch(Plan* pl, cudaStream_t stream) {
+    void* argv[2] = {(void*)pl->kargs, (void*)pl->mparams};
+    cudaError_t e = cudaLaunchKernel(pl->kernel, dim3(pl->g.nb), dim3(pl->g.BD), argv, (size_t)pl->g.smem, stream);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "plan launch grid=%d block=%d smem=%d: %s (%s)", pl->g.nb, pl->g.BD, pl->g.smem,
+                 cudaGetErrorName(e), cudaGetErrorString(e));
+        return MPPI_ERR_CUDA;
+    }
+    return MPPI_OK;
+}
+
 int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
     int rc = validate(p);
     if (rc) return rc;
@@ -453,6 +530,71 @@ int mppi_fused_query(const MppiFusedParams* p, MppiLaunchInfo* out) {
 }
 
 int mppi_fused_command(const MppiFusedParams* p, void* stream) { return dispatch_fused(p, (cudaStream_t)stream, nullptr); }
+
+int mppi_plan_create(const MppiFusedParams* p, void** plan_out) {
+    if (plan_out == nullptr) return MPPI_ERR_BAD_ARG;
+    int rc = validate(p);
+    if (rc) return rc;
+    Plan* pl = new (std::nothrow) Plan();
+    if (pl == nullptr) return MPPI_ERR_BAD_ARG;
+    switch (p->model) {
+        case MPPI_MODEL_PENDULUM: rc = build_plan_dtype<PendulumModel>(p, pl); break;
+        case MPPI_MODEL_LINEAR_POINT: rc = build_plan_dtype<LinearPointModel>(p, pl); break;
+        default: rc = MPPI_ERR_UNSUPPORTED;
+    }
+    if (rc) {
+        delete pl;
+        return rc;
+    }
+    *plan_out = pl;
+    return MPPI_OK;
+}
+
+int mppi_plan_destroy(void* plan) {
+    if (plan == nullptr) return MPPI_ERR_BAD_ARG;
+    delete reinterpret_cast<Plan*>(plan);
+    return MPPI_OK;
+}
+
+int mppi_plan_command(void* plan, const double* state, const void* state_dev, uint32_t flags, uint64_t seed, uint64_t offset,
+                      const void* z, void* action_out, void* stream) {
+    Plan* pl = reinterpret_cast<Plan*>(plan);
+    if (pl == nullptr || action_out == nullptr) return MPPI_ERR_BAD_ARG;
+    if (state == nullptr && !(flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;
+    if (pl->is_double) plan_update<double>(pl, state, state_dev, flags, seed, offset, z, action_out, nullptr);
+    else plan_update<float>(pl, state, state_dev, flags, seed, offset, z, action_out, nullptr);
+    return plan_launch(pl, (cudaStream_t)stream);
+}
+
+int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset, const void* z,
+                           void* action_out_dev, void* host_mailbox, double* action_host_out, void* stream) {
+    Plan* pl = reinterpret_cast<Plan*>(plan);
+    if (pl == nullptr || state == nullptr || host_mailbox == nullptr || action_host_out == nullptr || action_out_dev == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    if (pl->is_double) plan_update<double>(pl, state, nullptr, flags, seed, offset, z, action_out_dev, host_mailbox);
+    else plan_update<float>(pl, state, nullptr, flags, seed, offset, z, action_out_dev, host_mailbox);
+    int rc = plan_launch(pl, (cudaStream_t)stream);
+    if (rc) return rc;
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(host_mailbox);
+    const unsigned long long want = pl->host_epoch;
+    unsigned long long spins = 0;
+    while (*flag != want) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0xFFFFF) == 0) {           // every ~1M spins: has the stream died or finished without publishing?
+            cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery while waiting for the mailbox");
+            if (q == cudaSuccess && *flag != want) return MPPI_ERR_TIMEOUT;
+        }
+    }
+    const unsigned char* vals = reinterpret_cast<const unsigned char*>(host_mailbox) + 16;
+    if (pl->is_double)
+        for (int i = 0; i < pl->upc_nu; ++i) action_host_out[i] = reinterpret_cast<const volatile double*>(vals)[i];
+    else
+        for (int i = 0; i < pl->upc_nu; ++i) action_host_out[i] = (double)reinterpret_cast<const volatile float*>(vals)[i];
+    return MPPI_OK;
+}
 
 int mppi_apply_partials(const MppiFusedParams* p, const void* partials, void* stream) {
     int rc = validate(p);

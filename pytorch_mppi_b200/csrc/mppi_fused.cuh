@@ -23,6 +23,15 @@
 #include <cuda_runtime.h>
 #include "mppi_math.cuh"
 
+#ifndef MPPI_ROLLOUT_PIPELINED
+#define MPPI_ROLLOUT_PIPELINED 1
+#endif
+#ifndef MPPI_ROLLOUT_UNROLL
+#define MPPI_ROLLOUT_UNROLL 2
+#endif
+#define MPPI_PRAGMA_(x) _Pragma(#x)
+#define MPPI_UNROLL_N(n) MPPI_PRAGMA_(unroll n)
+
 namespace mppi {
 
 enum { V_MPPI = 0, V_SMPPI = 1, V_KMPPI = 2 };
@@ -786,7 +795,7 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
             real vprev[NU], uprev[NU];
 #pragma unroll
             for (int n = 0; n < NU; ++n) { vprev[n] = (real)0; uprev[n] = (real)0; }
-#pragma unroll 2
+MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
             for (int t = 0; t < T; ++t) {
                 real v[NU], u[NU], eps[NU], xs[NX];
                 action_at<real, VARIANT, NU>(a, sm, kg, t, v);
@@ -795,8 +804,13 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
                 for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
 #pragma unroll
                 for (int i = 0; i < NX; ++i) xs[i] = x[i];
+#if MPPI_ROLLOUT_PIPELINED
                 Model::template step<real>(mp, x, u);                                     // mppi.py:314
                 if (t > 0) roll = O::add(roll, Model::template cost<real>(mp, xs, uprev));   // mppi.py:318-319 (step t-1)
+#else
+                Model::template step<real>(mp, x, u);                                     // mppi.py:314
+                roll = O::add(roll, Model::template cost<real>(mp, x, u));                // mppi.py:318-319
+#endif
                 pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
                 if (VARIANT == V_SMPPI) {
                     if (t > 0) {
@@ -812,7 +826,9 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
 #pragma unroll
                 for (int n = 0; n < NU; ++n) uprev[n] = u[n];
             }
+#if MPPI_ROLLOUT_PIPELINED
             roll = O::add(roll, Model::template cost<real>(mp, x, uprev));                // step T-1
+#endif
             if (Model::template has_terminal<real>(mp)) roll = O::add(roll, Model::template terminal<real>(mp, x));
             c_tot = O::add(roll, pert);                                                   // mppi.py:416
             if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569

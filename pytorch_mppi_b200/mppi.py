@@ -201,7 +201,8 @@ class MPPI:
         self._z_inject = None
         self._z_out = None
         self._host_box = None
-        self._host_epoch = 0
+        self._plan = None
+        self._last = None
 
         # device state
         self._alloc_nominal(U_init)
@@ -364,7 +365,8 @@ class MPPI:
         for g in range(_cabi.MPPI_MAX_RANKS):
             p.peer_slots[g] = None
         p.partial_out = None
-        p.debug_clocks = None
+        dbg = getattr(self, "_debug_clocks", None)
+        p.debug_clocks = None if dbg is None else dbg.data_ptr()
         p.host_mailbox = None
         p.host_epoch = 0
         self._variant_pack(p)
@@ -384,6 +386,34 @@ class MPPI:
         if self._world > 1:
             self._setup_exchange(p)
         self._dirty = False
+        if self._model is not None:
+            self._make_plan(p)
+
+    def _make_plan(self, p):
+        """Freeze the launch state in the C library (`mppi_plan_create`): per command only the state,
+        RNG counter, flags and action destination cross the boundary."""
+        self._drop_plan()
+        p.flags = self._base_flags | (_cabi.FLAG_EXPORT_PARTIAL if (self._world > 1 and self._exchange != "p2p") else 0)
+        p.z_out = None if self._z_out is None else self._z_out.data_ptr()
+        p.epoch = self._epoch
+        plan = C.c_void_p()
+        _cabi.check(self._lib.mppi_plan_create(C.byref(p), C.byref(plan)), "mppi_plan_create")
+        self._plan = plan
+        self._state_arr = (C.c_double * _cabi.MPPI_MAX_NX)()
+        self._scratch_action = torch.empty((self.u_per_command, self.nu), device=self.d, dtype=self.dtype)
+        self._host_out = (C.c_double * (self.u_per_command * self.nu))()
+
+    def _drop_plan(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None:
+            self._lib.mppi_plan_destroy(plan)
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._drop_plan()
+        except Exception:
+            pass
 
     def _noise_rows(self):
         return self.T * self.nu
@@ -443,6 +473,7 @@ class MPPI:
     def record_noise(self, enable=True):
         """Keep the standard normals each command actually used in `self.z_used`."""
         self._z_out = torch.empty(self._K_local * self._noise_rows(), device=self.d, dtype=self.dtype) if enable else None
+        self._dirty = True
 
     @property
     def z_used(self):
@@ -501,46 +532,88 @@ class MPPI:
     # ------------------------------------------------------------------------------------------
     # fused route
     # ------------------------------------------------------------------------------------------
-    def _set_state(self, p, state, flags):
-        """State by value in the parameter struct when it lives on the host (no H2D copy);
-        device pointer when it is already a CUDA tensor or one state per sample."""
+    def _host_state(self, state):
+        """(flags, state_dev_ptr) — host states go by value into the launch (no H2D copy); CUDA tensors
+        and one-state-per-sample batches are read from device memory."""
         if torch.is_tensor(state) and state.is_cuda:
             st = state.to(self.dtype)
             if st.dim() == 2 and st.shape == (self.K, self.nx) and self.K != 1:
                 st = st[self._k_offset:self._k_offset + self._K_local].contiguous()
-                flags |= _cabi.FLAG_STATE_DEVICE | _cabi.FLAG_STATE_PER_SAMPLE
-            else:
-                st = st.reshape(-1).contiguous()
-                flags |= _cabi.FLAG_STATE_DEVICE
+                self.state = st
+                return _cabi.FLAG_STATE_DEVICE | _cabi.FLAG_STATE_PER_SAMPLE, st.data_ptr()
+            st = st.reshape(-1).contiguous()
             self.state = st
-            p.state_dev = st.data_ptr()
-            return flags
+            return _cabi.FLAG_STATE_DEVICE, st.data_ptr()
         vals = state.tolist() if hasattr(state, "tolist") else list(state)
         if len(vals) and isinstance(vals[0], (list, tuple)):
             if len(vals) == self.K and self.K != 1:   # (K,nx) host states -> upload once
-                return self._set_state(p, torch.as_tensor(state).to(self.d), flags)
+                return self._host_state(torch.as_tensor(state).to(self.d))
             vals = vals[0]
         if len(vals) < self.nx:
             raise ValueError(f"state has {len(vals)} entries, nx={self.nx}")
-        for i in range(self.nx):
-            p.state[i] = vals[i]
+        self._state_arr[: self.nx] = vals[: self.nx]
         self.state = state
-        p.state_dev = None
-        return flags
+        return 0, None
 
+    def _noise_source(self):
+        """(z_ptr, seed, offset) for this command."""
+        if self._z_inject is not None:
+            self._z_keep = self._z_inject          # stays alive for lazy materialisation
+            self._z_inject = None
+            return self._z_keep.data_ptr(), 0, 0
+        self._z_keep = None
+        seed, off = self._next_rng()
+        return None, seed, off
+
+    def _command_fused(self, state, shift):
+        sflags, sdev = self._host_state(state)
+        flags = self._base_flags | sflags | (_cabi.FLAG_SHIFT if shift else 0)
+        zptr, seed, off = self._noise_source()
+        action = torch.empty((self.u_per_command, self.nu), device=self.d, dtype=self.dtype)
+        stream = torch._C._cuda_getCurrentRawStream(self.d.index)
+        self._last = (flags, seed, off, zptr, sdev)
+        self._cmd_count += 1
+        rc = self._lib.mppi_plan_command(self._plan, None if sdev is not None else self._state_arr, sdev, flags, seed, off,
+                                         zptr, action.data_ptr(), stream)
+        if rc != 0:
+            _cabi.check(rc, "mppi_plan_command")
+        if self._world > 1:
+            self._epoch += 1
+            if self._exchange != "p2p":
+                self._finish_exported(action, stream)
+        self.cost_total = self._cost_buf
+        self._states = None
+        self._actions = None
+        return action[0] if self.u_per_command == 1 else action                            # mppi.py:273-274
+
+    def _finish_exported(self, action, stream):
+        """NCCL route: all-gather the per-rank records, then `mppi_apply_partials` finishes the update."""
+        import torch.distributed as dist
+        p = self._p
+        dist.all_gather_into_tensor(self._gathered, self._partial, group=self._pg)
+        p.flags = self._base_flags
+        p.action_out = action.data_ptr()
+        _cabi.check(self._lib.mppi_apply_partials(C.byref(p), self._gathered.data_ptr(), stream), "mppi_apply_partials")
+
+    def _sync_params_for_materialize(self):
+        """Write the last command's per-call values back into the parameter struct (the plan path does not)."""
+        p = self._p
+        flags, seed, off, zptr, sdev = self._last
+        p.flags = flags & ~_cabi.FLAG_SHIFT
+        p.seed, p.offset = seed, off
+        p.z = zptr
+        p.state_dev = sdev
+        for i in range(self.nx):
+            p.state[i] = self._state_arr[i]
+
+    # -- struct-based command setup used by the stepped route ------------------------------------
     def _begin_command(self, state, shift):
         p = self._p
         flags = self._base_flags | (_cabi.FLAG_SHIFT if shift else 0)
-        flags = self._set_state(p, state, flags)
-        if self._z_inject is not None:
-            p.z = self._z_inject.data_ptr()
-            self._z_keep = self._z_inject      # stays alive for lazy materialisation
-            self._z_inject = None
-            p.seed, p.offset = 0, 0
-        else:
-            p.z = None
-            self._z_keep = None
-            p.seed, p.offset = self._next_rng()
+        zptr, seed, off = self._noise_source()
+        p.z = zptr
+        p.seed, p.offset = seed, off
+        p.state_dev = None
         p.z_out = None if self._z_out is None else self._z_out.data_ptr()
         if self._world > 1:
             self._epoch += 1
@@ -551,14 +624,12 @@ class MPPI:
         action = torch.empty((self.u_per_command, self.nu), device=self.d, dtype=self.dtype)
         p.action_out = action.data_ptr()
         self._cmd_count += 1
+        self._last = None
         return p, action
 
     def _finish_command(self, p, action, stream):
         if self._world > 1 and self._exchange != "p2p":
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self._gathered, self._partial, group=self._pg)
-            p.flags &= ~_cabi.FLAG_EXPORT_PARTIAL
-            _cabi.check(self._lib.mppi_apply_partials(C.byref(p), self._gathered.data_ptr(), stream), "mppi_apply_partials")
+            self._finish_exported(action, stream)
         self.cost_total = self._cost_buf
         self._states = None
         self._actions = None
@@ -566,44 +637,39 @@ class MPPI:
             return action[0]
         return action
 
-    def _command_fused(self, state, shift):
-        p, action = self._begin_command(state, shift)
-        stream = torch.cuda.current_stream(self.d).cuda_stream
-        rc = self._lib.mppi_fused_command(C.byref(p), stream)
-        if rc != 0:
-            _cabi.check(rc, "mppi_fused_command")
-        return self._finish_command(p, action, stream)
-
     def command_host(self, state, shift_nominal_trajectory=True, info=None):
         """`command()` for a control loop that lives on the host: the start state travels in the
         kernel's parameter block (no H2D copy) and the kernel stores the action straight into pinned
-        host memory, then an epoch flag the host spins on — no D2H memcpy call, no stream
-        synchronise.  Returns a CPU tensor ((nu,) or (u_per_command, nu)); the device-side state
-        (U, cost_total, ...) is exactly what `command()` leaves."""
-        if self._host_box is None:
-            words = 2 + (self.u_per_command * self.nu * _ES[self.dtype] + 7) // 8
-            self._host_box = torch.zeros(words, dtype=torch.int64).pin_memory()
-            self._host_flag = self._host_box.numpy()[:1]
-            self._host_vals = self._host_box[2:].view(self.dtype)[: self.u_per_command * self.nu].view(self.u_per_command, self.nu)
-        self._host_epoch += 1
+        host memory followed by an epoch flag; the C library spins on that flag — no D2H memcpy call,
+        no stream synchronise.  Returns a CPU tensor ((nu,) or (u_per_command, nu)); the device-side
+        state (U, cost_total, ...) is exactly what `command()` leaves."""
+        self.info = info
         if self._dirty:
-            self._pack()          # (re)packing clears the mailbox fields, so do it first
-        p = self._p
-        p.host_mailbox = self._host_box.data_ptr()
-        p.host_epoch = self._host_epoch
-        try:
-            self.command(state, shift_nominal_trajectory, info)
-        finally:
-            p.host_mailbox = None
-        flag, want = self._host_flag, self._host_epoch
-        spins = 0
-        while flag[0] != want:
-            spins += 1
-            if spins > 50_000_000:
-                torch.cuda.synchronize(self.d)
-                if flag[0] != want:
-                    raise RuntimeError("command_host: the kernel never published its result")
-        out = self._host_vals.clone()
+            self._pack()
+        if self._model is None or (torch.is_tensor(state) and state.is_cuda) or self._world > 1 and self._exchange != "p2p":
+            out = self.command(state, shift_nominal_trajectory, info)      # stepped / device-state / NCCL route
+            return out.cpu()
+        if self._host_box is None:
+            nbytes = 16 + self.u_per_command * self.nu * _ES[self.dtype]
+            self._host_box = torch.zeros((nbytes + 7) // 8, dtype=torch.int64).pin_memory()
+        sflags, sdev = self._host_state(state)
+        if sdev is not None:
+            return self.command(state, shift_nominal_trajectory, info).cpu()
+        flags = self._base_flags | (_cabi.FLAG_SHIFT if shift_nominal_trajectory else 0)
+        zptr, seed, off = self._noise_source()
+        stream = torch._C._cuda_getCurrentRawStream(self.d.index)
+        self._last = (flags, seed, off, zptr, None)
+        self._cmd_count += 1
+        rc = self._lib.mppi_plan_command_host(self._plan, self._state_arr, flags, seed, off, zptr,
+                                              self._scratch_action.data_ptr(), self._host_box.data_ptr(), self._host_out, stream)
+        if rc != 0:
+            _cabi.check(rc, "mppi_plan_command_host")
+        if self._world > 1:
+            self._epoch += 1
+        self.cost_total = self._cost_buf
+        self._states = None
+        self._actions = None
+        out = torch.tensor(self._host_out[:], dtype=self.dtype).view(self.u_per_command, self.nu)
         return out[0] if self.u_per_command == 1 else out
 
     # ------------------------------------------------------------------------------------------
@@ -626,7 +692,7 @@ class MPPI:
         if not torch.is_tensor(state):
             state = torch.tensor(state)
         st = state.to(dtype=self.dtype, device=self.d)                                     # mppi.py:262-264
-        p, action = self._begin_command(st if st.dim() == 1 else st.reshape(-1)[: self.nx], shift)
+        p, action = self._begin_command(st, shift)
         self.state = st
         stream = torch.cuda.current_stream(self.d).cuda_stream
         K, T, nu = self._K_local, self.T, self.nu
@@ -750,6 +816,8 @@ class MPPI:
             return True
         self._ensure_step_buffers()
         p = self._p
+        if getattr(self, "_last", None) is not None:
+            self._sync_params_for_materialize()
         stream = torch.cuda.current_stream(self.d).cuda_stream
         nth = None if self._noise_theta_buf is None else self._noise_theta_buf.data_ptr()
         st_ptr = None

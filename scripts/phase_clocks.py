@@ -19,7 +19,8 @@ for _ in range(5):
     ctrl.command(x)
 nb = ctrl.launch_info.grid_blocks
 dbg = torch.zeros(nb, 16, dtype=torch.int64, device="cuda")
-ctrl._p.debug_clocks = dbg.data_ptr()
+ctrl._debug_clocks = dbg
+ctrl._dirty = True
 names = ["start", "staged", "filled", "transformed", "rolled", "folded", "published", "end(last)", "L:fence", "L:beta", "L:eta", "L:numer"]
 for rep in range(3):
     dbg.zero_()
