@@ -190,33 +190,83 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     int rc = get_dev_info(di);
     if (rc) return rc;
     const int R = rows_of(p);
-    // BS samples per tile; tps threads share one sample's sampling/transform work.  Small problems
-    // (fewer tiles than SMs) cannot fill the machine with one thread per sample, so they get
-    // 4 (or 2) threads per sample; large ones already have the thread-level parallelism.
+    // BS samples per tile; tps threads share one sample's sampling/transform work.
+    //
+    // Automatic geometry (block_threads == 0): blocks are statically assigned tiles (determinism:
+    // the reduction order must not depend on scheduling), so the finish time follows the most
+    // loaded SM.  Enumerate BS in steps of a warp and j = resident CTAs per SM, size the grid as
+    // min(n_tiles, SMs*j), and keep the candidate with the smallest worst-case samples per SM
+    // (ties: fewer passes, then more threads).  Measured on B200 (scripts/geom_sweep.py) this picks
+    // the winners of an exhaustive sweep within ~3 %: e.g. K=131072 -> BS=448, 293 CTAs, one pass.
     int BS = p->block_threads;
-    if (BS <= 0) BS = (p->K <= di.sm_count * 128 * 2) ? 128 : 256;
+    int tps = p->threads_per_sample;
+    int grid_hint = 0;
+    if (BS <= 0) {
+        cudaFuncAttributes fa0;
+        CK(cudaFuncGetAttributes(&fa0, kernel));
+        const int dyn0 = di.max_smem_optin - (int)fa0.sharedSizeBytes;
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn0));
+        long long best_load = -1;
+        int best_bs = 128, best_passes = 0, best_grid = 0;
+        for (int bs = 128; bs <= 512; bs += 32) {
+            SmemLayout Lc = layout(p->variant, p->T, p->nu, p->S, R, bs, bs, single_partial_grid ? 1 : di.sm_count * 4, need_rows2);
+            if (Lc.total > dyn0) continue;
+            int occ_c = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, kernel, bs, Lc.total));
+            if (occ_c < 1) continue;
+            const int nt = (p->K + bs - 1) / bs;
+            for (int j = 1; j <= occ_c && j <= 8; ++j) {
+                const int nbc = nt < di.sm_count * j ? nt : di.sm_count * j;
+                const int passes = (nt + nbc - 1) / nbc;
+                const int bps = (nbc + di.sm_count - 1) / di.sm_count;
+                const long long load = (long long)bps * passes * bs;
+                const bool better = best_load < 0 || load < best_load ||
+                                    (load == best_load && (passes < best_passes || (passes == best_passes && bs > best_bs)));
+                if (better) {
+                    best_load = load;
+                    best_bs = bs;
+                    best_passes = passes;
+                    best_grid = nbc;
+                }
+            }
+        }
+        BS = best_bs;
+        grid_hint = best_grid;
+    }
     if (BS % 32 != 0 || BS < 32 || BS > 512) return MPPI_ERR_BAD_ARG;
     const int n_tiles = (p->K + BS - 1) / BS;
-    int tps = p->threads_per_sample;
-    if (tps <= 0) tps = (n_tiles <= di.sm_count) ? 4 : (n_tiles <= 2 * di.sm_count ? 2 : 1);
+    if (tps <= 0) {
+        // helper threads only pay off while an SM hosts a single small CTA
+        tps = 1;
+        if (n_tiles <= di.sm_count) tps = 512 / BS >= 4 ? 4 : (512 / BS >= 2 ? 2 : 1);
+    }
     while (tps > 1 && BS * tps > 512) tps >>= 1;
     if (tps != 1 && tps != 2 && tps != 4) return MPPI_ERR_BAD_ARG;
     const int BD = BS * tps;
     const int cap = di.sm_count * 16;
-    SmemLayout L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : cap, need_rows2);
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, kernel));
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;   // static + dynamic <= opt-in maximum
-    if (L.total > dyn_limit) return MPPI_ERR_UNSUPPORTED;
     // The attribute is a per-kernel LIMIT (setting a smaller value later lowers it), so raise it
     // once to the device maximum; the carve-out actually used follows each launch's request.
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
+    // The layout depends on the grid (rescale factors of nb partials live in shared memory) and the
+    // grid on the occupancy the layout allows: iterate from an optimistic guess to a fixed point.
+    int nb = n_tiles < cap ? n_tiles : cap;
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
-    if (occ < 1) return MPPI_ERR_UNSUPPORTED;
-    int nb = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
-    if (nb > cap) nb = cap;
-    if (p->grid_blocks > 0 && p->grid_blocks < nb) nb = p->grid_blocks;
+    SmemLayout L;
+    for (int it = 0; it < 4; ++it) {
+        L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : nb, need_rows2);
+        if (L.total > dyn_limit) return MPPI_ERR_UNSUPPORTED;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
+        if (occ < 1) return MPPI_ERR_UNSUPPORTED;
+        int nb2 = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
+        if (nb2 > cap) nb2 = cap;
+        if (p->grid_blocks > 0 && p->grid_blocks < nb2) nb2 = p->grid_blocks;
+        if (grid_hint > 0 && grid_hint < nb2) nb2 = grid_hint;
+        if (nb2 == nb) break;
+        nb = nb2;
+    }
     L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : nb, need_rows2);
     g.BS = BS;
     g.tps = tps;

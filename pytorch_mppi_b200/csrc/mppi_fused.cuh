@@ -624,16 +624,18 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
         a.etaP[b] = eta_run;
     }
     for (int j = tid; j < R; j += BD) a.VP[(size_t)b * R + j] = sm.Vrun[j];
-    __threadfence();
+    // release: the CTA barrier orders every thread's stores before thread 0, whose single gpu-scope
+    // fence + ticket increment publishes them (one MEMBAR per CTA instead of one per warp)
     __syncthreads();
     if (tid == 0) {
+        __threadfence();
         const unsigned int t = atomicAdd(a.ticket, 1u);
         s_is_last = (t == gridDim.x - 1);
+        if (s_is_last) __threadfence();   // acquire side for the partials read below
     }
     __syncthreads();
     stamp(a.dbg, 6);
     if (!s_is_last) return;
-    __threadfence();
     stamp(a.dbg, 8);
 
     // The partials were written by other SMs before their ticket increments; this CTA has not

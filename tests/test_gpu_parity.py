@@ -204,3 +204,103 @@ def test_command_host_zero_copy_equals_command():
                 acts.append(a.clone())
             outs.append(torch.stack(acts))
         assert torch.equal(outs[0], outs[1])
+
+
+def _mlp_dynamics(dtype, device, seed=25):
+    """BASELINE config 4 workload (/root/reference/tests/pendulum_approximate.py:47-67): residual MLP
+    Linear(3,32)-tanh-Linear(32,32)-tanh-Linear(32,2) on [state, clamp(u)], then angle-normalise theta."""
+    import math
+    torch.manual_seed(seed)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                              torch.nn.Linear(32, 2)).to(dtype)
+    net_d = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                                torch.nn.Linear(32, 2)).to(dtype).to(device)
+    net_d.load_state_dict(net.state_dict())
+
+    def make(n):
+        def dynamics(state, action):
+            with torch.no_grad():
+                u = torch.clamp(action, -2.0, 2.0)
+                xu = torch.cat((state, u), dim=1)
+                nxt = state + n(xu)
+                th = ((nxt[:, 0] + math.pi) % (2 * math.pi)) - math.pi
+                return torch.stack((th, nxt[:, 1]), dim=1)
+        return dynamics
+
+    def cost(state, action):
+        th = ((state[:, 0] + math.pi) % (2 * math.pi)) - math.pi
+        return th ** 2 + 0.1 * state[:, 1] ** 2
+    return make(net), make(net_d), cost
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-5)])
+def test_mlp_dynamics_stepped_route_matches_oracle(dtype, tol):
+    """Config 4 shape (K reduced): a torch MLP is an arbitrary callable -> stepped route; injected noise;
+    compared with the oracle running the same weights on the CPU."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    dyn_cpu, dyn_gpu, cost = _mlp_dynamics(dtype, "cuda")
+    K, T = 4096, 30
+    g = torch.Generator().manual_seed(1)
+    U0 = torch.randn(T, 1, generator=g, dtype=dtype)
+    prob = orc.Problem(dyn_cpu, cost, 2, torch.tensor(1.0, dtype=dtype), K=K, T=T, u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0))
+    ctrl = eng.MPPI(dyn_gpu, cost, 2, torch.tensor(1.0, dtype=dtype), num_samples=K, horizon=T, U_init=U0.clone(),
+                    u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda")
+    assert ctrl._model is None
+    U = U0.clone()
+    x = torch.tensor([3.0, 0.5], dtype=dtype)
+    for step in range(3):
+        z = torch.randn(K, T, 1, generator=g, dtype=dtype)
+        ctrl.inject_noise(z)
+        a = ctrl.command(x)
+        r = orc.mppi_command(prob, U, x, z)
+        U = r["U"]
+        err = float((ctrl.U.cpu() - U).abs().max())
+        assert err < tol, (step, err)
+        assert float((a.cpu() - r["action"]).abs().max()) < tol
+        ctrl.U = U
+        x = dyn_cpu(x.view(1, -1), r["action"].view(1, -1)).view(-1)
+
+
+def test_stepped_route_M_gt_1_and_action_sampler_match_oracle_semantics():
+    """rollout_samples M>1 with a variance cost (mppi.py:334-373) and a SpecificActionSampler
+    (mppi.py:387-400) against a direct torch restatement on the same injected noise."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    dt = torch.float64
+    lin = eng.LinearPoint.unit_test_env()
+    g = torch.Generator().manual_seed(3)
+    K, T, M = 256, 8, 3
+    U0 = torch.randn(T, 2, generator=g, dtype=dt) * 0.2
+
+    class Sampler(eng.SpecificActionSampler):
+        def sample_trajectories(self, state, info):
+            return torch.full((2, T, 2), 0.25, dtype=dt, device=state.device)
+
+    samp = Sampler()
+    dyn = lambda s, a: lin.dynamics(s, a)
+    cost = lambda s, a: lin.running_cost(s, a)
+    ctrl = eng.MPPI(dyn, cost, 2, torch.eye(2, dtype=dt), num_samples=K, horizon=T, U_init=U0.clone(), device="cuda",
+                    rollout_samples=M, rollout_var_cost=0.5, rollout_var_discount=0.9, sample_null_action=True,
+                    specific_action_sampler=samp, u_max=torch.tensor([1.0, 1.0], dtype=dt))
+    z = torch.randn(K, T, 2, generator=g, dtype=dt)
+    ctrl.inject_noise(z)
+    x = torch.tensor([-1.0, 0.5], dtype=dt)
+    ctrl.command(x)
+    assert (samp.start_idx, samp.end_idx) == (1, 3)
+    # restatement (deterministic dynamics: the M copies are identical, the variance term is 0)
+    olin = orc.LinearPointModel(B=lin.B, goal=lin.goal, dtype=dt)
+    prob = orc.Problem(olin.dynamics, olin.running_cost, 2, torch.eye(2, dtype=dt), K=K, T=T, u_max=torch.tensor([1.0, 1.0], dtype=dt))
+    Us = orc.shift_rows(U0.clone(), prob.u_init)
+    pa = Us + prob.colour(z)
+    pa[0] = 0
+    pa[1:3] = 0.25
+    pa = prob.clamp_u(pa)
+    noise = pa - Us
+    roll, _, _ = orc.rollout_costs(prob, x, pa)
+    total = roll + torch.sum(Us * prob.action_cost(noise), dim=(1, 2))
+    _, _, _, omega = orc.softmin_weights(total, 1.0)
+    U_want = Us + torch.einsum("k,ktn->tn", omega, noise)
+    assert float((ctrl.U.cpu() - U_want).abs().max()) < 1e-10
+    assert float((ctrl.cost_total.cpu() - total).abs().max()) < 1e-9
+    np.testing.assert_allclose(ctrl.perturbed_action.cpu().numpy(), pa.numpy(), atol=1e-12)
