@@ -81,9 +81,8 @@ template <typename real> void fill_noise_model(const MppiFusedParams* p, NoiseMo
     nm.abs_cost = (p->flags & MPPI_FLAG_ABS_COST) ? 1 : 0;
 }
 
-inline uint64_t ws_bytes(int nb, int R, int es) {
-    return 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
-}
+// workspace: [0,16) launch sequence number; then nb records of (R+2) values as flagged 8-byte words
+inline uint64_t ws_bytes(int nb, int R, int es) { return 16 + (uint64_t)nb * (R + 2) * (es / 4) * 8; }
 
 template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BS, int nb, int tps = 1) {
     memset(&a, 0, sizeof(a));
@@ -122,10 +121,8 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     // workspace carve
     if (p->workspace != nullptr) {
         unsigned char* w = (unsigned char*)p->workspace;
-        a.ticket = (unsigned int*)w;
-        a.betaP = (real*)(w + 16);
-        a.etaP = (real*)(w + 16 + align_up(nb * es, 16));
-        a.VP = (real*)(w + 16 + 2 * align_up(nb * es, 16));
+        a.seq = (unsigned int*)w;
+        a.ll = (unsigned long long*)(w + 16);
     }
     a.rank = p->rank;
     a.world = p->world <= 0 ? 1 : p->world;
@@ -208,6 +205,9 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
         CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn0));
         long long best_load = -1;
         int best_bs = 128, best_passes = 0, best_grid = 0;
+        // latency hiding needs ~24 resident warps per SM when the problem is large enough to supply them
+        const long long per_sm = ((long long)p->K + di.sm_count - 1) / di.sm_count;
+        const long long want_threads = per_sm < 768 ? per_sm : 768;
         for (int bs = 128; bs <= 512; bs += 32) {
             SmemLayout Lc = layout(p->variant, p->T, p->nu, p->S, R, bs, bs, single_partial_grid ? 1 : di.sm_count * 4, need_rows2);
             if (Lc.total > dyn0) continue;
@@ -219,7 +219,9 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
                 const int nbc = nt < di.sm_count * j ? nt : di.sm_count * j;
                 const int passes = (nt + nbc - 1) / nbc;
                 const int bps = (nbc + di.sm_count - 1) / di.sm_count;
-                const long long load = (long long)bps * passes * bs;
+                long long load = (long long)bps * passes * bs;
+                const long long resident = (long long)bps * bs;
+                if (resident < want_threads) load = load * want_threads / resident;   // under-occupied: proportionally slower
                 const bool better = best_load < 0 || load < best_load ||
                                     (load == best_load && (passes < best_passes || (passes == best_passes && bs > best_bs)));
                 if (better) {
