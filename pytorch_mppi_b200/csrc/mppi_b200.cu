@@ -81,8 +81,9 @@ template <typename real> void fill_noise_model(const MppiFusedParams* p, NoiseMo
     nm.abs_cost = (p->flags & MPPI_FLAG_ABS_COST) ? 1 : 0;
 }
 
-// workspace: [0,16) launch sequence number; then nb records of (R+2) values as flagged 8-byte words
-inline uint64_t ws_bytes(int nb, int R, int es) { return 16 + (uint64_t)nb * (R + 2) * (es / 4) * 8; }
+inline uint64_t ws_bytes(int nb, int R, int es) {
+    return 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
+}
 
 template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BS, int nb, int tps = 1) {
     memset(&a, 0, sizeof(a));
@@ -121,8 +122,10 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     // workspace carve
     if (p->workspace != nullptr) {
         unsigned char* w = (unsigned char*)p->workspace;
-        a.seq = (unsigned int*)w;
-        a.ll = (unsigned long long*)(w + 16);
+        a.ticket = (unsigned int*)w;
+        a.betaP = (real*)(w + 16);
+        a.etaP = (real*)(w + 16 + align_up(nb * es, 16));
+        a.VP = (real*)(w + 16 + 2 * align_up(nb * es, 16));
     }
     a.rank = p->rank;
     a.world = p->world <= 0 ? 1 : p->world;

@@ -9,7 +9,7 @@
 //      bulk copy), clamp -> the tile now holds the perturbed actions (KMPPI: the control points)
 //   C. T-step rollout with the state in registers, cost accumulated in the reference's op order
 //   D. online-softmin fold of the tile into the CTA's running partial (beta_b, eta_b, V_b[R])
-// CTA 0 polls the flagged per-CTA records, rescales all partials to the global beta, optionally
+// The last CTA to finish (atomic ticket) rescales all CTA partials to the global beta, optionally
 // exchanges the rank partial with peer GPUs through NVLink mailboxes, and writes the updated nominal
 // sequence: `U += sum_k w_k eps_k / eta` lands without a second launch.
 //
@@ -52,9 +52,11 @@ template <typename real> struct KArgs {
     double* stats;
     const real* z;
     real* z_out;
-    // workspace carve: launch sequence number + flagged per-CTA records
-    unsigned int* seq;
-    unsigned long long* ll;
+    // workspace carve
+    unsigned int* ticket;
+    real* betaP;
+    real* etaP;
+    real* VP;
     // multi-GPU
     unsigned long long* peers[8];
     double* partial_out;
@@ -161,15 +163,6 @@ __device__ __forceinline__ void stamp(unsigned long long* dbg, int slot) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         dbg[(size_t)blockIdx.x * 16 + slot] = t;
     }
-}
-
-__device__ __forceinline__ void st_peer(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_poll(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
 }
 
 // ---- block reductions (deterministic: fixed shuffle tree, fixed warp order) ----------------------
@@ -489,6 +482,14 @@ __device__ void fold_tile(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool
 
 // ---- peer exchange over NVLink mailboxes (LL-style 8-byte records: payload32 | flag32) ----------
 // mailbox layout per rank: [2 parity][MPPI_MAX_RANKS src][MPPI_XCHG_MAX_WORDS] u64
+__device__ __forceinline__ void st_peer(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_poll(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // numd[0]=beta, numd[1]=eta, numd[2..2+R) = numerators of THIS rank; on return they hold the
 // all-rank combination (bit-identical on every rank).  Returns 0, or 1 on timeout.
@@ -609,106 +610,58 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
     }
 }
 
-// ---- flagged words: 8 bytes = 32-bit payload | 32-bit launch sequence number ------------------------
-// A record word is valid for this launch iff its flag equals the launch's sequence number, so the
-// consumer needs neither a fence nor a ticket: it polls, and payload + flag arrive in one 8-byte store.
-template <typename real> struct LLWord;
-template <> struct LLWord<float> {
-    static const int WPR = 1;
-    __device__ static __forceinline__ void store(unsigned long long* p, float v, uint32_t flag) {
-        st_peer(p, ((unsigned long long)flag << 32) | (unsigned long long)__float_as_uint(v));
-    }
-    // returns true and the value once the word carries `flag`
-    __device__ static __forceinline__ bool try_load(const unsigned long long* p, uint32_t flag, float& v) {
-        const unsigned long long w = ld_poll(p);
-        if ((uint32_t)(w >> 32) != flag) return false;
-        v = __uint_as_float((uint32_t)w);
-        return true;
-    }
-};
-template <> struct LLWord<double> {
-    static const int WPR = 2;
-    __device__ static __forceinline__ void store(unsigned long long* p, double v, uint32_t flag) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-        st_peer(p, ((unsigned long long)flag << 32) | (bits & 0xffffffffull));
-        st_peer(p + 1, ((unsigned long long)flag << 32) | (bits >> 32));
-    }
-    __device__ static __forceinline__ bool try_load(const unsigned long long* p, uint32_t flag, double& v) {
-        const unsigned long long w0 = ld_poll(p), w1 = ld_poll(p + 1);
-        if ((uint32_t)(w0 >> 32) != flag || (uint32_t)(w1 >> 32) != flag) return false;
-        v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
-        return true;
-    }
-};
-
-// spin until `n` (<= 8) words are valid; all polls of one sweep are in flight together
-template <typename real>
-__device__ __forceinline__ bool poll_many(const unsigned long long* const* ptrs, int n, uint32_t flag, real* vals, long long t0) {
-    unsigned pend = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
-    while (pend) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (pend & (1u << u)) {
-                real v;
-                if (LLWord<real>::try_load(ptrs[u], flag, v)) {
-                    vals[u] = v;
-                    pend &= ~(1u << u);
-                }
-            }
-        if (pend && clock64() - t0 > 4000000000ll) return false;
-    }
-    return true;
-}
-
-// ---- tail: publish the CTA record; CTA 0 combines, exchanges, updates ------------------------------
-// Every CTA stores its (V_b[R], beta_b, eta_b) as flagged words and exits; CTA 0 polls all records
-// (the grid never exceeds the resident capacity, so every producer is running or done), which puts
-// ONE global-memory round trip between the last CTA's stores and the combination.
+// ---- tail: publish the CTA partial; the last CTA combines, exchanges, updates ----------------------
 template <typename real, int VARIANT, int NU>
-__device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real beta_run, real eta_run, uint32_t flag) {
+__device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real beta_run, real eta_run) {
     typedef Ops<real> O;
-    typedef LLWord<real> W;
     const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
-    const int R = a.R, TN = a.TN, RW = a.R + 2;
+    const int R = a.R, TN = a.TN;
     const real nfl = a.nm.neg_inv_lambda;
-    const int b = blockIdx.x, nb = gridDim.x;
-    unsigned long long* mine = a.ll + (size_t)b * RW * W::WPR;
-    for (int i = tid; i < RW; i += BD) {
-        const real v = i < R ? sm.Vrun[i] : (i == R ? beta_run : eta_run);
-        W::store(mine + (size_t)i * W::WPR, v, flag);
+    __shared__ int s_is_last;
+    const int b = blockIdx.x;
+    if (tid == 0) {
+        a.betaP[b] = beta_run;
+        a.etaP[b] = eta_run;
     }
+    for (int j = tid; j < R; j += BD) a.VP[(size_t)b * R + j] = sm.Vrun[j];
+    // release: the CTA barrier orders every thread's stores before thread 0, whose single gpu-scope
+    // fence + ticket increment publishes them (one MEMBAR per CTA instead of one per warp)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(a.ticket, 1u);
+        s_is_last = (t == gridDim.x - 1);
+        if (s_is_last) __threadfence();   // acquire side for the partials read below
+    }
+    __syncthreads();
     stamp(a.dbg, 6);
-    if (b != 0) return;
+    if (!s_is_last) return;
+    stamp(a.dbg, 8);
 
-    __shared__ int s_fail;
-    if (tid == 0) s_fail = 0;
-    const long long t0 = clock64();
+    // The partials were written by other SMs before their ticket increments; this CTA has not
+    // touched those lines during this launch, and __ldcg reads them from L2.  Every load whose
+    // address does not depend on beta is issued up front (one L2 round trip for the common case),
+    // the scalar part (beta, eta, rescale factors) is done by warp 0 with shuffles only, and three
+    // barriers separate the remaining stages.
+    const int nb = gridDim.x;
+    const real* betaP = a.betaP;
+    const real* etaP = a.etaP;
+    const real* VP = a.VP;
     real* sB = sm.sS;            // [nb] beta_q, then rescale factors s_q
     real* sE = sm.sS + nb;       // [nb] eta_q
-    bool ok = true;
-    // warp 0 first collects the scalars of every record
+    real vpre[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int q = warp + u * nw;
+        vpre[u] = (lane < R && q < nb) ? __ldcg(VP + (size_t)q * R + lane) : (real)0;
+    }
     if (warp == 0) {
         real bl = O::inf();
-        for (int q0 = lane; q0 < nb; q0 += 32 * 4) {
-            const unsigned long long* ptrs[8];
-            real vals[8];
-            int n = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = q0 + 32 * u;
-                if (q < nb) {
-                    ptrs[n++] = a.ll + ((size_t)q * RW + R) * W::WPR;
-                    ptrs[n++] = a.ll + ((size_t)q * RW + R + 1) * W::WPR;
-                }
-            }
-            for (int u = n; u < 8; ++u) ptrs[u] = ptrs[0];
-            ok = poll_many<real>(ptrs, n, flag, vals, t0) && ok;
-            for (int u = 0; u < n; u += 2) {
-                const int q = q0 + 32 * (u >> 1);
-                sB[q] = vals[u];
-                sE[q] = vals[u + 1];
-                bl = vals[u] < bl ? vals[u] : bl;
-            }
+        for (int q = lane; q < nb; q += 32) {
+            const real bq = __ldcg(betaP + q);
+            sB[q] = bq;
+            sE[q] = __ldcg(etaP + q);
+            bl = bq < bl ? bq : bl;
         }
         const real beta = warp_min<real>(bl);
         __syncwarp();
@@ -722,29 +675,11 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
         if (lane == 0) {
             sm.numd[0] = (double)beta;
             sm.numd[1] = eta;
+            *a.ticket = 0u;   // self-reset: the next launch needs no memset
         }
     }
-    // every warp collects its share of the V words: rows j = lane (+32..), records q = warp (+nw..)
-    real vpre[8];
-    {
-        const unsigned long long* ptrs[8];
-        int n = 0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int q = warp + u * nw;
-            vpre[u] = (real)0;
-            if (lane < R && q < nb) ptrs[n++] = a.ll + ((size_t)q * RW + lane) * W::WPR;
-        }
-        for (int u = n; u < 8; ++u) ptrs[u] = a.ll;
-        if (n > 0) ok = poll_many<real>(ptrs, n, flag, vpre, t0) && ok;   // n valid slots are the first n (q ascending)
-    }
-    if (!ok) s_fail = 1;
     __syncthreads();
     stamp(a.dbg, 10);
-    if (s_fail) {
-        if (tid == 0) a.stats[3] = -6.0;   // MPPI_ERR_TIMEOUT: a producer CTA never published
-        return;
-    }
     for (int j = lane; j < R; j += 32) {
         double acc = 0.0;
         int q = warp;
@@ -756,13 +691,14 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
             }
             q = warp + 8 * nw;
         }
-        for (; q < nb; q += nw) {
-            real v;
-            while (!W::try_load(a.ll + ((size_t)q * RW + j) * W::WPR, flag, v)) {
-                if (clock64() - t0 > 4000000000ll) { s_fail = 1; break; }
-            }
-            acc += (double)sB[q] * (double)v;
+        for (; q + 7 * nw < nb; q += 8 * nw) {
+            real v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(VP + (size_t)(q + u * nw) * R + j);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += (double)sB[q + u * nw] * (double)v[u];
         }
+        for (; q < nb; q += nw) acc += (double)sB[q] * (double)__ldcg(VP + (size_t)q * R + j);
         sm.part2[warp * R + j] = acc;
     }
     __syncthreads();
@@ -771,13 +707,8 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
         for (int q = 1; q < nw; ++q) s2 += sm.part2[q * R + j];
         sm.numd[2 + j] = s2;
     }
-    if (tid == 0) *a.seq = flag;   // the next launch on this stream uses flag + 1
     __syncthreads();
     stamp(a.dbg, 11);
-    if (s_fail) {
-        if (tid == 0) a.stats[3] = -6.0;
-        return;
-    }
 
     if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
         for (int j = tid; j < R + 2; j += BD) a.partial_out[j] = sm.numd[j];
@@ -820,8 +751,6 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
 
-    __shared__ uint32_t s_flag;
-    if (tid == 0) s_flag = __ldcg(a.seq) + 1u;     // consumed at publish time, many barriers from here
     stamp(a.dbg, 0);
     stage_issue<real, VARIANT, NU>(a, sm);
     stamp(a.dbg, 1);
@@ -913,7 +842,7 @@ MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
         if (tile == blockIdx.x) stamp(a.dbg, 5);
     }
     if (!staged) stage_finish<real, VARIANT, NU>(a, sm);
-    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run, s_flag);
+    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
     stamp(a.dbg, 7);
 }
 
@@ -1060,8 +989,6 @@ __global__ void __launch_bounds__(512) softmin_update_kernel(const KArgs<real> a
         for (int j = tid; j < a.T * a.S; j += BD) sm.Ws[j] = a.W[j];
     }
     for (int j = tid; j < R; j += BD) sm.Vrun[j] = (real)0;
-    __shared__ uint32_t s_flag;
-    if (tid == 0) s_flag = __ldcg(a.seq) + 1u;
     __syncthreads();
     real beta_run = O::inf(), eta_run = (real)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -1078,7 +1005,7 @@ __global__ void __launch_bounds__(512) softmin_update_kernel(const KArgs<real> a
         real w;
         fold_tile<real, VARIANT, true>(a, sm, c, active, nvalid, beta_run, eta_run, w);   // first barrier inside publishes rows
     }
-    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run, s_flag);
+    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
 }
 
 // omega_k = exp(-(c_k - beta)/lambda) / eta from the stats a command left behind (mppi.py:256-258)
