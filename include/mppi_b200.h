@@ -67,8 +67,11 @@ enum {
     MPPI_FLAG_STATE_PER_SAMPLE = 1u << 5, /* state_dev is (K,nx): one start state per sample (:302-303)          */
     MPPI_FLAG_EXPORT_PARTIAL = 1u << 6,   /* multi-GPU, library collective: write this rank's (beta,eta,V) to
                                              partial_out and do NOT update U (mppi_apply_partials finishes)    */
-    MPPI_FLAG_NOMINAL_PADDED = 1u << 7    /* U (and A) are 16-byte aligned allocations padded to a multiple of
+    MPPI_FLAG_NOMINAL_PADDED = 1u << 7,   /* U (and A) are 16-byte aligned allocations padded to a multiple of
                                              16 bytes: lets the kernel stage them with one TMA bulk copy        */
+    MPPI_FLAG_PDL = 1u << 8               /* programmatic dependent launch: the kernel may start while the previous
+                                             kernel on the stream is finishing; it draws its Philox normals (shared
+                                             memory only) and touches global memory only after griddepcontrol.wait */
 };
 
 /* One `command()` of a registered analytic model: replaces, in one launch,

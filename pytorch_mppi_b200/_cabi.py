@@ -29,6 +29,7 @@ FLAG_STATE_DEVICE = 1 << 4
 FLAG_STATE_PER_SAMPLE = 1 << 5
 FLAG_EXPORT_PARTIAL = 1 << 6
 FLAG_NOMINAL_PADDED = 1 << 7
+FLAG_PDL = 1 << 8
 
 STATUS = {0: "ok", -1: "bad argument", -2: "unsupported", -3: "workspace too small", -4: "CUDA error",
           -5: "ABI mismatch", -6: "peer exchange timeout"}

@@ -116,6 +116,7 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     a.offset = p->offset;
     a.shift = (p->flags & MPPI_FLAG_SHIFT) ? 1 : 0;
     a.null_action = (p->flags & MPPI_FLAG_NULL_ACTION) ? 1 : 0;
+    a.pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
     const int es = (int)sizeof(real);
     const bool padded = (p->flags & MPPI_FLAG_NOMINAL_PADDED) || ((a.TN * es) % 16 == 0);
     a.tma_ok = padded && ((uintptr_t)p->U % 16 == 0) && (p->variant != MPPI_VARIANT_SMPPI || (uintptr_t)p->A % 16 == 0);
@@ -142,6 +143,22 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     }
     if (!any_peer || a.export_partial) a.world = a.export_partial ? a.world : 1;
     return MPPI_OK;
+}
+
+inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cudaStream_t stream, void** argv, bool pdl) {
+    if (!pdl) return cudaLaunchKernel(kernel, dim3(nb), dim3(BD), argv, (size_t)smem, stream);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nb);
+    cfg.blockDim = dim3(BD);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, kernel, argv);
 }
 
 template <typename... Args>
@@ -326,7 +343,10 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params);
-    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a, mp);
+    void* argv2[2] = {(void*)&a, (void*)&mp};
+    cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0);
+    if (e != cudaSuccess) return cuda_fail(e, "fused launch");
+    return MPPI_OK;
 }
 
 template <class Model, typename real>
@@ -348,7 +368,7 @@ struct Plan {
     MppiFusedParams p;
     const void* kernel;
     Geometry g;
-    int is_double, nx, upc_nu;
+    int is_double, nx, upc_nu, pdl;
     unsigned long long epoch, host_epoch;
     alignas(16) unsigned char kargs[sizeof(KArgs<double>)];
     alignas(16) unsigned char mparams[1024];
@@ -372,6 +392,7 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     pl->is_double = sizeof(real) == 8;
     pl->nx = Model::NX;
     pl->upc_nu = p->u_per_command * p->nu;
+    pl->pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
     pl->epoch = p->epoch;
     pl->host_epoch = 0;
     pl->p = *p;
@@ -410,7 +431,7 @@ inline void plan_update(Plan* pl, const double* state, const void* state_dev, ui
 
 inline int plan_launch(Plan* pl, cudaStream_t stream) {
     void* argv[2] = {(void*)pl->kargs, (void*)pl->mparams};
-    cudaError_t e = cudaLaunchKernel(pl->kernel, dim3(pl->g.nb), dim3(pl->g.BD), argv, (size_t)pl->g.smem, stream);
+    cudaError_t e = launch_raw(pl->kernel, pl->g.nb, pl->g.BD, pl->g.smem, stream, argv, pl->pdl != 0);
     if (e != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "plan launch grid=%d block=%d smem=%d: %s (%s)", pl->g.nb, pl->g.BD, pl->g.smem,
                  cudaGetErrorName(e), cudaGetErrorString(e));

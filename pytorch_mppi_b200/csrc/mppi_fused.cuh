@@ -68,6 +68,7 @@ template <typename real> struct KArgs {
     unsigned long long seed, offset;
     int shift, null_action, tma_ok, state_per_sample;
     int tps;   // threads cooperating on one sample's sampling/transform phases (1, 2 or 4)
+    int pdl;   // launched with programmatic stream serialization
     unsigned long long* dbg;   // optional (grid,16) globaltimer stamps
     unsigned long long* host_mailbox;   // optional pinned host memory: [0]=epoch flag, [2..]=action values
     unsigned long long host_epoch;
@@ -752,6 +753,16 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
     const int T = a.T;
 
     stamp(a.dbg, 0);
+    // Programmatic dependent launch: this grid may be resident while the previous kernel on the stream is
+    // still finishing.  Let our own successor start early too, draw the first tile's normals (pure
+    // compute into shared memory), and only then wait for the predecessor's memory to be visible.
+    const bool early_fill = a.pdl && a.z == nullptr && a.z_out == nullptr && blockIdx.x < a.n_tiles;
+    if (a.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (early_fill) {
+        const int k0 = blockIdx.x * BS + (tid % BS);
+        fill_normals<real>(a, sm, blockIdx.x, k0 < a.K, (unsigned long long)(a.k_offset + k0), min(BS, a.K - blockIdx.x * BS));
+    }
+    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     stage_issue<real, VARIANT, NU>(a, sm);
     stamp(a.dbg, 1);
     bool staged = false;
@@ -764,7 +775,7 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a,
         const int nvalid = min(BS, a.K - tile * BS);
         const unsigned long long kg = (unsigned long long)(a.k_offset + k);
 
-        fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
+        if (!(early_fill && tile == blockIdx.x)) fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
         if (!staged) {   // the nominal sequence is first needed now; its TMA copy flew during the draws
             stage_finish<real, VARIANT, NU>(a, sm);
             staged = true;

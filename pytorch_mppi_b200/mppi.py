@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import math
 import time
 import typing
@@ -172,6 +173,7 @@ class MPPI:
             if m is not None and m.nx == self.nx and m.nu == self.nu:
                 self._model = m
         self._block_threads = int(block_threads)
+        self._pdl = os.environ.get("MPPI_B200_PDL", "1") != "0"
         self._threads_per_sample = int(threads_per_sample)
 
         # multi-GPU: K is the GLOBAL sample count, sharded over the group
@@ -350,7 +352,8 @@ class MPPI:
         self._base_flags = ((_cabi.FLAG_NULL_ACTION if self.sample_null_action else 0)
                             | (_cabi.FLAG_ABS_COST if self.noise_abs_cost else 0)
                             | (_cabi.FLAG_DIAG_SIGMA if self._diagonal_sigma else 0)
-                            | _cabi.FLAG_NOMINAL_PADDED)
+                            | _cabi.FLAG_NOMINAL_PADDED
+                            | (_cabi.FLAG_PDL if (self._pdl and self._model is not None) else 0))
         p.U = self._Ubuf.data_ptr()
         p.A = None
         p.theta = None
