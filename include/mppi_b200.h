@@ -130,9 +130,10 @@ typedef struct MppiFusedParams {
     void* peer_slots[MPPI_MAX_RANKS];   /* in-kernel exchange: pointer to every rank's mailbox (own included),
                                            from mppi_xchg_*; all NULL = no in-kernel exchange            */
     void* partial_out;           /* MPPI_FLAG_EXPORT_PARTIAL: (2 + R) doubles out                        */
-    void* host_mailbox;          /* optional PINNED HOST memory (device-visible under UVA), >= 16 + u_per_command*nu
-                                    elements: the kernel stores the action at byte 16.. and then host_epoch
-                                    at byte 0, so the host can spin on the flag instead of issuing a D2H copy */
+    void* host_mailbox;          /* optional PINNED HOST memory (device-visible under UVA), u_per_command*nu 8-byte
+                                    words (x2 for f64): the kernel stores every action value as a self-validating
+                                    word, payload32 | (host_epoch & 0xffffffff) << 32, so the host spins on the
+                                    words themselves instead of issuing a D2H copy or a stream synchronise      */
     uint64_t host_epoch;
     void* debug_clocks;          /* optional profiling aid: (grid_blocks, 16) uint64 %globaltimer stamps (ns) at
                                     phase boundaries of each CTA's first tile; NULL on the product path   */
@@ -171,11 +172,11 @@ int mppi_plan_destroy(void* plan);
 int mppi_plan_command(void* plan, const double* state, const void* state_dev, uint32_t flags, uint64_t seed,
                       uint64_t offset, const void* z, void* action_out, void* stream);
 /* One command() for a host-resident control loop: launches, then spins (in C) on the pinned-host
- * mailbox the kernel stores the action + epoch flag into, and returns the action as doubles in
- * `action_host_out` (u_per_command*nu).  No D2H memcpy call, no stream synchronise.
- * `host_mailbox`: >= 16 + u_per_command*nu*sizeof(dtype) bytes of pinned host memory. */
+ * mailbox the kernel stores the flagged action words into, and returns the action in
+ * `action_host_out` (u_per_command*nu elements of the controller dtype).  No D2H memcpy call, no stream synchronise.
+ * `host_mailbox`: u_per_command*nu*8 bytes (x2 for f64) of zero-initialised pinned host memory. */
 int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset,
-                           const void* z, void* action_out_dev, void* host_mailbox, double* action_host_out, void* stream);
+                           const void* z, void* action_out_dev, void* host_mailbox, void* action_host_out, void* stream);
 
 /* Multi-GPU, library-collective route: after every rank exported its partial and the caller
  * all-gathered them (NCCL), finish the update on each rank: beta=min, rescale, U += sum/eta

@@ -643,7 +643,7 @@ int mppi_plan_command(void* plan, const double* state, const void* state_dev, ui
 }
 
 int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset, const void* z,
-                           void* action_out_dev, void* host_mailbox, double* action_host_out, void* stream) {
+                           void* action_out_dev, void* host_mailbox, void* action_host_out, void* stream) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
     if (pl == nullptr || state == nullptr || host_mailbox == nullptr || action_host_out == nullptr || action_out_dev == nullptr)
         return MPPI_ERR_BAD_ARG;
@@ -651,24 +651,31 @@ int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint
     else plan_update<float>(pl, state, nullptr, flags, seed, offset, z, action_out_dev, host_mailbox);
     int rc = plan_launch(pl, (cudaStream_t)stream);
     if (rc) return rc;
-    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(host_mailbox);
-    const unsigned long long want = pl->host_epoch;
+    // every action value arrives as self-validating 8-byte word(s): payload32 | (epoch & 0xffffffff) << 32
+    volatile unsigned long long* box = reinterpret_cast<volatile unsigned long long*>(host_mailbox);
+    const unsigned long long want = pl->host_epoch & 0xffffffffull;
+    const int nwords = pl->upc_nu * (pl->is_double ? 2 : 1);
     unsigned long long spins = 0;
-    while (*flag != want) {
+    for (int w = 0; w < nwords; ++w) {
+        while ((box[w] >> 32) != want) {
 #if defined(__x86_64__)
-        __builtin_ia32_pause();
+            __builtin_ia32_pause();
 #endif
-        if ((++spins & 0xFFFFF) == 0) {           // every ~1M spins: has the stream died or finished without publishing?
-            cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery while waiting for the mailbox");
-            if (q == cudaSuccess && *flag != want) return MPPI_ERR_TIMEOUT;
+            if ((++spins & 0xFFFFF) == 0) {       // every ~1M spins: has the stream died or finished without publishing?
+                cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery while waiting for the mailbox");
+                if (q == cudaSuccess && (box[w] >> 32) != want) return MPPI_ERR_TIMEOUT;
+            }
         }
     }
-    const unsigned char* vals = reinterpret_cast<const unsigned char*>(host_mailbox) + 16;
-    if (pl->is_double)
-        for (int i = 0; i < pl->upc_nu; ++i) action_host_out[i] = reinterpret_cast<const volatile double*>(vals)[i];
-    else
-        for (int i = 0; i < pl->upc_nu; ++i) action_host_out[i] = (double)reinterpret_cast<const volatile float*>(vals)[i];
+    // the action is returned in the controller's own dtype (f32 words or f64 double-words)
+    if (pl->is_double) {
+        unsigned long long* out = reinterpret_cast<unsigned long long*>(action_host_out);
+        for (int i = 0; i < pl->upc_nu; ++i) out[i] = (box[2 * i] & 0xffffffffull) | (box[2 * i + 1] << 32);
+    } else {
+        uint32_t* out = reinterpret_cast<uint32_t*>(action_host_out);
+        for (int i = 0; i < pl->upc_nu; ++i) out[i] = (uint32_t)box[i];
+    }
     return MPPI_OK;
 }
 

@@ -539,6 +539,20 @@ __device__ int exchange_partials(const KArgs<real>& a, double* numd, double* scr
     return 0;
 }
 
+// value i of the action as flagged 8-byte word(s) in pinned host memory (float: 1 word, double: 2)
+template <typename real>
+__device__ __forceinline__ void host_store(unsigned long long* box, int i, real v, unsigned long long epoch);
+template <>
+__device__ __forceinline__ void host_store<float>(unsigned long long* box, int i, float v, unsigned long long epoch) {
+    st_peer(box + i, ((epoch & 0xffffffffull) << 32) | (unsigned long long)__float_as_uint(v));
+}
+template <>
+__device__ __forceinline__ void host_store<double>(unsigned long long* box, int i, double v, unsigned long long epoch) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_peer(box + 2 * i, ((epoch & 0xffffffffull) << 32) | (bits & 0xffffffffull));
+    st_peer(box + 2 * i + 1, ((epoch & 0xffffffffull) << 32) | (bits >> 32));
+}
+
 // ---- final update from (beta, eta, numerators) with the post-shift nominal in shared memory -----
 template <typename real, int VARIANT>
 __device__ void finish_update(const KArgs<real>& a, const double* numd, const real* Us, const real* As, real* ths,
@@ -559,14 +573,16 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
         a.stats[0] = numd[0];
         a.stats[1] = eta;
     }
-    real* hact = a.host_mailbox != nullptr ? reinterpret_cast<real*>(a.host_mailbox + 2) : nullptr;
+    // Host delivery: each action value goes out as self-validating 8-byte words (payload32 | epoch32), so
+    // the host sees a value as soon as its own store lands — no system-wide fence, no separate flag.
+    unsigned long long* hact = a.host_mailbox;
     if (VARIANT == V_MPPI) {
         for (int j = tid; j < TN; j += BD) {
             const real un = O::add(Us[j], (real)(numd[2 + j] * inv_eta));                // mppi.py:270
             a.U[j] = un;
             if (j < a.upc * nu) {                                                          // mppi.py:271-275
                 a.action_out[j] = un;
-                if (hact != nullptr) hact[j] = un;
+                if (hact != nullptr) host_store<real>(hact, j, un, a.host_epoch);
             }
         }
     } else if (VARIANT == V_SMPPI) {
@@ -577,7 +593,7 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
             a.A[j] = an;
             if (j < a.upc * nu) {                                                          // mppi.py:533-537
                 a.action_out[j] = an;
-                if (hact != nullptr) hact[j] = an;
+                if (hact != nullptr) host_store<real>(hact, j, an, a.host_epoch);
             }
         }
     } else {
@@ -596,17 +612,8 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
             a.U[j] = acc;
             if (j < a.upc * nu) {
                 a.action_out[j] = acc;
-                if (hact != nullptr) hact[j] = acc;
+                if (hact != nullptr) host_store<real>(hact, j, acc, a.host_epoch);
             }
-        }
-    }
-    if (a.host_mailbox != nullptr) {
-        // zero-copy result delivery: action words first, then the epoch flag the host spins on
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            *reinterpret_cast<volatile unsigned long long*>(a.host_mailbox) = a.host_epoch;
-            __threadfence_system();
         }
     }
 }

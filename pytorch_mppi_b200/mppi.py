@@ -404,7 +404,8 @@ class MPPI:
         self._plan = plan
         self._state_arr = (C.c_double * _cabi.MPPI_MAX_NX)()
         self._scratch_action = torch.empty((self.u_per_command, self.nu), device=self.d, dtype=self.dtype)
-        self._host_out = (C.c_double * (self.u_per_command * self.nu))()
+        self._host_res = torch.empty((self.u_per_command, self.nu), dtype=self.dtype)
+        self._host_res_ptr = self._host_res.data_ptr()
 
     def _drop_plan(self):
         plan = getattr(self, "_plan", None)
@@ -653,8 +654,8 @@ class MPPI:
             out = self.command(state, shift_nominal_trajectory, info)      # stepped / device-state / NCCL route
             return out.cpu()
         if self._host_box is None:
-            nbytes = 16 + self.u_per_command * self.nu * _ES[self.dtype]
-            self._host_box = torch.zeros((nbytes + 7) // 8, dtype=torch.int64).pin_memory()
+            words = self.u_per_command * self.nu * (2 if self.dtype == torch.float64 else 1)
+            self._host_box = torch.zeros(words, dtype=torch.int64).pin_memory()
         sflags, sdev = self._host_state(state)
         if sdev is not None:
             return self.command(state, shift_nominal_trajectory, info).cpu()
@@ -664,7 +665,7 @@ class MPPI:
         self._last = (flags, seed, off, zptr, None)
         self._cmd_count += 1
         rc = self._lib.mppi_plan_command_host(self._plan, self._state_arr, flags, seed, off, zptr,
-                                              self._scratch_action.data_ptr(), self._host_box.data_ptr(), self._host_out, stream)
+                                              self._scratch_action.data_ptr(), self._host_box.data_ptr(), self._host_res_ptr, stream)
         if rc != 0:
             _cabi.check(rc, "mppi_plan_command_host")
         if self._world > 1:
@@ -672,7 +673,7 @@ class MPPI:
         self.cost_total = self._cost_buf
         self._states = None
         self._actions = None
-        out = torch.tensor(self._host_out[:], dtype=self.dtype).view(self.u_per_command, self.nu)
+        out = self._host_res.clone()
         return out[0] if self.u_per_command == 1 else out
 
     # ------------------------------------------------------------------------------------------
