@@ -130,6 +130,12 @@ typedef struct MppiFusedParams {
     void* peer_slots[MPPI_MAX_RANKS];   /* in-kernel exchange: pointer to every rank's mailbox (own included),
                                            from mppi_xchg_*; all NULL = no in-kernel exchange            */
     void* partial_out;           /* MPPI_FLAG_EXPORT_PARTIAL: (2 + R) doubles out                        */
+    /* ---- batched environments (MPPI_Batched, mppi.py:691-873): n_env independent problems sharing one noise
+     * stream, launched as gridDim.y = n_env.  Buffers are (n_env, ...) with these strides; state_dev is
+     * (n_env, nx) on the device.  n_env <= 1 means a single problem.  MPPI variant only. */
+    int32_t n_env;
+    int32_t env_u_stride;        /* ELEMENTS between consecutive environments' U (>= T*nu, 16-byte multiple for TMA) */
+    uint64_t env_ws_stride;      /* BYTES between consecutive environments' workspace slices                       */
     void* host_mailbox;          /* optional PINNED HOST memory (device-visible under UVA), u_per_command*nu 8-byte
                                     words (x2 for f64): the kernel stores every action value as a self-validating
                                     word, payload32 | (host_epoch & 0xffffffff) << 32, so the host spins on the

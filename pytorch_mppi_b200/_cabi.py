@@ -89,6 +89,9 @@ class MppiFusedParams(C.Structure):
         ("epoch", C.c_uint64),
         ("peer_slots", C.c_void_p * MPPI_MAX_RANKS),
         ("partial_out", C.c_void_p),
+        ("n_env", C.c_int32),
+        ("env_u_stride", C.c_int32),
+        ("env_ws_stride", C.c_uint64),
         ("host_mailbox", C.c_void_p),
         ("host_epoch", C.c_uint64),
         ("debug_clocks", C.c_void_p),

@@ -43,10 +43,11 @@ int get_dev_info(DevInfo& d) {
     return MPPI_OK;
 }
 
-int validate(const MppiFusedParams* p) {
+int validate(const MppiFusedParams* p, bool fused = false) {
     if (p == nullptr) return MPPI_ERR_BAD_ARG;
     if (p->struct_size != sizeof(MppiFusedParams)) return MPPI_ERR_ABI;
-    if (p->K <= 0 || p->T <= 0 || p->nu <= 0 || p->nu > MPPI_MAX_NU || p->nx <= 0 || p->nx > MPPI_MAX_NX) return MPPI_ERR_BAD_ARG;
+    if (p->K <= 0 || p->T <= 0 || p->nu <= 0 || p->nu > MPPI_MAX_NU || p->nx <= 0) return MPPI_ERR_BAD_ARG;
+    if (fused && p->nx > MPPI_MAX_NX) return MPPI_ERR_BAD_ARG;      // state by value; the per-step entry points never touch the state
     if (p->variant < 0 || p->variant > 2) return MPPI_ERR_BAD_ARG;
     if (p->dtype != MPPI_F32 && p->dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
     if (p->variant == MPPI_VARIANT_KMPPI && (p->S <= 0 || p->W == nullptr || p->theta == nullptr)) return MPPI_ERR_BAD_ARG;
@@ -133,6 +134,9 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     a.epoch = p->epoch;
     a.export_partial = (p->flags & MPPI_FLAG_EXPORT_PARTIAL) ? 1 : 0;
     a.partial_out = (double*)p->partial_out;
+    a.n_env = p->n_env > 1 ? p->n_env : 1;
+    a.env_u_stride = p->env_u_stride;
+    a.env_ws_stride = (long long)p->env_ws_stride;
     a.dbg = (unsigned long long*)p->debug_clocks;
     a.host_mailbox = (unsigned long long*)p->host_mailbox;
     a.host_epoch = p->host_epoch;
@@ -145,11 +149,11 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     return MPPI_OK;
 }
 
-inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cudaStream_t stream, void** argv, bool pdl) {
-    if (!pdl) return cudaLaunchKernel(kernel, dim3(nb), dim3(BD), argv, (size_t)smem, stream);
+inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cudaStream_t stream, void** argv, bool pdl, int ny = 1) {
+    if (!pdl) return cudaLaunchKernel(kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(nb);
+    cfg.gridDim = dim3(nb, ny);
     cfg.blockDim = dim3(BD);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = stream;
@@ -162,9 +166,9 @@ inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cuda
 }
 
 template <typename... Args>
-int launch_kernel(void (*kernel)(Args...), int nb, int BD, int smem, cudaStream_t stream, Args... args) {
+int launch_kernel(void (*kernel)(Args...), int nb, int BD, int smem, cudaStream_t stream, int ny, Args... args) {
     void* argv[] = {(void*)&args...};
-    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(nb), dim3(BD), argv, (size_t)smem, stream);
+    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
     if (e != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "launch grid=%d block=%d smem=%d: %s (%s)", nb, BD, smem,
                  cudaGetErrorName(e), cudaGetErrorString(e));
@@ -179,10 +183,10 @@ struct Geometry {
 
 struct GeomKey {
     const void* kernel;
-    int dev, variant, K, T, nu, S, bt, tp, gb, r2, single;
+    int dev, variant, K, T, nu, S, bt, tp, gb, r2, single, ne;
     bool operator==(const GeomKey& o) const {
         return kernel == o.kernel && dev == o.dev && variant == o.variant && K == o.K && T == o.T && nu == o.nu && S == o.S &&
-               bt == o.bt && tp == o.tp && gb == o.gb && r2 == o.r2 && single == o.single;
+               bt == o.bt && tp == o.tp && gb == o.gb && r2 == o.r2 && single == o.single && ne == o.ne;
     }
 };
 
@@ -197,7 +201,7 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     int dev = 0;
     CK(cudaGetDevice(&dev));
     const GeomKey key{(const void*)kernel, dev, p->variant, p->K, p->T, p->nu, p->S, p->block_threads, p->threads_per_sample,
-                      p->grid_blocks, need_rows2, single_partial_grid ? 1 : 0};
+                      p->grid_blocks, need_rows2, single_partial_grid ? 1 : 0, p->n_env > 1 ? p->n_env : 1};
     for (int i = 0; i < n_cached; ++i)
         if (keys[i] == key) {
             g = vals[i];
@@ -260,7 +264,8 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     if (tps <= 0) {
         // helper threads only pay off while an SM hosts a single small CTA
         tps = 1;
-        if (n_tiles <= di.sm_count) tps = 512 / BS >= 4 ? 4 : (512 / BS >= 2 ? 2 : 1);
+        const int envs = p->n_env > 1 ? p->n_env : 1;
+        if ((long long)n_tiles * envs <= di.sm_count) tps = 512 / BS >= 4 ? 4 : (512 / BS >= 2 ? 2 : 1);
     }
     while (tps > 1 && BS * tps > 512) tps >>= 1;
     if (tps != 1 && tps != 2 && tps != 4) return MPPI_ERR_BAD_ARG;
@@ -313,7 +318,10 @@ template <typename real> SmemLayout layout_fn(int v, int T, int nu, int S, int R
 template <class Model, typename real, int V>
 int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    auto kernel = fused_command_kernel<Model, real, V>;
+    const bool batched = p->n_env > 1;
+    if (batched && (V != V_MPPI || p->world > 1)) return MPPI_ERR_UNSUPPORTED;
+    if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
+    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
     Geometry g;
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
     if (rc) return rc;
@@ -339,12 +347,15 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
         p->stats == nullptr || p->workspace == nullptr)
         return MPPI_ERR_BAD_ARG;
     if (p->workspace_bytes < need_ws) return MPPI_ERR_WORKSPACE;
+    if (batched && (p->env_ws_stride < need_ws || p->workspace_bytes < p->env_ws_stride * (uint64_t)p->n_env ||
+                    p->env_u_stride < p->T * p->nu))
+        return MPPI_ERR_WORKSPACE;
     if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params);
     void* argv2[2] = {(void*)&a, (void*)&mp};
-    cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0);
+    cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env);
     if (e != cudaSuccess) return cuda_fail(e, "fused launch");
     return MPPI_OK;
 }
@@ -376,7 +387,9 @@ struct Plan {
 
 template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    auto kernel = fused_command_kernel<Model, real, V>;
+    const bool batched = p->n_env > 1;
+    if (batched && (V != V_MPPI || p->world > 1)) return MPPI_ERR_UNSUPPORTED;
+    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
     if (rc) return rc;
     if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
@@ -431,7 +444,7 @@ inline void plan_update(Plan* pl, const double* state, const void* state_dev, ui
 
 inline int plan_launch(Plan* pl, cudaStream_t stream) {
     void* argv[2] = {(void*)pl->kargs, (void*)pl->mparams};
-    cudaError_t e = launch_raw(pl->kernel, pl->g.nb, pl->g.BD, pl->g.smem, stream, argv, pl->pdl != 0);
+    cudaError_t e = launch_raw(pl->kernel, pl->g.nb, pl->g.BD, pl->g.smem, stream, argv, pl->pdl != 0, pl->p.n_env > 1 ? pl->p.n_env : 1);
     if (e != cudaSuccess) {
         snprintf(g_cuda_err, sizeof(g_cuda_err), "plan launch grid=%d block=%d smem=%d: %s (%s)", pl->g.nb, pl->g.BD, pl->g.smem,
                  cudaGetErrorName(e), cudaGetErrorString(e));
@@ -441,7 +454,7 @@ inline int plan_launch(Plan* pl, cudaStream_t stream) {
 }
 
 int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
-    int rc = validate(p);
+    int rc = validate(p, true);
     if (rc) return rc;
     switch (p->model) {
         case MPPI_MODEL_PENDULUM: return run_fused_dtype<PendulumModel>(p, s, info);
@@ -474,7 +487,7 @@ int run_sample(const MppiFusedParams* p, KArgs<real>& a_extra, cudaStream_t stre
         a.tma_ok = 0;
         a.nominal_used = nullptr;
     }
-    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a);
+    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a.n_env, a);
 }
 
 template <typename real, int V> int run_sample_nu(const MppiFusedParams* p, KArgs<real>& e, cudaStream_t s) {
@@ -514,13 +527,15 @@ int run_softmin(const MppiFusedParams* p, const void* cost, const void* eps, cud
     Geometry g;
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
     if (rc) return rc;
-    if (p->workspace == nullptr || p->workspace_bytes < ws_bytes(g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
+    const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
+    if (p->workspace == nullptr || p->workspace_bytes < need_ws) return MPPI_ERR_WORKSPACE;
+    if (p->n_env > 1 && (p->env_ws_stride < need_ws || p->workspace_bytes < p->env_ws_stride * (uint64_t)p->n_env)) return MPPI_ERR_WORKSPACE;
     KArgs<real> a;
     fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
     a.in_cost = (const real*)cost;
     a.in_eps = (const real*)eps;
     if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
-    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a);
+    return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a.n_env, a);
 }
 
 template <typename real, int V> int run_softmin_nu(const MppiFusedParams* p, const void* c, const void* e, cudaStream_t s) {
@@ -609,7 +624,7 @@ int mppi_fused_command(const MppiFusedParams* p, void* stream) { return dispatch
 
 int mppi_plan_create(const MppiFusedParams* p, void** plan_out) {
     if (plan_out == nullptr) return MPPI_ERR_BAD_ARG;
-    int rc = validate(p);
+    int rc = validate(p, true);
     if (rc) return rc;
     Plan* pl = new (std::nothrow) Plan();
     if (pl == nullptr) return MPPI_ERR_BAD_ARG;

@@ -69,6 +69,11 @@ template <typename real> struct KArgs {
     int shift, null_action, tma_ok, state_per_sample;
     int tps;   // threads cooperating on one sample's sampling/transform phases (1, 2 or 4)
     int pdl;   // launched with programmatic stream serialization
+    // batched environments (MPPI_Batched, mppi.py:691-873): gridDim.y = n_env independent problems that
+    // share the noise stream; per-environment buffers are strided
+    int n_env;
+    long long env_u_stride;      // elements between consecutive environments' U
+    long long env_ws_stride;     // BYTES between consecutive environments' workspace
     unsigned long long* dbg;   // optional (grid,16) globaltimer stamps
     unsigned long long* host_mailbox;   // optional pinned host memory: [0]=epoch flag, [2..]=action values
     unsigned long long host_epoch;
@@ -744,15 +749,54 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
     if (tid == 0) a.stats[3] = 0.0;
 }
 
+// ---- per-environment view of the kernel arguments (batched launches) -------------------------------
+// The argument block lives in constant (parameter) space; a batched CTA needs its environment's
+// pointers, so it builds an adjusted copy in shared memory once and every stage reads that copy.
+template <typename real, int NXv, int NUv>
+__device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
+    const int tid = threadIdx.x, BD = blockDim.x;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&in);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+    for (int i = tid; i < (int)(sizeof(KArgs<real>) / 4); i += BD) dst[i] = src[i];
+    __syncthreads();
+    if (tid == 0) {
+        const long long e = blockIdx.y;
+        const long long K = in.K, TN = in.TN, R = in.R;
+        out->U = in.U + e * in.env_u_stride;
+        if (in.cost_total) out->cost_total = in.cost_total + e * K;
+        if (in.action_out) out->action_out = in.action_out + e * in.upc * NUv;
+        if (in.nominal_used) out->nominal_used = in.nominal_used + e * (3 * TN + 4);
+        if (in.stats) out->stats = in.stats + e * 4;
+        if (in.state_dev) out->state_dev = in.state_dev + e * NXv;
+        if (in.ticket) {
+            const long long off = e * in.env_ws_stride;
+            out->ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<unsigned char*>(in.ticket) + off);
+            out->betaP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.betaP) + off);
+            out->etaP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.etaP) + off);
+            out->VP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.VP) + off);
+        }
+        if (in.out_pa) out->out_pa = in.out_pa + e * K * TN;
+        if (in.out_noise) out->out_noise = in.out_noise + e * K * TN;
+        if (in.out_cost_init) out->out_cost_init = in.out_cost_init + e * K;
+        if (in.in_cost) out->in_cost = in.in_cost + e * K;
+        if (in.in_eps) out->in_eps = in.in_eps + e * K * R;
+    }
+    __syncthreads();
+}
+
 // =================================================================================================
 // The fused command kernel
 // =================================================================================================
-template <class Model, typename real, int VARIANT>
-__global__ void __launch_bounds__(512) fused_command_kernel(const KArgs<real> a, const typename Model::template P<real> mp) {
+template <class Model, typename real, int VARIANT, bool BATCHED>
+__global__ void __launch_bounds__(512) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
+                                                            const typename Model::template P<real> mp) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, BD = blockDim.x;
+    __shared__ __align__(16) unsigned char a_env_raw[BATCHED ? sizeof(KArgs<real>) : 16];
+    if (BATCHED) make_env_args<real, NX, NU>(a_in, reinterpret_cast<KArgs<real>*>(a_env_raw));
+    const KArgs<real>& a = BATCHED ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, 0);
     Smem<real> sm(smem, L);
@@ -869,10 +913,13 @@ MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
 // SMPPI :539-562; KMPPI :657-670).  Also used to materialise noise/perturbed_action lazily.
 // =================================================================================================
 template <typename real, int VARIANT, int NU>
-__global__ void __launch_bounds__(512) sample_kernel(const KArgs<real> a) {
+__global__ void __launch_bounds__(512) sample_kernel(const __grid_constant__ KArgs<real> a_in) {
     typedef Ops<real> O;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, BD = blockDim.x;
+    __shared__ __align__(16) unsigned char a_env_raw[sizeof(KArgs<real>)];
+    if (a_in.n_env > 1) make_env_args<real, 0, NU>(a_in, reinterpret_cast<KArgs<real>*>(a_env_raw));
+    const KArgs<real>& a = a_in.n_env > 1 ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1, VARIANT == V_KMPPI);
     Smem<real> sm(smem, L);
@@ -989,10 +1036,13 @@ __global__ void states_kernel(const real* __restrict__ pa, real* __restrict__ st
 // (mppi.py:254-259, 268-270).  HBM-bound: reads 4*K*(R+1) bytes once, coalesced.
 // =================================================================================================
 template <typename real, int VARIANT, int NU>
-__global__ void __launch_bounds__(512) softmin_update_kernel(const KArgs<real> a) {
+__global__ void __launch_bounds__(512) softmin_update_kernel(const __grid_constant__ KArgs<real> a_in) {
     typedef Ops<real> O;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, BD = blockDim.x;
+    __shared__ __align__(16) unsigned char a_env_raw[sizeof(KArgs<real>)];
+    if (a_in.n_env > 1) make_env_args<real, 0, NU>(a_in, reinterpret_cast<KArgs<real>*>(a_env_raw));
+    const KArgs<real>& a = a_in.n_env > 1 ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, 0);
     Smem<real> sm(smem, L);

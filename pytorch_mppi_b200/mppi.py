@@ -370,6 +370,7 @@ class MPPI:
         p.partial_out = None
         dbg = getattr(self, "_debug_clocks", None)
         p.debug_clocks = None if dbg is None else dbg.data_ptr()
+        p.n_env, p.env_u_stride, p.env_ws_stride = 0, 0, 0
         p.host_mailbox = None
         p.host_epoch = 0
         self._variant_pack(p)
@@ -1114,6 +1115,144 @@ class KMPPI(MPPI):
     @property
     def noise_theta(self):
         return self._noise_theta_buf if self._materialize() else None
+
+
+class MPPI_Batched(MPPI):
+    """MPPI for N parallel environments (mppi.py:691-873): the K noise samples are shared across
+    environments, every environment keeps its own nominal sequence and softmin.  The reference
+    concatenates N*K rows into one dynamics call per step; here the N problems are the y-dimension of
+    ONE launch (registered models: the fused kernel; arbitrary callables: the sampling and softmin
+    kernels around the Python T-loop)."""
+
+    def __init__(self, dynamics, running_cost, nx, noise_sigma, num_envs, num_samples=100, horizon=15, device="cuda",
+                 lambda_=1., noise_mu=None, u_min=None, u_max=None, u_init=None, u_scale=1, u_per_command=1,
+                 step_dependent_dynamics=False, noise_abs_cost=False, *, rng_seed=None, block_threads=0):
+        self.N = int(num_envs)
+        super().__init__(dynamics, running_cost, nx, noise_sigma, num_samples=num_samples, horizon=horizon, device=device,
+                         lambda_=lambda_, noise_mu=noise_mu, u_min=u_min, u_max=u_max, u_init=u_init, u_scale=u_scale,
+                         u_per_command=u_per_command, step_dependent_dynamics=step_dependent_dynamics,
+                         noise_abs_cost=noise_abs_cost, rng_seed=rng_seed, block_threads=block_threads, threads_per_sample=0)
+
+    # ---- (N, ...) buffers ------------------------------------------------------------------------
+    def _alloc_nominal(self, U_init):
+        es = _ES[self.dtype]
+        self._u_stride = _pad16(self.T * self.nu, es)
+        self._Ubuf = torch.zeros(self.N, self._u_stride, device=self.d, dtype=self.dtype)
+        self.U = self._sample_noise((self.N, self.T)) if U_init is None else U_init          # mppi.py:807
+
+    def _alloc_results(self):
+        tn = self.T * self.nu
+        self._cost_buf = torch.empty(self.N, self.K, device=self.d, dtype=self.dtype)
+        self._nominal_used = torch.zeros(self.N, 3 * tn + 4, device=self.d, dtype=self.dtype)
+        self._stats = torch.zeros(self.N, 4, device=self.d, dtype=torch.float64)
+        self._workspace = None
+        self._partial = None
+
+    @property
+    def U(self):
+        return self._Ubuf[:, : self.T * self.nu].view(self.N, self.T, self.nu)
+
+    @U.setter
+    def U(self, value):
+        value = torch.as_tensor(value).to(self.d, self.dtype).reshape(self.N, self.T * self.nu)
+        self._Ubuf[:, : self.T * self.nu].copy_(value)
+
+    def _variant_pack(self, p):
+        es = _ES[self.dtype]
+        rows = self.T * self.nu
+        nb_max = min((self.K + 31) // 32 + 1, 148 * 16)
+        stride = 16 + 2 * ((nb_max * es + 15) // 16 * 16) + ((nb_max * rows * es + 15) // 16 * 16) + 64
+        self._env_ws_stride = (stride + 255) // 256 * 256
+        need = self._env_ws_stride * self.N
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.zeros(need, device=self.d, dtype=torch.uint8)
+        p.n_env = self.N
+        p.env_u_stride = self._u_stride
+        p.env_ws_stride = self._env_ws_stride
+
+    def _pack(self):
+        super()._pack()
+        # super() sized the workspace for one problem; restore the per-environment slices
+        p = self._p
+        assert p.workspace == self._workspace.data_ptr() and p.workspace_bytes >= self._env_ws_stride * self.N
+
+    def reset(self):
+        """mppi.py:819-820"""
+        self.U = self._sample_noise((self.N, self.T))
+
+    def shift_nominal_trajectory(self):
+        U = torch.roll(self.U, -1, dims=1)
+        U[:, -1] = self._u_init
+        self.U = U
+
+    def change_horizon(self, horizon):
+        raise NotImplementedError("MPPI_Batched has no change_horizon in the reference either")
+
+    def command_host(self, *a, **k):
+        raise NotImplementedError("use command(); N actions are returned as a device tensor")
+
+    def command(self, states, shift_nominal_trajectory=True):
+        """mppi.py:822-873: states (N, nx) -> actions (N, nu) (or (N, u_per_command, nu))."""
+        if not torch.is_tensor(states):
+            states = torch.tensor(states)
+        states = states.to(dtype=self.dtype, device=self.d).reshape(self.N, self.nx).contiguous()
+        self.state = states
+        if self._dirty:
+            self._pack()
+        N, K, T, nu = self.N, self.K, self.T, self.nu
+        action = torch.empty((N, self.u_per_command, nu), device=self.d, dtype=self.dtype)
+        stream = torch._C._cuda_getCurrentRawStream(self.d.index)
+        flags = self._base_flags | _cabi.FLAG_STATE_DEVICE | (_cabi.FLAG_SHIFT if shift_nominal_trajectory else 0)
+        zptr, seed, off = self._noise_source()
+        self._cmd_count += 1
+        if self._model is not None:
+            self._last = (flags, seed, off, zptr, states.data_ptr())
+            _cabi.check(self._lib.mppi_plan_command(self._plan, None, states.data_ptr(), flags, seed, off, zptr,
+                                                    action.data_ptr(), stream), "mppi_plan_command")
+        else:
+            self._last = None
+            p = self._p
+            p.flags = flags & ~_cabi.FLAG_STATE_DEVICE
+            p.z, p.seed, p.offset = zptr, seed, off
+            p.action_out = action.data_ptr()
+            if getattr(self, "_pa_buf", None) is None or self._pa_buf.shape != (N, K, T, nu):
+                self._pa_buf = torch.empty(N, K, T, nu, device=self.d, dtype=self.dtype)
+                self._noise_buf = torch.empty(N, K, T, nu, device=self.d, dtype=self.dtype)
+                self._cost_init = torch.empty(N, K, device=self.d, dtype=self.dtype)
+            lib = self._lib
+            _cabi.check(lib.mppi_sample_perturb(C.byref(p), self._pa_buf.data_ptr(), self._noise_buf.data_ptr(), None,
+                                                self._cost_init.data_ptr(), None, 0, 0, stream), "mppi_sample_perturb")
+            NK = N * K
+            state = states.unsqueeze(1).expand(N, K, self.nx).reshape(NK, self.nx)                # mppi.py:846
+            total = torch.zeros(N, K, device=self.d, dtype=self.dtype)
+            dt = _DT[self.dtype]
+            for t in range(T):                                                                    # mppi.py:849-853
+                u = self._u_scale * self._pa_buf[:, :, t].reshape(NK, nu)
+                state = self._dynamics_fn(state, u, t)
+                c = self._running_cost_fn(state, u, t).reshape(NK).to(self.dtype).contiguous()
+                _cabi.check(lib.mppi_cost_accumulate(total.data_ptr(), c.data_ptr(), None, 1, NK, 1.0, dt, stream),
+                            "mppi_cost_accumulate")
+            _cabi.check(lib.mppi_cost_accumulate(total.data_ptr(), self._cost_init.data_ptr(), None, 1, NK, 1.0, dt, stream),
+                        "mppi_cost_accumulate")
+            self._cost_buf = total
+            _cabi.check(lib.mppi_softmin_update(C.byref(p), total.data_ptr(), self._noise_buf.data_ptr(), stream),
+                        "mppi_softmin_update")
+        self.cost_total = self._cost_buf
+        return action[:, 0] if self.u_per_command == 1 else action                               # mppi.py:870-873
+
+    # per-environment intermediates are not materialised lazily for the batched controller
+    noise = property(lambda self: None)
+    perturbed_action = property(lambda self: None)
+    states = property(lambda self: None)
+    actions = property(lambda self: None)
+
+    @property
+    def omega(self):
+        if self.cost_total is None:
+            return None
+        beta = self._stats[:, 0:1].to(self.dtype)
+        eta = self._stats[:, 1:2].to(self.dtype)
+        return torch.exp(-(1.0 / self._lambda) * (self.cost_total - beta)) / eta
 
 
 def run_mppi(mppi, env, retrain_dynamics, retrain_after_iter=50, iter=1000, render=True):

@@ -304,3 +304,65 @@ def test_stepped_route_M_gt_1_and_action_sampler_match_oracle_semantics():
     assert float((ctrl.U.cpu() - U_want).abs().max()) < 1e-10
     assert float((ctrl.cost_total.cpu() - total).abs().max()) < 1e-9
     np.testing.assert_allclose(ctrl.perturbed_action.cpu().numpy(), pa.numpy(), atol=1e-12)
+
+
+@pytest.mark.parametrize("route", ["fused", "stepped"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 5e-5)])
+def test_mppi_batched_matches_oracle(route, dtype, tol):
+    """MPPI_Batched (mppi.py:691-873): N environments share the K noise samples; per-environment softmin.
+    Both routes against the oracle's restatement on injected noise, two closed-loop commands."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    N, K, T = 5, 300, 9
+    lin = eng.LinearPoint.unit_test_env()
+    olin = orc.LinearPointModel(B=lin.B, goal=lin.goal, dtype=dtype)
+    g = torch.Generator().manual_seed(9)
+    sigma = torch.tensor([[0.8, 0.1], [0.1, 0.6]], dtype=dtype)
+    umax = torch.tensor([0.9, 0.7], dtype=dtype)
+    prob = orc.Problem(olin.dynamics, olin.running_cost, 2, sigma, K=K, T=T, lambda_=0.8, u_max=umax, u_scale=1.2)
+    dyn, cost = (lin.dynamics, lin.running_cost) if route == "fused" else ((lambda s, a: lin.dynamics(s, a)), (lambda s, a: lin.running_cost(s, a)))
+    torch.manual_seed(1)
+    ctrl = eng.MPPI_Batched(dyn, cost, 2, sigma, num_envs=N, num_samples=K, horizon=T, lambda_=0.8, u_max=umax, u_scale=1.2, device="cuda")
+    assert (ctrl._model is not None) == (route == "fused")
+    U = ctrl.U.cpu().clone()
+    assert U.shape == (N, T, 2)
+    x = torch.randn(N, 2, generator=g, dtype=dtype)
+    for step in range(2):
+        z = torch.randn(K, T, 2, generator=g, dtype=dtype)
+        ctrl.inject_noise(z)
+        a = ctrl.command(x.cuda())
+        r = orc.mppi_batched_command(prob, U, x, z)
+        assert a.shape == (N, 2)
+        assert float((ctrl.U.cpu() - r["U"]).abs().max()) < tol
+        assert float((a.cpu() - r["action"]).abs().max()) < tol
+        np.testing.assert_allclose(ctrl.cost_total.cpu().numpy(), r["cost_total"].numpy(), rtol=1e-9 if dtype == torch.float64 else 1e-5)
+        om = ctrl.omega.cpu()
+        assert float((om.sum(dim=1) - 1).abs().max()) < 1e-5
+        U = r["U"]
+        ctrl.U = U
+        x = olin.dynamics(x, 1.2 * r["action"])
+
+
+def test_mppi_batched_envs_are_independent_and_bounded():
+    """/root/reference/tests/test_mppi.py:743-771: bounds hold; identical start states with identical nominal
+    sequences give identical actions, different states give different ones; reset resamples U."""
+    import pytorch_mppi_b200 as eng
+    pend = eng.Pendulum()
+    N = 64
+    c = eng.MPPI_Batched(pend.dynamics, pend.running_cost, 2, torch.tensor(4.0), num_envs=N, num_samples=2048, horizon=20,
+                         u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=5)
+    c.U = torch.zeros(N, 20, 1)
+    x = torch.zeros(N, 2)
+    x[:, 0] = 3.0
+    x[N // 2:, 0] = 1.0
+    a = c.command(x.cuda()).cpu()
+    assert a.shape == (N, 1) and (a.abs() <= 2.0 + 1e-6).all()
+    assert torch.equal(a[0], a[1]) and torch.equal(a[N // 2], a[N - 1]) and not torch.equal(a[0], a[N - 1])
+    before = c.U.clone()
+    c.reset()
+    assert not torch.allclose(c.U, before)
+    # the batched launch equals N single-environment controllers fed the same draws
+    single = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(4.0), num_samples=2048, horizon=20,
+                      u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=5, U_init=torch.zeros(20, 1))
+    a1 = single.command([3.0, 0.0]).cpu()
+    assert float((a1 - a[0]).abs().max()) < 2e-6
