@@ -179,6 +179,6 @@ def check(rc, what="mppi call"):
     if rc != 0:
         lib = load()
         msg = lib.mppi_status_string(rc).decode()
-        if rc == -4:
+        if rc in (-4, -2):
             msg += ": " + lib.mppi_last_cuda_error().decode()
         raise MppiLibraryError(f"{what} failed: {msg} ({rc})")

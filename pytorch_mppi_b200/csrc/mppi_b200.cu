@@ -19,6 +19,11 @@ int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     return MPPI_ERR_CUDA;
 }
+int unsupported_at(const char* why, int line) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (mppi_b200.cu:%d)", why, line);
+    return MPPI_ERR_UNSUPPORTED;
+}
+#define UNSUPPORTED(why) unsupported_at(why, __LINE__)
 #define CK(call)                                              \
     do {                                                      \
         cudaError_t _e = (call);                              \
@@ -284,9 +289,9 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     SmemLayout L;
     for (int it = 0; it < 4; ++it) {
         L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : nb, need_rows2);
-        if (L.total > dyn_limit) return MPPI_ERR_UNSUPPORTED;
+        if (L.total > dyn_limit) return UNSUPPORTED("shared-memory tile does not fit");
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
-        if (occ < 1) return MPPI_ERR_UNSUPPORTED;
+        if (occ < 1) return UNSUPPORTED("kernel does not fit on an SM with this block size");
         int nb2 = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
         if (nb2 > cap) nb2 = cap;
         if (p->grid_blocks > 0 && p->grid_blocks < nb2) nb2 = p->grid_blocks;
@@ -319,7 +324,7 @@ template <class Model, typename real, int V>
 int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
     const bool batched = p->n_env > 1;
-    if (batched && (V != V_MPPI || p->world > 1)) return MPPI_ERR_UNSUPPORTED;
+    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
     if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
     auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
     Geometry g;
@@ -350,7 +355,7 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (batched && (p->env_ws_stride < need_ws || p->workspace_bytes < p->env_ws_stride * (uint64_t)p->n_env ||
                     p->env_u_stride < p->T * p->nu))
         return MPPI_ERR_WORKSPACE;
-    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
+    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params);
@@ -388,7 +393,7 @@ struct Plan {
 template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
     const bool batched = p->n_env > 1;
-    if (batched && (V != V_MPPI || p->world > 1)) return MPPI_ERR_UNSUPPORTED;
+    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
     auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
     if (rc) return rc;
@@ -398,7 +403,7 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     static_assert(sizeof(typename Model::template P<real>) <= sizeof(pl->mparams), "model parameter block too large");
     KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
     fill_kargs<real>(p, *a, pl->g.BS, pl->g.nb, pl->g.tps);
-    if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
+    if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
     Model::template load<real>(*mp, p->model_params);
     pl->kernel = (const void*)kernel;
@@ -534,7 +539,7 @@ int run_softmin(const MppiFusedParams* p, const void* cost, const void* eps, cud
     fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
     a.in_cost = (const real*)cost;
     a.in_eps = (const real*)eps;
-    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return MPPI_ERR_UNSUPPORTED;
+    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     return launch_kernel(kernel, g.nb, g.BD, g.smem, stream, a.n_env, a);
 }
 

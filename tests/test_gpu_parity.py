@@ -335,7 +335,7 @@ def test_mppi_batched_matches_oracle(route, dtype, tol):
         assert a.shape == (N, 2)
         assert float((ctrl.U.cpu() - r["U"]).abs().max()) < tol
         assert float((a.cpu() - r["action"]).abs().max()) < tol
-        np.testing.assert_allclose(ctrl.cost_total.cpu().numpy(), r["cost_total"].numpy(), rtol=1e-9 if dtype == torch.float64 else 1e-5)
+        np.testing.assert_allclose(ctrl.cost_total.cpu().numpy(), r["cost_total"].numpy(), rtol=1e-9 if dtype == torch.float64 else 2e-4, atol=0 if dtype == torch.float64 else 1e-4)
         om = ctrl.omega.cpu()
         assert float((om.sum(dim=1) - 1).abs().max()) < 1e-5
         U = r["U"]
