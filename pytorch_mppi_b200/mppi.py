@@ -541,6 +541,9 @@ class MPPI:
         """(flags, state_dev_ptr) — host states go by value into the launch (no H2D copy); CUDA tensors
         and one-state-per-sample batches are read from device memory."""
         if torch.is_tensor(state) and state.is_cuda:
+            if state.dim() == 1 and state.dtype == self.dtype and state.is_contiguous() and state.shape[0] >= self.nx:
+                self.state = state                     # fast path: no torch ops on the hot path
+                return _cabi.FLAG_STATE_DEVICE, state.data_ptr()
             st = state.to(self.dtype)
             if st.dim() == 2 and st.shape == (self.K, self.nx) and self.K != 1:
                 st = st[self._k_offset:self._k_offset + self._K_local].contiguous()

@@ -366,3 +366,27 @@ def test_mppi_batched_envs_are_independent_and_bounded():
                       u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=5, U_init=torch.zeros(20, 1))
     a1 = single.command([3.0, 0.0]).cpu()
     assert float((a1 - a[0]).abs().max()) < 2e-6
+
+
+def test_full_size_c5_properties():
+    """BASELINE config 5 size on one GPU (K=2^20, T=50, fp32), checked through size-independent
+    properties: weights sum to one, beta is the minimum cost, bounds hold, the update is a convex
+    combination of the clamped samples (so it stays inside the bounds), same seed -> same result, and a
+    different launch geometry gives the same nominal sequence to fp32 accuracy."""
+    import pytorch_mppi_b200 as eng
+    pend = eng.Pendulum()
+    K, T = 1 << 20, 50
+    outs = []
+    for bt in (0, 256):
+        c = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=K, horizon=T,
+                     u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), U_init=torch.zeros(T, 1), device="cuda", rng_seed=77,
+                     block_threads=bt)
+        for _ in range(2):
+            a = c.command([3.14159, 1.0])
+        cost = c.cost_total
+        assert cost.shape == (K,) and torch.isfinite(cost).all()
+        assert abs(c.omega.double().sum().item() - 1.0) < 1e-4
+        assert abs(cost.min().item() - c.beta.item()) < 1e-6 * max(1.0, abs(c.beta.item()))
+        assert (c.U.abs() <= 2.0 + 1e-5).all() and (a.abs() <= 2.0 + 1e-5).all()
+        outs.append(c.U.cpu().clone())
+    assert float((outs[0] - outs[1]).abs().max()) < 5e-5
