@@ -24,7 +24,7 @@
 #include "mppi_math.cuh"
 
 #ifndef MPPI_ROLLOUT_PIPELINED
-#define MPPI_ROLLOUT_PIPELINED 1
+#define MPPI_ROLLOUT_PIPELINED 0
 #endif
 #ifndef MPPI_ROLLOUT_UNROLL
 #define MPPI_ROLLOUT_UNROLL 2
@@ -641,10 +641,12 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
     // fence + ticket increment publishes them (one MEMBAR per CTA instead of one per warp)
     __syncthreads();
     if (tid == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(a.ticket, 1u);
+        // one acq_rel ticket increment: releases this CTA's record (the barrier above made every thread's
+        // stores visible to thread 0) and, for the last arrival, acquires all the others' — cheaper than
+        // the two sequentially-consistent fences __threadfence() would insert around a relaxed atomic
+        unsigned int t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(t) : "l"(a.ticket), "r"(1u) : "memory");
         s_is_last = (t == gridDim.x - 1);
-        if (s_is_last) __threadfence();   // acquire side for the partials read below
     }
     __syncthreads();
     stamp(a.dbg, 6);
@@ -653,65 +655,123 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
 
     // The partials were written by other SMs before their ticket increments; this CTA has not
     // touched those lines during this launch, and __ldcg reads them from L2.  Every load whose
-    // address does not depend on beta is issued up front (one L2 round trip for the common case),
-    // the scalar part (beta, eta, rescale factors) is done by warp 0 with shuffles only, and three
-    // barriers separate the remaining stages.
+    // address does not depend on beta is issued up front (one L2 round trip for the common case);
+    // the scalar part (beta, rescale factors, eta) is spread over all threads.
     const int nb = gridDim.x;
     const real* betaP = a.betaP;
     const real* etaP = a.etaP;
     const real* VP = a.VP;
     real* sB = sm.sS;            // [nb] beta_q, then rescale factors s_q
     real* sE = sm.sS + nb;       // [nb] eta_q
-    real vpre[8];
+    // 1) issue every load whose address is known now: this thread's scalars and the first 16 records of
+    //    its (warp, lane) numerator slice — one L2 round trip covers the common case completely
+    constexpr int PF = 16;
+    real vpre[PF];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < PF; ++u) {
         const int q = warp + u * nw;
         vpre[u] = (lane < R && q < nb) ? __ldcg(VP + (size_t)q * R + lane) : (real)0;
     }
-    if (warp == 0) {
-        real bl = O::inf();
-        for (int q = lane; q < nb; q += 32) {
+    if (nb <= 256) {
+        // small grids: warp 0 alone, shuffles only, ONE barrier (measured faster than block-wide
+        // reductions here: 16 warps' barriers cost more than 8 loads per lane)
+        if (warp == 0) {
+            real b8[8], e8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = lane + 32 * u;
+                b8[u] = q < nb ? __ldcg(betaP + q) : O::inf();
+                e8[u] = q < nb ? __ldcg(etaP + q) : (real)0;
+            }
+            real bl = b8[0];
+#pragma unroll
+            for (int u = 1; u < 8; ++u) bl = b8[u] < bl ? b8[u] : bl;
+            const real beta = warp_min<real>(bl);
+            double el = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = lane + 32 * u;
+                if (q < nb) {
+                    const real sq = O::exp_(nfl * (b8[u] - beta));
+                    sB[q] = sq;
+                    el += (double)sq * (double)e8[u];
+                }
+            }
+            const double eta = warp_sum<double>(el);
+            if (lane == 0) {
+                sm.numd[0] = (double)beta;
+                sm.numd[1] = eta;
+                *a.ticket = 0u;   // self-reset: the next launch needs no memset
+            }
+        }
+        __syncthreads();
+    } else {
+        real bq0 = O::inf(), eq0 = (real)0, bq1 = O::inf(), eq1 = (real)0;
+        if (tid < nb) {
+            bq0 = __ldcg(betaP + tid);
+            eq0 = __ldcg(etaP + tid);
+        }
+        if (tid + BD < nb) {
+            bq1 = __ldcg(betaP + tid + BD);
+            eq1 = __ldcg(etaP + tid + BD);
+        }
+        real bl = bq0 < bq1 ? bq0 : bq1;
+        for (int q = tid + 2 * BD; q < nb; q += BD) {          // very large grids only
             const real bq = __ldcg(betaP + q);
             sB[q] = bq;
             sE[q] = __ldcg(etaP + q);
             bl = bq < bl ? bq : bl;
         }
-        const real beta = warp_min<real>(bl);
-        __syncwarp();
+        const real beta = block_min<real>(bl, sm.red);
         double el = 0.0;
-        for (int q = lane; q < nb; q += 32) {
+        if (tid < nb) {
+            const real sq = O::exp_(nfl * (bq0 - beta));
+            sB[tid] = sq;
+            el += (double)sq * (double)eq0;
+        }
+        if (tid + BD < nb) {
+            const real sq = O::exp_(nfl * (bq1 - beta));
+            sB[tid + BD] = sq;
+            el += (double)sq * (double)eq1;
+        }
+        for (int q = tid + 2 * BD; q < nb; q += BD) {
             const real sq = O::exp_(nfl * (sB[q] - beta));
             sB[q] = sq;
             el += (double)sq * (double)sE[q];
         }
-        const double eta = warp_sum<double>(el);
-        if (lane == 0) {
+        const double eta = block_sum<double>(el, sm.redd);   // its barriers also publish sB
+        if (tid == 0) {
             sm.numd[0] = (double)beta;
             sm.numd[1] = eta;
             *a.ticket = 0u;   // self-reset: the next launch needs no memset
         }
     }
-    __syncthreads();
     stamp(a.dbg, 10);
+    // 3) numerators: rows j = lane (+32..), records q = warp (+nw..), PF loads in flight per thread
     for (int j = lane; j < R; j += 32) {
         double acc = 0.0;
         int q = warp;
         if (j == lane) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < PF; ++u) {
                 const int qq = warp + u * nw;
                 if (qq < nb) acc += (double)sB[qq] * (double)vpre[u];
             }
-            q = warp + 8 * nw;
+            q = warp + PF * nw;
         }
-        for (; q + 7 * nw < nb; q += 8 * nw) {
-            real v[8];
+        for (; q < nb; q += PF * nw) {
+            real v[PF];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(VP + (size_t)(q + u * nw) * R + j);
+            for (int u = 0; u < PF; ++u) {
+                const int qq = q + u * nw;
+                v[u] = qq < nb ? __ldcg(VP + (size_t)qq * R + j) : (real)0;
+            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc += (double)sB[q + u * nw] * (double)v[u];
+            for (int u = 0; u < PF; ++u) {
+                const int qq = q + u * nw;
+                if (qq < nb) acc += (double)sB[qq] * (double)v[u];
+            }
         }
-        for (; q < nb; q += nw) acc += (double)sB[q] * (double)__ldcg(VP + (size_t)q * R + j);
         sm.part2[warp * R + j] = acc;
     }
     __syncthreads();
