@@ -48,7 +48,8 @@ typedef enum MppiDType { MPPI_F32 = 0, MPPI_F64 = 1 } MppiDType;
  * per-step entry points further down.) */
 typedef enum MppiModel {
     MPPI_MODEL_PENDULUM = 1,      /* /root/reference/tests/pendulum.py:30-60                      */
-    MPPI_MODEL_LINEAR_POINT = 2   /* tests/test_mppi.py:24-51 and tests/smooth_mppi.py:29-142    */
+    MPPI_MODEL_LINEAR_POINT = 2,  /* tests/test_mppi.py:24-51 and tests/smooth_mppi.py:29-142    */
+    MPPI_MODEL_PENDULUM_MLP = 3   /* tests/pendulum_approximate.py:47-67 (3-32-32-2 tanh residual MLP) */
 } MppiModel;
 
 /* model_params layouts (doubles):
@@ -56,6 +57,8 @@ typedef enum MppiModel {
  *  LINEAR_POINT : [0..3]=B(2x2 row-major) [4..5]=goal [6..9]=Q [10]=has_R [11..14]=R
  *                 [15]=terminal_scale [16]=n_hills(<=3) then per hill h at 17+7h:
  *                 Qh(4) centre(2) height(1)
+ *  PENDULUM_MLP : [0]=max_torque [1]=w_thdot [2]=tanh_mode(0 exp-based, 1 MUFU.TANH); the 1,250 weights go in
+ *                 model_params_ext: W1 (32x3 row-major), b1 (32), W2 (32x32), b2 (32), W3 (2x32), b3 (2)
  */
 
 enum {
@@ -141,6 +144,10 @@ typedef struct MppiFusedParams {
                                     word, payload32 | (host_epoch & 0xffffffff) << 32, so the host spins on the
                                     words themselves instead of issuing a D2H copy or a stream synchronise      */
     uint64_t host_epoch;
+    const double* model_params_ext;   /* HOST pointer: extra model parameters (e.g. MLP weights), read at call /
+                                         plan-creation time; NULL if the model needs none                    */
+    int32_t n_model_params_ext;
+    int32_t _pad1;
     void* debug_clocks;          /* optional profiling aid: (grid_blocks, 16) uint64 %globaltimer stamps (ns) at
                                     phase boundaries of each CTA's first tile; NULL on the product path   */
 } MppiFusedParams;

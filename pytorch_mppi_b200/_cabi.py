@@ -20,7 +20,7 @@ ABI_VERSION = 1
 # enums
 VARIANT_MPPI, VARIANT_SMPPI, VARIANT_KMPPI = 0, 1, 2
 F32, F64 = 0, 1
-MODEL_PENDULUM, MODEL_LINEAR_POINT = 1, 2
+MODEL_PENDULUM, MODEL_LINEAR_POINT, MODEL_PENDULUM_MLP = 1, 2, 3
 FLAG_SHIFT = 1 << 0
 FLAG_NULL_ACTION = 1 << 1
 FLAG_ABS_COST = 1 << 2
@@ -94,6 +94,9 @@ class MppiFusedParams(C.Structure):
         ("env_ws_stride", C.c_uint64),
         ("host_mailbox", C.c_void_p),
         ("host_epoch", C.c_uint64),
+        ("model_params_ext", C.c_void_p),
+        ("n_model_params_ext", C.c_int32),
+        ("_pad1", C.c_int32),
         ("debug_clocks", C.c_void_p),
     ]
 

@@ -358,7 +358,7 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
     typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params);
+    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
     void* argv2[2] = {(void*)&a, (void*)&mp};
     cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env);
     if (e != cudaSuccess) return cuda_fail(e, "fused launch");
@@ -387,7 +387,7 @@ struct Plan {
     int is_double, nx, upc_nu, pdl;
     unsigned long long epoch, host_epoch;
     alignas(16) unsigned char kargs[sizeof(KArgs<double>)];
-    alignas(16) unsigned char mparams[1024];
+    alignas(16) unsigned char mparams[12288];
 };
 
 template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
@@ -405,7 +405,7 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     fill_kargs<real>(p, *a, pl->g.BS, pl->g.nb, pl->g.tps);
     if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
-    Model::template load<real>(*mp, p->model_params);
+    Model::template load<real>(*mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
     pl->kernel = (const void*)kernel;
     pl->is_double = sizeof(real) == 8;
     pl->nx = Model::NX;
@@ -464,6 +464,9 @@ int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* inf
     switch (p->model) {
         case MPPI_MODEL_PENDULUM: return run_fused_dtype<PendulumModel>(p, s, info);
         case MPPI_MODEL_LINEAR_POINT: return run_fused_dtype<LinearPointModel>(p, s, info);
+        case MPPI_MODEL_PENDULUM_MLP:
+            if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) return MPPI_ERR_BAD_ARG;
+            return run_fused_dtype<PendulumMLPModel>(p, s, info);
     }
     return MPPI_ERR_UNSUPPORTED;
 }
@@ -567,7 +570,7 @@ int run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStrea
     KArgs<real> a;
     fill_kargs<real>(p, a, 128, 1);
     typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params);
+    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
     states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp);
     CK(cudaGetLastError());
     return MPPI_OK;
@@ -636,6 +639,10 @@ int mppi_plan_create(const MppiFusedParams* p, void** plan_out) {
     switch (p->model) {
         case MPPI_MODEL_PENDULUM: rc = build_plan_dtype<PendulumModel>(p, pl); break;
         case MPPI_MODEL_LINEAR_POINT: rc = build_plan_dtype<LinearPointModel>(p, pl); break;
+        case MPPI_MODEL_PENDULUM_MLP:
+            rc = (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr)
+                     ? (int)MPPI_ERR_BAD_ARG : build_plan_dtype<PendulumMLPModel>(p, pl);
+            break;
         default: rc = MPPI_ERR_UNSUPPORTED;
     }
     if (rc) {

@@ -311,7 +311,7 @@ struct PendulumModel {
     template <typename real> struct P {
         real c_sin, c_u, dt, max_torque, max_speed, pi, two_pi, w_thdot;
     };
-    template <typename real> static void load(P<real>& p, const double* b) {
+    template <typename real> static void load(P<real>& p, const double* b, const double* = nullptr, int = 0) {
         double g = b[0], m = b[1], l = b[2];
         p.c_sin = (real)(3 * g / (2 * l));          // tests/pendulum.py:43, python-float literal
         p.c_u = (real)(3.0 / (m * l * l));
@@ -351,7 +351,7 @@ struct LinearPointModel {
         real terminal_scale;
         int has_R, n_hills;
     };
-    template <typename real> static void load(P<real>& p, const double* b) {
+    template <typename real> static void load(P<real>& p, const double* b, const double* = nullptr, int = 0) {
         for (int i = 0; i < 4; ++i) p.B[i] = (real)b[i];
         p.goal[0] = (real)b[4]; p.goal[1] = (real)b[5];
         for (int i = 0; i < 4; ++i) p.Q[i] = (real)b[6 + i];
@@ -404,6 +404,84 @@ struct LinearPointModel {
     template <typename real> static MPPI_HD real terminal(const P<real>& p, const real* xT) {
         return Ops<real>::mul(p.terminal_scale, state_cost<real>(p, xT));
     }
+};
+
+// Learned pendulum dynamics (BASELINE config 4; /root/reference/tests/pendulum_approximate.py:47-67):
+//   u <- clamp(u, +-max_torque); x' = x + MLP([x, u]);  x'_0 <- angle_normalize(x'_0)
+//   MLP = Linear(3,H) - tanh - Linear(H,H) - tanh - Linear(H,2),  H = 32
+// with the pendulum running cost.  The 1,250 weights travel in the kernel parameter block, i.e. constant
+// bank 0, so every FFMA takes its weight operand straight from the constant cache (no loads).  The
+// contraction order differs from the reference's BLAS calls anyway, so FMAs are used freely here.
+struct PendulumMLPModel {
+    static const int NX = 2, NU = 1, H = 32;
+    static const int N_EXT = H * 3 + H + H * H + H + 2 * H + 2;     // 1250
+    template <typename real> struct P {
+        real W1[H * 3], b1[H], W2[H * H], b2[H], W3[2 * H], b3[2];
+        real max_torque, pi, two_pi, w_thdot;
+        int tanh_mode;     // 0: exp-based (abs err < 5e-7 in fp32; libm tanh in fp64), 1: MUFU.TANH (fp32 only, ~1e-3)
+    };
+    // blob: [0]=max_torque [1]=w_thdot [2]=tanh_mode ; ext: W1 (H x 3 row-major), b1, W2 (H x H), b2, W3 (2 x H), b3
+    template <typename real> static void load(P<real>& p, const double* b, const double* ext = nullptr, int n_ext = 0) {
+        p.max_torque = (real)b[0];
+        p.w_thdot = (real)b[1];
+        p.tanh_mode = (int)b[2];
+        p.pi = (real)3.141592653589793;
+        p.two_pi = (real)(2 * 3.141592653589793);
+        real* dst = p.W1;     // the six arrays are laid out contiguously in declaration order
+        for (int i = 0; i < N_EXT; ++i) dst[i] = (ext != nullptr && i < n_ext) ? (real)ext[i] : (real)0;
+    }
+    static MPPI_HD float tanh_(float x, int mode) {
+#if defined(__CUDA_ARCH__)
+        if (mode == 1) {
+            float y;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+            return y;
+        }
+        // 1 - 2 / (1 + e^{2x}) on the SFU: saturates correctly (e^{2x} -> inf gives 1, -> 0 gives -1)
+        const float t = exp2f(x * 2.885390081777927f);
+        return fmaf(-2.0f, __frcp_rn(1.0f + t), 1.0f);
+#else
+        return tanhf(x);
+#endif
+    }
+    static MPPI_HD double tanh_(double x, int) { return tanh(x); }
+
+    template <typename real> static MPPI_HD void step(const P<real>& p, real* x, const real* u) {
+        const real uc = clamp<real>(u[0], -p.max_torque, p.max_torque);
+        real h1[H], h2[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            real acc = p.b1[i];
+            acc = fma(p.W1[i * 3 + 0], x[0], acc);
+            acc = fma(p.W1[i * 3 + 1], x[1], acc);
+            acc = fma(p.W1[i * 3 + 2], uc, acc);
+            h1[i] = tanh_(acc, p.tanh_mode);
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            real acc = p.b2[i];
+#pragma unroll
+            for (int j = 0; j < H; ++j) acc = fma(p.W2[i * H + j], h1[j], acc);
+            h2[i] = tanh_(acc, p.tanh_mode);
+        }
+        real o0 = p.b3[0], o1 = p.b3[1];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            o0 = fma(p.W3[j], h2[j], o0);
+            o1 = fma(p.W3[H + j], h2[j], o1);
+        }
+        typedef Ops<real> O;
+        const real th = O::add(x[0], o0);
+        x[0] = O::sub(remainder<real>(O::add(th, p.pi), p.two_pi), p.pi);       // pendulum_approximate.py:65
+        x[1] = O::add(x[1], o1);
+    }
+    template <typename real> static MPPI_HD real cost(const P<real>& p, const real* x, const real* u) {
+        typedef Ops<real> O;
+        const real an = O::sub(remainder<real>(O::add(x[0], p.pi), p.two_pi), p.pi);
+        return O::add(O::mul(an, an), O::mul(p.w_thdot, O::mul(x[1], x[1])));
+    }
+    template <typename real> static MPPI_HD bool has_terminal(const P<real>&) { return false; }
+    template <typename real> static MPPI_HD real terminal(const P<real>&, const real*) { return (real)0; }
 };
 
 }  // namespace mppi

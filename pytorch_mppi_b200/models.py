@@ -32,6 +32,10 @@ class AnalyticModel:
         """The `model_params` doubles of MppiFusedParams for this instance."""
         raise NotImplementedError
 
+    def param_blob_ext(self) -> list:
+        """Extra parameters too large for `model_params` (e.g. network weights); [] if none."""
+        return []
+
     @property
     def has_terminal(self) -> bool:
         return False
@@ -159,6 +163,52 @@ class LinearPoint(AnalyticModel):
 
     def terminal_cost(self, states, actions):
         return self.terminal_scale * self.state_cost(states[..., -1, :])
+
+
+class PendulumMLP(AnalyticModel):
+    """Learned pendulum dynamics of BASELINE config 4 (/root/reference/tests/pendulum_approximate.py:47-67):
+    ``x' = x + net([x, clamp(u)])`` with ``net = Linear(3,32)-Tanh-Linear(32,32)-Tanh-Linear(32,2)``, then the
+    angle is wrapped to [-pi, pi); running cost as the analytic pendulum.
+
+    Pass ``model.dynamics`` / ``model.running_cost`` to the controller: the fused kernel then evaluates the
+    network inside the rollout (weights in the kernel's constant parameter block).  The torch callables
+    below evaluate the same ``net`` module, so they are the stepped-route / simulator definition too.
+    Call ``refresh()`` after retraining ``net`` (the controller re-reads the weights when repacked).
+    """
+    model_id = _cabi.MODEL_PENDULUM_MLP
+    nx, nu = 2, 1
+    H = 32
+
+    def __init__(self, net: torch.nn.Sequential, max_torque=2.0, w_thdot=0.1, fast_tanh=False):
+        lin = [m for m in net if isinstance(m, torch.nn.Linear)]
+        act = [m for m in net if not isinstance(m, torch.nn.Linear)]
+        shapes = [tuple(l.weight.shape) for l in lin]
+        if shapes != [(self.H, 3), (self.H, self.H), (2, self.H)] or not all(isinstance(a, torch.nn.Tanh) for a in act):
+            raise ValueError("PendulumMLP expects Linear(3,32)-Tanh-Linear(32,32)-Tanh-Linear(32,2); got " + str(shapes))
+        self.net = net
+        self.max_torque, self.w_thdot, self.fast_tanh = float(max_torque), float(w_thdot), bool(fast_tanh)
+
+    def param_blob(self):
+        return [self.max_torque, self.w_thdot, 1.0 if self.fast_tanh else 0.0]
+
+    def param_blob_ext(self):
+        out = []
+        with torch.no_grad():
+            for m in self.net:
+                if isinstance(m, torch.nn.Linear):
+                    out += m.weight.detach().double().cpu().reshape(-1).tolist()
+                    out += m.bias.detach().double().cpu().reshape(-1).tolist()
+        return out
+
+    def dynamics(self, state, action):
+        with torch.no_grad():
+            u = torch.clamp(action[:, 0:1], -self.max_torque, self.max_torque)
+            nxt = state + self.net(torch.cat((state, u), dim=1))
+            th = Pendulum.angle_normalize(nxt[:, 0])
+            return torch.stack((th, nxt[:, 1]), dim=1)
+
+    def running_cost(self, state, action):
+        return Pendulum.angle_normalize(state[:, 0]) ** 2 + self.w_thdot * state[:, 1] ** 2
 
 
 def resolve_fused_model(dynamics, running_cost, terminal_state_cost) -> Optional[AnalyticModel]:

@@ -349,6 +349,14 @@ class MPPI:
         blob = self._model.param_blob() if self._model is not None else []
         for i in range(_cabi.MPPI_MODEL_PARAM_DOUBLES):
             p.model_params[i] = float(blob[i]) if i < len(blob) else 0.0
+        ext = self._model.param_blob_ext() if self._model is not None else []
+        if ext:
+            self._ext_arr = (C.c_double * len(ext))(*ext)      # host memory, read by the library at plan creation / launch
+            p.model_params_ext = C.cast(self._ext_arr, C.c_void_p)
+            p.n_model_params_ext = len(ext)
+        else:
+            p.model_params_ext = None
+            p.n_model_params_ext = 0
         self._base_flags = ((_cabi.FLAG_NULL_ACTION if self.sample_null_action else 0)
                             | (_cabi.FLAG_ABS_COST if self.noise_abs_cost else 0)
                             | (_cabi.FLAG_DIAG_SIGMA if self._diagonal_sigma else 0)
@@ -461,6 +469,10 @@ class MPPI:
             off = 4 * self._rng_counter
             self._rng_counter += chunks
         return seed, off // 4
+
+    def refresh(self):
+        """Re-read everything that feeds kernel constants (e.g. after retraining a PendulumMLP's network)."""
+        self._dirty = True
 
     def inject_noise(self, z):
         """Parity hook: the next command consumes these standard normals — shape (K,T,nu)

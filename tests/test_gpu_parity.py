@@ -390,3 +390,46 @@ def test_full_size_c5_properties():
         assert (c.U.abs() <= 2.0 + 1e-5).all() and (a.abs() <= 2.0 + 1e-5).all()
         outs.append(c.U.cpu().clone())
     assert float((outs[0] - outs[1]).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-9), (torch.float32, 5e-5)])
+def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
+    """BASELINE config 4 workload on the FUSED route: the registered PendulumMLP model evaluates the
+    3-32-32-2 tanh network inside the rollout kernel; compared with the oracle running the same torch
+    module on the CPU (injected noise, 3 closed-loop commands), and with the stepped route."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    torch.manual_seed(25)                                             # pendulum_approximate.py:31
+    net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                              torch.nn.Linear(32, 2)).to(dtype)
+    import copy
+    cpu_model = eng.PendulumMLP(copy.deepcopy(net))
+    gpu_model = eng.PendulumMLP(copy.deepcopy(net).cuda())
+    K, T = 4096, 30
+    g = torch.Generator().manual_seed(2)
+    U0 = torch.randn(T, 1, generator=g, dtype=dtype)
+    prob = orc.Problem(cpu_model.dynamics, cpu_model.running_cost, 2, torch.tensor(1.0, dtype=dtype), K=K, T=T,
+                       u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0))
+    mk = lambda dyn, cost: eng.MPPI(dyn, cost, 2, torch.tensor(1.0, dtype=dtype), num_samples=K, horizon=T, U_init=U0.clone(),
+                                    u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda")
+    fused = mk(gpu_model.dynamics, gpu_model.running_cost)
+    stepped = mk(lambda s, a: gpu_model.dynamics(s, a), lambda s, a: gpu_model.running_cost(s, a))
+    assert fused._model is gpu_model and stepped._model is None
+    U = U0.clone()
+    x = torch.tensor([3.0, 0.5], dtype=dtype)
+    for step in range(3):
+        z = torch.randn(K, T, 1, generator=g, dtype=dtype)
+        fused.inject_noise(z)
+        stepped.inject_noise(z)
+        a = fused.command(x)
+        stepped.command(x)
+        r = orc.mppi_command(prob, U, x, z)
+        U = r["U"]
+        err = float((fused.U.cpu() - U).abs().max())
+        assert err < tol, (step, err)
+        assert float((a.cpu() - r["action"]).abs().max()) < tol
+        assert float((fused.U - stepped.U).abs().max()) < tol
+        np.testing.assert_allclose(fused.cost_total.cpu().numpy(), r["cost_total"].numpy(), rtol=1e-9 if dtype == torch.float64 else 2e-4, atol=1e-4)
+        fused.U = U
+        stepped.U = U
+        x = cpu_model.dynamics(x.view(1, -1), r["action"].view(1, -1)).view(-1)
