@@ -420,15 +420,27 @@ struct PendulumMLPModel {
         real max_torque, pi, two_pi, w_thdot;
         int tanh_mode;     // 0: exp-based (abs err < 5e-7 in fp32; libm tanh in fp64), 1: MUFU.TANH (fp32 only, ~1e-3)
     };
-    // blob: [0]=max_torque [1]=w_thdot [2]=tanh_mode ; ext: W1 (H x 3 row-major), b1, W2 (H x H), b2, W3 (2 x H), b3
+    // blob: [0]=max_torque [1]=w_thdot [2]=tanh_mode ; ext: W1 (H x 3 row-major), b1, W2 (H x H), b2, W3 (2 x H), b3.
+    // W1 and W2 are stored TRANSPOSED in the parameter block (input-major), so that for a fixed input j the
+    // weights of 8 consecutive neurons are contiguous: the kernel keeps 8 independent accumulator chains
+    // in flight and fetches their weights with wide uniform constant loads.
     template <typename real> static void load(P<real>& p, const double* b, const double* ext = nullptr, int n_ext = 0) {
         p.max_torque = (real)b[0];
         p.w_thdot = (real)b[1];
         p.tanh_mode = (int)b[2];
         p.pi = (real)3.141592653589793;
         p.two_pi = (real)(2 * 3.141592653589793);
-        real* dst = p.W1;     // the six arrays are laid out contiguously in declaration order
-        for (int i = 0; i < N_EXT; ++i) dst[i] = (ext != nullptr && i < n_ext) ? (real)ext[i] : (real)0;
+        auto at = [&](int i) { return (ext != nullptr && i < n_ext) ? (real)ext[i] : (real)0; };
+        int o = 0;
+        for (int i = 0; i < H; ++i)
+            for (int c = 0; c < 3; ++c) p.W1[c * H + i] = at(o++);          // W1t[c][i] = W1[i][c]
+        for (int i = 0; i < H; ++i) p.b1[i] = at(o++);
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < H; ++j) p.W2[j * H + i] = at(o++);          // W2t[j][i] = W2[i][j]
+        for (int i = 0; i < H; ++i) p.b2[i] = at(o++);
+        for (int i = 0; i < 2 * H; ++i) p.W3[i] = at(o++);
+        p.b3[0] = at(o++);
+        p.b3[1] = at(o++);
     }
     static MPPI_HD float tanh_(float x, int mode) {
 #if defined(__CUDA_ARCH__)
@@ -448,28 +460,48 @@ struct PendulumMLPModel {
 
     template <typename real> static MPPI_HD void step(const P<real>& p, real* x, const real* u) {
         const real uc = clamp<real>(u[0], -p.max_torque, p.max_torque);
+        constexpr int NB = 8;      // neurons per block = independent FMA chains in flight
         real h1[H], h2[H];
 #pragma unroll
-        for (int i = 0; i < H; ++i) {
-            real acc = p.b1[i];
-            acc = fma(p.W1[i * 3 + 0], x[0], acc);
-            acc = fma(p.W1[i * 3 + 1], x[1], acc);
-            acc = fma(p.W1[i * 3 + 2], uc, acc);
-            h1[i] = tanh_(acc, p.tanh_mode);
+        for (int ib = 0; ib < H; ib += NB) {
+            real acc[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) acc[k] = p.b1[ib + k];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) acc[k] = fma(p.W1[0 * H + ib + k], x[0], acc[k]);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) acc[k] = fma(p.W1[1 * H + ib + k], x[1], acc[k]);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) acc[k] = fma(p.W1[2 * H + ib + k], uc, acc[k]);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) h1[ib + k] = tanh_(acc[k], p.tanh_mode);
         }
 #pragma unroll
-        for (int i = 0; i < H; ++i) {
-            real acc = p.b2[i];
+        for (int ib = 0; ib < H; ib += NB) {
+            real acc[NB];
 #pragma unroll
-            for (int j = 0; j < H; ++j) acc = fma(p.W2[i * H + j], h1[j], acc);
-            h2[i] = tanh_(acc, p.tanh_mode);
-        }
-        real o0 = p.b3[0], o1 = p.b3[1];
+            for (int k = 0; k < NB; ++k) acc[k] = p.b2[ib + k];
 #pragma unroll
-        for (int j = 0; j < H; ++j) {
-            o0 = fma(p.W3[j], h2[j], o0);
-            o1 = fma(p.W3[H + j], h2[j], o1);
+            for (int j = 0; j < H; ++j) {
+                const real hj = h1[j];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) acc[k] = fma(p.W2[j * H + ib + k], hj, acc[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) h2[ib + k] = tanh_(acc[k], p.tanh_mode);
         }
+        // output layer: 2 x 4 partial sums, combined at the end
+        real oa[4] = {p.b3[0], (real)0, (real)0, (real)0}, ob[4] = {p.b3[1], (real)0, (real)0, (real)0};
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                oa[k] = fma(p.W3[j + k], h2[j + k], oa[k]);
+                ob[k] = fma(p.W3[H + j + k], h2[j + k], ob[k]);
+            }
+        }
+        const real o0 = (oa[0] + oa[1]) + (oa[2] + oa[3]);
+        const real o1 = (ob[0] + ob[1]) + (ob[2] + ob[3]);
         typedef Ops<real> O;
         const real th = O::add(x[0], o0);
         x[0] = O::sub(remainder<real>(O::add(th, p.pi), p.two_pi), p.pi);       // pendulum_approximate.py:65
