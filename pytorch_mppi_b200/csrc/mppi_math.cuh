@@ -450,8 +450,10 @@ struct PendulumMLPModel {
             return y;
         }
         // 1 - 2 / (1 + e^{2x}) on the SFU: saturates correctly (e^{2x} -> inf gives 1, -> 0 gives -1)
-        const float t = exp2f(x * 2.885390081777927f);
-        return fmaf(-2.0f, __frcp_rn(1.0f + t), 1.0f);
+        float t, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.885390081777927f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+        return fmaf(-2.0f, r, 1.0f);
 #else
         return tanhf(x);
 #endif
