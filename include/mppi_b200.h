@@ -144,6 +144,10 @@ typedef struct MppiFusedParams {
                                     word, payload32 | (host_epoch & 0xffffffff) << 32, so the host spins on the
                                     words themselves instead of issuing a D2H copy or a stream synchronise      */
     uint64_t host_epoch;
+    void* offset_dev;            /* optional DEVICE u64: when set, the Philox counter base is read from here instead of
+                                    `offset`, and the finishing kernel adds `offset_inc` to it — lets a captured CUDA
+                                    graph of a whole command draw fresh noise on every replay                       */
+    uint64_t offset_inc;
     const double* model_params_ext;   /* HOST pointer: extra model parameters (e.g. MLP weights), read at call /
                                          plan-creation time; NULL if the model needs none                    */
     int32_t n_model_params_ext;

@@ -94,6 +94,8 @@ class MppiFusedParams(C.Structure):
         ("env_ws_stride", C.c_uint64),
         ("host_mailbox", C.c_void_p),
         ("host_epoch", C.c_uint64),
+        ("offset_dev", C.c_void_p),
+        ("offset_inc", C.c_uint64),
         ("model_params_ext", C.c_void_p),
         ("n_model_params_ext", C.c_int32),
         ("_pad1", C.c_int32),

@@ -69,6 +69,8 @@ template <typename real> struct KArgs {
     int shift, null_action, tma_ok, state_per_sample;
     int tps;   // threads cooperating on one sample's sampling/transform phases (1, 2 or 4)
     int pdl;   // launched with programmatic stream serialization
+    unsigned long long* offset_dev;   // optional device-resident Philox counter base (CUDA-graph replays)
+    unsigned long long offset_inc;
     // batched environments (MPPI_Batched, mppi.py:691-873): gridDim.y = n_env independent problems that
     // share the noise stream; per-environment buffers are strided
     int n_env;
@@ -319,9 +321,10 @@ __device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, boo
     } else if (active) {
         constexpr int PER = Normals<real>::PER_CALL;
         real* col = sm.rows + s_;
+        const unsigned long long off = a.offset_dev != nullptr ? __ldcg(a.offset_dev) : a.offset;
         for (int c = g_; c * PER < R; c += a.tps) {
             real tmp[PER];
-            Normals<real>::draw(a.seed, kg, a.offset + (unsigned long long)c, tmp);
+            Normals<real>::draw(a.seed, kg, off + (unsigned long long)c, tmp);
 #pragma unroll
             for (int q = 0; q < PER; ++q)
                 if (c * PER + q < R) col[(c * PER + q) * LD] = tmp[q];
@@ -577,6 +580,7 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
     if (tid == 0) {
         a.stats[0] = numd[0];
         a.stats[1] = eta;
+        if (a.offset_dev != nullptr && blockIdx.y == 0) *a.offset_dev += a.offset_inc;   // every sampler of this command is done
     }
     // Host delivery: each action value goes out as self-validating 8-byte words (payload32 | epoch32), so
     // the host sees a value as soon as its own store lands — no system-wide fence, no separate flag.

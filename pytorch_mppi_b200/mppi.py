@@ -379,6 +379,10 @@ class MPPI:
         dbg = getattr(self, "_debug_clocks", None)
         p.debug_clocks = None if dbg is None else dbg.data_ptr()
         p.n_env, p.env_u_stride, p.env_ws_stride = 0, 0, 0
+        od = getattr(self, "_offset_dev", None)
+        p.offset_dev = None if od is None else od.data_ptr()
+        per = 4 if self.dtype == torch.float32 else 2
+        p.offset_inc = (self._noise_rows() + per - 1) // per
         p.host_mailbox = None
         p.host_epoch = 0
         self._variant_pack(p)
@@ -500,9 +504,79 @@ class MPPI:
     # public API (mppi.py:208-290)
     # ------------------------------------------------------------------------------------------
     def compile(self, **kwargs):
-        """API compatibility (mppi.py:208-215).  The fused route is already one kernel; on the stepped
-        route the user's callables run as given.  No tracing compiler is involved."""
+        """The reference wraps the plugins in torch.compile (mppi.py:208-215).  Here: the fused route is
+        already one kernel; on the stepped route the WHOLE command — sampling kernel, the T-loop of the
+        user's callables, cost accumulation, softmin update — is captured once into a CUDA graph and
+        replayed (the Philox counter lives in device memory so every replay draws fresh noise).  The
+        callables must be capture-safe (no host syncs, no data-dependent Python control flow)."""
         self._compile_kwargs = kwargs
+        self._graph_mode = self._model is None
+        self._graphs = {}
+
+    # ---- CUDA-graph replay of the stepped route ---------------------------------------------------
+    def _graph_eligible(self, state):
+        return (getattr(self, "_graph_mode", False) and self._z_inject is None and self._z_out is None and self._world == 1
+                and self.specific_action_sampler is None)
+
+    def _command_graphed(self, state, shift):
+        st = torch.as_tensor(state).to(self.d, self.dtype)
+        key = (bool(shift), tuple(st.shape))
+        if key not in self._graphs:
+            self._capture_graph(key, st, shift)
+        g, st_static, action_static = self._graphs[key]
+        st_static.copy_(st)
+        g.replay()
+        self._cmd_count += 1
+        self._materialized_at["noise"] = self._cmd_count
+        self._last = None
+        self.cost_total = self._cost_buf
+        out = action_static.clone()
+        return out[0] if self.u_per_command == 1 else out
+
+    def _nominal_snapshot(self):
+        snap = {"U": self._Ubuf.clone()}
+        if getattr(self, "_Abuf", None) is not None:
+            snap["A"] = self._Abuf.clone()
+        if getattr(self, "_theta", None) is not None:
+            snap["theta"] = self._theta.clone()
+        return snap
+
+    def _nominal_restore(self, snap):
+        self._Ubuf.copy_(snap["U"])
+        if "A" in snap:
+            self._Abuf.copy_(snap["A"])
+        if "theta" in snap:
+            self._theta.copy_(snap["theta"])
+
+    def _capture_graph(self, key, st, shift):
+        if getattr(self, "_offset_dev", None) is None:
+            # continue the host-side stream on the device: same seed, counter where the host counter stands
+            if self._rng_seed is not None:
+                self._graph_seed, start = self._rng_seed, self._rng_counter
+            else:
+                self._graph_seed, start = self._next_rng()
+            self._offset_dev = torch.full((1,), start, dtype=torch.int64, device=self.d)
+            self._dirty = True
+        if self._dirty:
+            self._pack()
+        st_static = st.clone()
+        snap = self._nominal_snapshot()
+        off0 = self._offset_dev.clone()
+        cur = torch.cuda.current_stream(self.d)
+        side = torch.cuda.Stream(device=self.d)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                       # warm-up: allocator, geometry cache, lazy module loads
+            for _ in range(2):
+                self._command_stepped(st_static, shift)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.d)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            p, action = self._begin_command(st_static, shift)
+            action = self._stepped_body(p, action, st_static)
+        self._nominal_restore(snap)                          # the warm-up commands were real ones: undo them
+        self._offset_dev.copy_(off0)
+        self._graphs[key] = (g, st_static, action)
 
     def get_params(self):
         return f"K={self.K} T={self.T} M={self.M} lambda={self.lambda_} noise_mu={self.noise_mu.cpu().numpy()} noise_sigma={self.noise_sigma.cpu().numpy()}".replace(
@@ -544,6 +618,8 @@ class MPPI:
             self._pack()
         if self._model is not None:
             return self._command_fused(state, shift_nominal_trajectory)
+        if self._graph_eligible(state):
+            return self._command_graphed(state, shift_nominal_trajectory)
         return self._command_stepped(state, shift_nominal_trajectory)
 
     # ------------------------------------------------------------------------------------------
@@ -582,6 +658,8 @@ class MPPI:
             self._z_inject = None
             return self._z_keep.data_ptr(), 0, 0
         self._z_keep = None
+        if getattr(self, "_offset_dev", None) is not None:     # counter lives on the device (CUDA-graph mode)
+            return None, self._graph_seed, 0
         seed, off = self._next_rng()
         return None, seed, off
 
@@ -713,6 +791,12 @@ class MPPI:
             state = torch.tensor(state)
         st = state.to(dtype=self.dtype, device=self.d)                                     # mppi.py:262-264
         p, action = self._begin_command(st, shift)
+        out = self._stepped_body(p, action, st)
+        return out[0] if self.u_per_command == 1 else out
+
+    def _stepped_body(self, p, action, st):
+        """Everything of one stepped command that runs on the device; returns the (u_per_command, nu) action."""
+        lib = self._lib
         self.state = st
         stream = torch.cuda.current_stream(self.d).cuda_stream
         K, T, nu = self._K_local, self.T, self.nu
@@ -743,10 +827,10 @@ class MPPI:
         p.cost_total = rollout.data_ptr()
         _cabi.check(lib.mppi_softmin_update(C.byref(p), rollout.data_ptr(), self._eps_for_update().data_ptr(), stream),
                     "mppi_softmin_update")
-        out = self._finish_command(p, action, stream)
+        self._finish_command(p, action, stream)
         self._states = states
         self._actions = actions / self._u_scale if actions is not None else None         # mppi.py:412
-        return out
+        return action
 
     def _rollout_single(self, perturbed_actions, stream):
         """mppi.py:297-332"""

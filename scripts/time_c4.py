@@ -27,3 +27,14 @@ for fast in (False, True):
         run(f"fused   fp32 fast_tanh={fast} bt={bt}", m.dynamics, m.running_cost, 50, block_threads=bt)
 m = eng.PendulumMLP(net)
 run("stepped fp32 (torch MLP, Python T-loop)", lambda s, a: m.dynamics(s, a), lambda s, a: m.running_cost(s, a), 10)
+c = eng.MPPI(lambda s, a: m.dynamics(s, a), lambda s, a: m.running_cost(s, a), 2, torch.tensor(1.0), num_samples=K, horizon=T,
+             u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=1)
+c.compile()
+x = [3.0, 0.5]
+for _ in range(5): c.command(x)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20): c.command(x)
+e1.record(); torch.cuda.synchronize()
+print(f"stepped fp32 + compile() (CUDA graph replay): {e0.elapsed_time(e1)/20*1e3:.1f} us/command")

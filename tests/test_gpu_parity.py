@@ -433,3 +433,31 @@ def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
         fused.U = U
         stepped.U = U
         x = cpu_model.dynamics(x.view(1, -1), r["action"].view(1, -1)).view(-1)
+
+
+@pytest.mark.parametrize("variant", ["mppi", "smppi", "kmppi"])
+def test_compile_cuda_graph_replay_equals_eager_stepped(variant):
+    """compile() on the stepped route captures the whole command in a CUDA graph; replays must equal the
+    eager stepped commands bit for bit (same seed; the Philox counter advances on the device)."""
+    import pytorch_mppi_b200 as eng
+    dyn_cpu, dyn_gpu, cost = _mlp_dynamics(torch.float32, "cuda")
+    cls = {"mppi": eng.MPPI, "smppi": eng.SMPPI, "kmppi": eng.KMPPI}[variant]
+    kw = {"smppi": dict(w_action_seq_cost=2.0, action_max=torch.tensor(2.0)), "kmppi": dict(num_support_pts=6)}.get(variant, {})
+
+    def make():
+        return cls(dyn_gpu, cost, 2, torch.tensor(1.0), num_samples=2048, horizon=12, U_init=torch.zeros(12, 1),
+                   u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=11, **kw)
+    eager, graphed = make(), make()
+    graphed.compile()
+    x = torch.tensor([3.0, 0.5])
+    for step in range(4):
+        a1 = eager.command(x)
+        a2 = graphed.command(x)
+        assert torch.equal(a1, a2), (variant, step)
+        assert torch.equal(eager.U, graphed.U)
+        assert torch.equal(eager.cost_total, graphed.cost_total)
+        x = dyn_cpu(x.view(1, -1), a1.cpu().view(1, -1)).view(-1)
+    assert len(graphed._graphs) == 1
+    # refinement without shifting is a second captured graph
+    assert torch.equal(eager.command(x, shift_nominal_trajectory=False), graphed.command(x, shift_nominal_trajectory=False))
+    assert len(graphed._graphs) == 2
