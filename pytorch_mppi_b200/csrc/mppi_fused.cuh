@@ -853,7 +853,7 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
 // =================================================================================================
 template <class Model, typename real, int VARIANT, bool BATCHED>
 __global__ void __launch_bounds__(512) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
-                                                            const typename Model::template P<real> mp) {
+                                                            const __grid_constant__ typename Model::template P<real> mp) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;
     extern __shared__ __align__(16) unsigned char smem[];

@@ -522,7 +522,13 @@ class MPPI:
         st = torch.as_tensor(state).to(self.d, self.dtype)
         key = (bool(shift), tuple(st.shape))
         if key not in self._graphs:
-            self._capture_graph(key, st, shift)
+            try:
+                self._capture_graph(key, st, shift)
+            except Exception as e:     # plugin not capture-safe (host sync, H2D copy, ...): stay on the eager route
+                logger.warning("compile(): CUDA-graph capture failed (%s); continuing without graphs", e)
+                self._graph_mode = False
+                torch.cuda.synchronize(self.d)
+                return self._command_stepped(state, shift)
         g, st_static, action_static = self._graphs[key]
         st_static.copy_(st)
         g.replay()

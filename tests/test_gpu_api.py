@@ -14,16 +14,28 @@ GOAL = torch.tensor([2.0, 2.0], dtype=DT)
 B = torch.tensor([[1.0, 0.0], [0.0, -1.0]], dtype=DT)
 
 
+_DEV_CACHE = {}
+
+
+def _on(t, like):
+    """device/dtype copy of a module-level constant, cached so the plugins never issue a host->device copy
+    on the hot path (which would also be illegal inside CUDA-graph capture)"""
+    key = (id(t), like.device, like.dtype)
+    if key not in _DEV_CACHE:
+        _DEV_CACHE[key] = t.to(like.device, like.dtype)
+    return _DEV_CACHE[key]
+
+
 def lin_dyn(s, a):
-    return s + a @ B.to(s.device, s.dtype).T
+    return s + a @ _on(B, s).T
 
 
 def quad_cost(s, a):
-    return ((GOAL.to(s.device, s.dtype) - s) ** 2).sum(-1)
+    return ((_on(GOAL, s) - s) ** 2).sum(-1)
 
 
 def term_cost(states, actions):
-    return ((GOAL.to(states.device, states.dtype) - states[..., -1, :]) ** 2).sum(-1)
+    return ((_on(GOAL, states) - states[..., -1, :]) ** 2).sum(-1)
 
 
 def plugins(route, terminal=False):
