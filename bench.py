@@ -292,6 +292,12 @@ def run_engine(args, wl):
     e2e_s = float(e2e_t.item())
     e2e_value = K_global * T * n_e2e / e2e_s
     clocks = stop_clock_sampler(sampler, sfile, local_rank, t_begin, t_end) if rank == 0 else None
+    ranks_agree = True
+    if world > 1:      # every rank must hold the bit-identical nominal sequence (no broadcast is ever issued)
+        mine = ctrl.U.detach().clone().contiguous()
+        allU = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allU, mine)
+        ranks_agree = all(torch.equal(allU[0], u) for u in allU) and bool(torch.isfinite(mine).all())
 
     if rank == 0:
         info = ctrl.launch_info
@@ -309,6 +315,7 @@ def run_engine(args, wl):
                        "commands_per_s": 1e3 / ms_per_step, "back_to_back_ms_per_step": b2b_ms,
                        "l2": "flushed between timed iterations (256 MiB memset), per-step CUDA events on the launch stream",
                        "parallelism": f"K sharded over {world} GPU(s), exchange={args.exchange if world > 1 else 'none'}",
+                       "ranks_hold_identical_U": ranks_agree,
                        "grid": info.grid_blocks, "block": info.block_threads, "threads_per_sample": info.threads_per_sample,
                        "smem_bytes": info.smem_bytes, "regs": info.regs_per_thread},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
