@@ -199,6 +199,9 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------------
 def run_engine(args, wl):
     import torch.distributed as dist
+    from pytorch_mppi_b200 import build as _build
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0 and _build.needs_build() and not os.path.exists(_build.OUT):
+        _build.build()      # normally the in-tree .so travels with the snapshot; build only if it is absent
     import pytorch_mppi_b200 as eng
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

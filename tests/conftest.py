@@ -20,3 +20,10 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The C-ABI library is built in-tree once per session (nvcc cross-compiles without a GPU)."""
+    from pytorch_mppi_b200 import build
+    build.build()
