@@ -49,7 +49,11 @@ typedef enum MppiDType { MPPI_F32 = 0, MPPI_F64 = 1 } MppiDType;
 typedef enum MppiModel {
     MPPI_MODEL_PENDULUM = 1,      /* /root/reference/tests/pendulum.py:30-60                      */
     MPPI_MODEL_LINEAR_POINT = 2,  /* tests/test_mppi.py:24-51 and tests/smooth_mppi.py:29-142    */
-    MPPI_MODEL_PENDULUM_MLP = 3   /* tests/pendulum_approximate.py:47-67 (3-32-32-2 tanh residual MLP) */
+    MPPI_MODEL_PENDULUM_MLP = 3,  /* tests/pendulum_approximate.py:47-67 (3-32-32-2 tanh residual MLP) */
+    MPPI_MODEL_USER = 100         /* a user-written model compiled into a variant of this library (build with
+                                     -DMPPI_USER_MODEL_HEADER=\"file\"; see pytorch_mppi_b200.models.CudaModel): the
+                                     reference accepts arbitrary Python callables (mppi.py:63-64) — this is the
+                                     compiled-in equivalent for analytic dynamics/costs                        */
 } MppiModel;
 
 /* model_params layouts (doubles):

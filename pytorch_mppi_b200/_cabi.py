@@ -21,6 +21,7 @@ ABI_VERSION = 1
 VARIANT_MPPI, VARIANT_SMPPI, VARIANT_KMPPI = 0, 1, 2
 F32, F64 = 0, 1
 MODEL_PENDULUM, MODEL_LINEAR_POINT, MODEL_PENDULUM_MLP = 1, 2, 3
+MODEL_USER = 100
 FLAG_SHIFT = 1 << 0
 FLAG_NULL_ACTION = 1 << 1
 FLAG_ABS_COST = 1 << 2
@@ -148,27 +149,33 @@ SYMBOLS = [
 ]
 
 _lib = None
+_variants = {}
 
 
 class MppiLibraryError(RuntimeError):
     pass
 
 
-def load():
-    """Load the shared library and bind every declared symbol; raises if anything is missing."""
+def load(path=None):
+    """Load the shared library (or a user-model variant at `path`) and bind every declared symbol;
+    raises if anything is missing."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+    if path is None:
+        if _lib is not None:
+            return _lib
+        path = LIB_PATH
+    elif path in _variants:
+        return _variants[path]
+    if not os.path.exists(path):
         raise MppiLibraryError(
-            f"{LIB_PATH} not found: build it with `python -m pytorch_mppi_b200.build` "
+            f"{path} not found: build it with `python -m pytorch_mppi_b200.build` "
             "(nvcc, sm_100a). pytorch_mppi_b200 has no CPU or eager-PyTorch fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, restype, argtypes in SYMBOLS:
         try:
             fn = getattr(lib, name)
         except AttributeError as e:
-            raise MppiLibraryError(f"{LIB_PATH} does not export `{name}`; rebuild the library") from e
+            raise MppiLibraryError(f"{path} does not export `{name}`; rebuild the library") from e
         fn.restype = restype
         fn.argtypes = argtypes
     v = lib.mppi_b200_abi_version()
@@ -176,7 +183,10 @@ def load():
         raise MppiLibraryError(f"ABI version mismatch: library {v}, python {ABI_VERSION}")
     if lib.mppi_abi_layout(0) != C.sizeof(MppiFusedParams):
         raise MppiLibraryError("MppiFusedParams layout differs between the ctypes mirror and the library")
-    _lib = lib
+    if path == LIB_PATH:
+        _lib = lib
+    else:
+        _variants[path] = lib
     return lib
 
 

@@ -43,5 +43,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_user_model(header_text: str, verbose: bool = False) -> str:
+    """JIT-build a variant of the library with a user model compiled in (the built-in models are
+    compiled out to keep the build short).  Cached by the hash of the header text under csrc/_user/."""
+    import hashlib
+    tag = hashlib.sha1((header_text + open(os.path.join(CSRC, "mppi_fused.cuh")).read()
+                        + open(os.path.join(CSRC, "mppi_math.cuh")).read() + open(SRC).read()).encode()).hexdigest()[:16]
+    udir = os.path.join(CSRC, "_user")
+    os.makedirs(udir, exist_ok=True)
+    hdr = os.path.join(udir, f"user_model_{tag}.cuh")
+    out = os.path.join(udir, f"libmppi_b200_user_{tag}.so")
+    if os.path.exists(out):
+        return out
+    with open(hdr, "w") as f:
+        f.write(header_text)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, f'-DMPPI_USER_MODEL_HEADER="{hdr}"', "-DMPPI_ONLY_USER_MODEL", "-o", out, SRC]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for the user model:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -464,11 +464,16 @@ int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* inf
     int rc = validate(p, true);
     if (rc) return rc;
     switch (p->model) {
+#ifndef MPPI_ONLY_USER_MODEL
         case MPPI_MODEL_PENDULUM: return run_fused_dtype<PendulumModel>(p, s, info);
         case MPPI_MODEL_LINEAR_POINT: return run_fused_dtype<LinearPointModel>(p, s, info);
         case MPPI_MODEL_PENDULUM_MLP:
             if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) return MPPI_ERR_BAD_ARG;
             return run_fused_dtype<PendulumMLPModel>(p, s, info);
+#endif
+#ifdef MPPI_USER_MODEL_HEADER
+        case MPPI_MODEL_USER: return run_fused_dtype<UserModel>(p, s, info);
+#endif
     }
     return MPPI_ERR_UNSUPPORTED;
 }
@@ -639,12 +644,17 @@ int mppi_plan_create(const MppiFusedParams* p, void** plan_out) {
     Plan* pl = new (std::nothrow) Plan();
     if (pl == nullptr) return MPPI_ERR_BAD_ARG;
     switch (p->model) {
+#ifndef MPPI_ONLY_USER_MODEL
         case MPPI_MODEL_PENDULUM: rc = build_plan_dtype<PendulumModel>(p, pl); break;
         case MPPI_MODEL_LINEAR_POINT: rc = build_plan_dtype<LinearPointModel>(p, pl); break;
         case MPPI_MODEL_PENDULUM_MLP:
             rc = (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr)
                      ? (int)MPPI_ERR_BAD_ARG : build_plan_dtype<PendulumMLPModel>(p, pl);
             break;
+#endif
+#ifdef MPPI_USER_MODEL_HEADER
+        case MPPI_MODEL_USER: rc = build_plan_dtype<UserModel>(p, pl); break;
+#endif
         default: rc = MPPI_ERR_UNSUPPORTED;
     }
     if (rc) {
@@ -780,12 +790,19 @@ int mppi_materialize(const MppiFusedParams* p, void* perturbed_action, void* noi
              : run_sample_any<double>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s);
     if (rc || states == nullptr) return rc;
     switch (p->model) {
+#ifndef MPPI_ONLY_USER_MODEL
         case MPPI_MODEL_PENDULUM:
             return p->dtype == MPPI_F32 ? run_states<PendulumModel, float>(p, perturbed_action, states, s)
                                         : run_states<PendulumModel, double>(p, perturbed_action, states, s);
         case MPPI_MODEL_LINEAR_POINT:
             return p->dtype == MPPI_F32 ? run_states<LinearPointModel, float>(p, perturbed_action, states, s)
                                         : run_states<LinearPointModel, double>(p, perturbed_action, states, s);
+#endif
+#ifdef MPPI_USER_MODEL_HEADER
+        case MPPI_MODEL_USER:
+            return p->dtype == MPPI_F32 ? run_states<UserModel, float>(p, perturbed_action, states, s)
+                                        : run_states<UserModel, double>(p, perturbed_action, states, s);
+#endif
     }
     return MPPI_ERR_UNSUPPORTED;
 }

@@ -529,3 +529,8 @@ struct PendulumMLPModel {
 };
 
 }  // namespace mppi
+
+// A user model (struct mppi::UserModel with the interface above) is injected at build time.
+#ifdef MPPI_USER_MODEL_HEADER
+#include MPPI_USER_MODEL_HEADER
+#endif

@@ -211,6 +211,103 @@ class PendulumMLP(AnalyticModel):
         return Pendulum.angle_normalize(state[:, 0]) ** 2 + self.w_thdot * state[:, 1] ** 2
 
 
+class CudaModel(AnalyticModel):
+    """A user-written analytic model compiled INTO the fused kernel.
+
+    The reference takes arbitrary Python callables (mppi.py:63-64); those cannot be inlined into CUDA, so for
+    analytic dynamics/costs you give the two function bodies as CUDA C++ and the engine JIT-builds (nvcc, cached)
+    a variant of its library with your model in the registry.  Inside the bodies:
+
+        x[NX]      state (read/write in `step_code`, read-only in `cost_code` / `terminal_code`)
+        u[NU]      action, already multiplied by u_scale
+        p[...]     your `params` (cast to the controller dtype)
+        real       the controller dtype; O::add/sub/mul/div are individually rounded ops (use them if you want
+                   bit-level agreement with an eager fp32 torch implementation), sinf/exp/... via O::sin_, O::exp_
+
+    `cost_code` and `terminal_code` must `return` a `real`.  `dynamics` / `running_cost` / `terminal_cost`
+    are the torch callables of the same model (used by the stepped route, by `get_rollouts`, and as your
+    simulator); pass ``model.dynamics`` / ``model.running_cost`` to the controller as usual.
+    """
+    model_id = _cabi.MODEL_USER
+
+    def __init__(self, nx, nu, step_code, cost_code, params=(), terminal_code=None, dynamics=None, running_cost=None,
+                 terminal_cost=None):
+        if not (1 <= nx <= _cabi.MPPI_MAX_NX and 1 <= nu <= _cabi.MPPI_MAX_NU):
+            raise ValueError(f"nx <= {_cabi.MPPI_MAX_NX} and nu <= {_cabi.MPPI_MAX_NU} required")
+        self.nx, self.nu = int(nx), int(nu)
+        self.params = [float(v) for v in params]
+        self._step_code, self._cost_code, self._terminal_code = step_code, cost_code, terminal_code
+        self._dyn, self._cost, self._term = dynamics, running_cost, terminal_cost
+        self._lib_path = None
+
+    @property
+    def has_terminal(self):
+        return self._terminal_code is not None
+
+    def param_blob(self):
+        return self.params[: _cabi.MPPI_MODEL_PARAM_DOUBLES]
+
+    def param_blob_ext(self):
+        return self.params[_cabi.MPPI_MODEL_PARAM_DOUBLES:]
+
+    def header_text(self):
+        n = max(len(self.params), 1)
+        term = self._terminal_code if self._terminal_code is not None else "return (real)0;"
+        return f"""// generated by pytorch_mppi_b200.models.CudaModel
+namespace mppi {{
+struct UserModel {{
+    static const int NX = {self.nx}, NU = {self.nu}, NP = {n};
+    template <typename real> struct P {{ real v[NP]; }};
+    template <typename real> static void load(P<real>& P_, const double* b, const double* ext = nullptr, int n_ext = 0) {{
+        for (int i = 0; i < NP; ++i)
+            P_.v[i] = (real)(i < {_cabi.MPPI_MODEL_PARAM_DOUBLES} ? b[i] : (ext != nullptr && i - {_cabi.MPPI_MODEL_PARAM_DOUBLES} < n_ext ? ext[i - {_cabi.MPPI_MODEL_PARAM_DOUBLES}] : 0.0));
+    }}
+    template <typename real> static MPPI_HD void step(const P<real>& P_, real* x, const real* u) {{
+        typedef Ops<real> O;
+        const real* p = P_.v;
+        (void)p;
+        {self._step_code}
+    }}
+    template <typename real> static MPPI_HD real cost(const P<real>& P_, const real* x, const real* u) {{
+        typedef Ops<real> O;
+        const real* p = P_.v;
+        (void)p; (void)u;
+        {self._cost_code}
+    }}
+    template <typename real> static MPPI_HD bool has_terminal(const P<real>&) {{ return {"true" if self.has_terminal else "false"}; }}
+    template <typename real> static MPPI_HD real terminal(const P<real>& P_, const real* x) {{
+        typedef Ops<real> O;
+        const real* p = P_.v;
+        (void)p; (void)x;
+        {term}
+    }}
+}};
+}}  // namespace mppi
+"""
+
+    def library_path(self):
+        """Path of the (cached) variant library with this model compiled in; builds it on first use."""
+        if self._lib_path is None:
+            from . import build
+            self._lib_path = build.build_user_model(self.header_text())
+        return self._lib_path
+
+    def dynamics(self, state, action):
+        if self._dyn is None:
+            raise NotImplementedError("this CudaModel was created without a torch `dynamics` callable")
+        return self._dyn(state, action)
+
+    def running_cost(self, state, action):
+        if self._cost is None:
+            raise NotImplementedError("this CudaModel was created without a torch `running_cost` callable")
+        return self._cost(state, action)
+
+    def terminal_cost(self, states, actions):
+        if self._term is None:
+            raise NotImplementedError("this CudaModel was created without a torch `terminal_cost` callable")
+        return self._term(states, actions)
+
+
 def resolve_fused_model(dynamics, running_cost, terminal_state_cost) -> Optional[AnalyticModel]:
     """The registered model these plugins belong to, or None if they are not (all) bound methods of
     one registered model — in which case the controller uses the per-step path."""

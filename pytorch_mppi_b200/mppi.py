@@ -172,6 +172,8 @@ class MPPI:
             m = resolve_fused_model(dynamics, running_cost, terminal_state_cost)
             if m is not None and m.nx == self.nx and m.nu == self.nu:
                 self._model = m
+                if hasattr(m, "library_path"):          # user model: its kernels live in a JIT-built variant library
+                    self._lib = _cabi.load(m.library_path())
         self._block_threads = int(block_threads)
         self._pdl = os.environ.get("MPPI_B200_PDL", "1") != "0"
         self._threads_per_sample = int(threads_per_sample)

@@ -461,3 +461,59 @@ def test_compile_cuda_graph_replay_equals_eager_stepped(variant):
     # refinement without shifting is a second captured graph
     assert torch.equal(eager.command(x, shift_nominal_trajectory=False), graphed.command(x, shift_nominal_trajectory=False))
     assert len(graphed._graphs) == 2
+
+
+def test_user_cuda_model_equals_builtin_and_oracle():
+    """CudaModel: the pendulum written as user CUDA snippets gives bit-identical commands to the built-in
+    registered model; a model that exists nowhere else (double integrator with drag, quadratic + terminal
+    cost) matches the oracle running its torch definition."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    from tests.test_host_logic import PEND_STEP, PEND_COST
+    ref = eng.Pendulum()
+    um = eng.CudaModel(2, 1, PEND_STEP, PEND_COST, params=[10.0, 1.0, 1.0, 0.05, 2.0, 8.0, 0.1],
+                       dynamics=ref.dynamics, running_cost=ref.running_cost)
+    outs = []
+    for model in (ref, um):
+        c = eng.MPPI(model.dynamics, model.running_cost, 2, torch.tensor(10.0), num_samples=4096, horizon=25,
+                     U_init=torch.zeros(25, 1), u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=3)
+        assert c._model is model
+        outs.append(torch.stack([c.command([3.0, 0.4]).clone() for _ in range(3)]))
+    assert torch.equal(outs[0], outs[1])
+
+    # a brand-new model: x = (pos, vel); vel' = vel + dt*(u - c*vel); pos' = pos + dt*vel'
+    dt_, drag, goal, wv, wT = 0.1, 0.3, 1.5, 0.05, 4.0
+    step = "real v = O::add(x[1], O::mul(p[0], O::sub(u[0], O::mul(p[1], x[1])))); x[0] = O::add(x[0], O::mul(p[0], v)); x[1] = v;"
+    cost = "real d = O::sub(x[0], p[2]); return O::add(O::mul(d, d), O::mul(p[3], O::mul(x[1], x[1])));"
+    term = "real d = O::sub(x[0], p[2]); return O::mul(p[4], O::mul(d, d));"
+
+    def dyn(s, a):
+        v = s[:, 1] + dt_ * (a[:, 0] - drag * s[:, 1])
+        return torch.stack((s[:, 0] + dt_ * v, v), dim=1)
+
+    def rc(s, a):
+        return (s[:, 0] - goal) ** 2 + wv * s[:, 1] ** 2
+
+    def tc(states, actions):
+        return wT * (states[..., -1, 0] - goal) ** 2
+    m = eng.CudaModel(2, 1, step, cost, params=[dt_, drag, goal, wv, wT], terminal_code=term, dynamics=dyn, running_cost=rc,
+                      terminal_cost=tc)
+    K, T = 1500, 18
+    dt = torch.float64
+    g = torch.Generator().manual_seed(4)
+    U0 = torch.randn(T, 1, generator=g, dtype=dt) * 0.3
+    c = eng.MPPI(m.dynamics, m.running_cost, 2, torch.tensor(0.5, dtype=dt), num_samples=K, horizon=T, U_init=U0.clone(),
+                 terminal_state_cost=m.terminal_cost, u_max=torch.tensor(1.0, dtype=dt), device="cuda")
+    assert c._model is m
+    prob = orc.Problem(dyn, rc, 2, torch.tensor(0.5, dtype=dt), K=K, T=T, u_max=torch.tensor(1.0, dtype=dt), terminal_state_cost=tc)
+    U = U0.clone()
+    x = torch.tensor([0.0, 0.0], dtype=dt)
+    for _ in range(3):
+        z = torch.randn(K, T, 1, generator=g, dtype=dt)
+        c.inject_noise(z)
+        a = c.command(x)
+        r = orc.mppi_command(prob, U, x, z)
+        U = r["U"]
+        assert float((c.U.cpu() - U).abs().max()) < 1e-10
+        np.testing.assert_allclose(c.states.cpu().numpy(), r["states"].numpy(), atol=1e-10)
+        x = dyn(x.view(1, -1), r["action"].view(1, -1)).view(-1)
