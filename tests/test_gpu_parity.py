@@ -469,10 +469,9 @@ def test_user_cuda_model_equals_builtin_and_oracle():
     cost) matches the oracle running its torch definition."""
     import pytorch_mppi_b200 as eng
     from oracle import mppi_oracle as orc
-    from tests.test_host_logic import PEND_STEP, PEND_COST
+    from tests import user_models as um_
     ref = eng.Pendulum()
-    um = eng.CudaModel(2, 1, PEND_STEP, PEND_COST, params=[10.0, 1.0, 1.0, 0.05, 2.0, 8.0, 0.1],
-                       dynamics=ref.dynamics, running_cost=ref.running_cost)
+    um = um_.pendulum_user_model()
     outs = []
     for model in (ref, um):
         c = eng.MPPI(model.dynamics, model.running_cost, 2, torch.tensor(10.0), num_samples=4096, horizon=25,
@@ -481,23 +480,8 @@ def test_user_cuda_model_equals_builtin_and_oracle():
         outs.append(torch.stack([c.command([3.0, 0.4]).clone() for _ in range(3)]))
     assert torch.equal(outs[0], outs[1])
 
-    # a brand-new model: x = (pos, vel); vel' = vel + dt*(u - c*vel); pos' = pos + dt*vel'
-    dt_, drag, goal, wv, wT = 0.1, 0.3, 1.5, 0.05, 4.0
-    step = "real v = O::add(x[1], O::mul(p[0], O::sub(u[0], O::mul(p[1], x[1])))); x[0] = O::add(x[0], O::mul(p[0], v)); x[1] = v;"
-    cost = "real d = O::sub(x[0], p[2]); return O::add(O::mul(d, d), O::mul(p[3], O::mul(x[1], x[1])));"
-    term = "real d = O::sub(x[0], p[2]); return O::mul(p[4], O::mul(d, d));"
-
-    def dyn(s, a):
-        v = s[:, 1] + dt_ * (a[:, 0] - drag * s[:, 1])
-        return torch.stack((s[:, 0] + dt_ * v, v), dim=1)
-
-    def rc(s, a):
-        return (s[:, 0] - goal) ** 2 + wv * s[:, 1] ** 2
-
-    def tc(states, actions):
-        return wT * (states[..., -1, 0] - goal) ** 2
-    m = eng.CudaModel(2, 1, step, cost, params=[dt_, drag, goal, wv, wT], terminal_code=term, dynamics=dyn, running_cost=rc,
-                      terminal_cost=tc)
+    m = um_.integrator_user_model()
+    dyn, rc, tc = um_.int_dyn, um_.int_cost, um_.int_term
     K, T = 1500, 18
     dt = torch.float64
     g = torch.Generator().manual_seed(4)

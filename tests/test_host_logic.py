@@ -140,27 +140,13 @@ def test_kernel_matrices_identities():
     assert len(idx) >= 2
 
 
-PEND_STEP = """
-    real uc = clamp<real>(u[0], -p[4], p[4]);
-    real acc = O::add(O::mul((real)(3 * 10.0 / 2), O::sin_(x[0])), O::mul((real)3.0, uc));
-    real thd = clamp<real>(O::add(x[1], O::mul(acc, p[3])), -p[5], p[5]);
-    x[0] = O::add(x[0], O::mul(thd, p[3]));
-    x[1] = thd;
-"""
-PEND_COST = """
-    const real pi = (real)3.141592653589793, two_pi = (real)(2 * 3.141592653589793);
-    real an = O::sub(remainder<real>(O::add(x[0], pi), two_pi), pi);
-    return O::add(O::mul(an, an), O::mul(p[6], O::mul(x[1], x[1])));
-"""
-
-
 def test_cuda_model_builds_a_variant_library():
     """A user-written model is JIT-built (nvcc, no GPU needed) into a variant library that exports the
     whole C ABI; the controller-side resolution treats its bound methods like any registered model."""
     from pytorch_mppi_b200 import _cabi
+    from tests.user_models import pendulum_user_model
     ref = eng.Pendulum()
-    m = eng.CudaModel(2, 1, PEND_STEP, PEND_COST, params=[10.0, 1.0, 1.0, 0.05, 2.0, 8.0, 0.1],
-                      dynamics=ref.dynamics, running_cost=ref.running_cost)
+    m = pendulum_user_model()
     assert "struct UserModel" in m.header_text() and "NX = 2, NU = 1" in m.header_text()
     assert resolve_fused_model(m.dynamics, m.running_cost, None) is m
     lib = _cabi.load(m.library_path())
