@@ -148,6 +148,12 @@ typedef struct MppiFusedParams {
                                     word, payload32 | (host_epoch & 0xffffffff) << 32, so the host spins on the
                                     words themselves instead of issuing a D2H copy or a stream synchronise      */
     uint64_t host_epoch;
+    uint64_t torch_rng_total;    /* 0: the engine's own stream (one Philox subsequence per sample).  > 0: reproduce the
+                                    stream of `torch.randn(K,T,nu, device="cuda")` (ATen/native/cuda/
+                                    DistributionTemplates.h:50-100): element li of the flat (K,T,nu) tensor comes from
+                                    thread idx = li % total, loop slot (li / total), with total = 256 * grid — so a
+                                    reference controller on device="cuda" and this engine draw identical noise from
+                                    the same (seed, offset).  `offset` is then the generator offset / 4.            */
     void* offset_dev;            /* optional DEVICE u64: when set, the Philox counter base is read from here instead of
                                     `offset`, and the finishing kernel adds `offset_inc` to it — lets a captured CUDA
                                     graph of a whole command draw fresh noise on every replay                       */

@@ -95,6 +95,7 @@ class MppiFusedParams(C.Structure):
         ("env_ws_stride", C.c_uint64),
         ("host_mailbox", C.c_void_p),
         ("host_epoch", C.c_uint64),
+        ("torch_rng_total", C.c_uint64),
         ("offset_dev", C.c_void_p),
         ("offset_inc", C.c_uint64),
         ("model_params_ext", C.c_void_p),

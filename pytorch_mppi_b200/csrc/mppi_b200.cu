@@ -139,6 +139,7 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     a.epoch = p->epoch;
     a.export_partial = (p->flags & MPPI_FLAG_EXPORT_PARTIAL) ? 1 : 0;
     a.partial_out = (double*)p->partial_out;
+    a.torch_total = p->torch_rng_total;
     a.offset_dev = (unsigned long long*)p->offset_dev;
     a.offset_inc = p->offset_inc;
     a.n_env = p->n_env > 1 ? p->n_env : 1;

@@ -69,6 +69,7 @@ template <typename real> struct KArgs {
     int shift, null_action, tma_ok, state_per_sample;
     int tps;   // threads cooperating on one sample's sampling/transform phases (1, 2 or 4)
     int pdl;   // launched with programmatic stream serialization
+    unsigned long long torch_total;   // > 0: reproduce torch.randn's CUDA stream (256 * grid of the ATen kernel)
     unsigned long long* offset_dev;   // optional device-resident Philox counter base (CUDA-graph replays)
     unsigned long long offset_inc;
     // batched environments (MPPI_Batched, mppi.py:691-873): gridDim.y = n_env independent problems that
@@ -322,6 +323,16 @@ __device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, boo
         constexpr int PER = Normals<real>::PER_CALL;
         real* col = sm.rows + s_;
         const unsigned long long off = a.offset_dev != nullptr ? __ldcg(a.offset_dev) : a.offset;
+        if (a.torch_total > 0) {
+            // torch-compatible stream: one Philox call per element (the ATen kernel scatters each call's
+            // outputs `total` elements apart), 4x the generator work of the native stream
+            constexpr int UN = TorchNormal<real>::UNROLL;
+            for (int j = g_; j < R; j += a.tps) {
+                const unsigned long long li = kg * (unsigned long long)R + (unsigned long long)j;
+                const unsigned long long idx = li % a.torch_total, m = li / a.torch_total;
+                col[j * LD] = TorchNormal<real>::one(a.seed, idx, off + m / UN, (int)(m % UN));
+            }
+        } else
         for (int c = g_; c * PER < R; c += a.tps) {
             real tmp[PER];
             Normals<real>::draw(a.seed, kg, off + (unsigned long long)c, tmp);

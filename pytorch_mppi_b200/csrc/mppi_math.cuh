@@ -238,6 +238,51 @@ template <> struct Normals<double> {
     }
 };
 
+// One element of the stream `torch.randn(..., device="cuda")` produces (curand_normal4 / curand_normal2_double on
+// Philox4_32_10; /usr/local/cuda/include/curand_normal.h:70-131, ATen DistributionTemplates.h:66-95): thread `idx`
+// of the ATen kernel owns subsequence idx; its L-th engine call yields 4 floats (2 doubles) that go to elements
+// idx + total*(4L+ii).  Same libm calls as curand so the values agree to the bit.
+template <typename real> struct TorchNormal;
+template <> struct TorchNormal<float> {
+    static const int UNROLL = 4;
+    static MPPI_HD float one(uint64_t seed, uint64_t idx, uint64_t ctr, int ii) {
+        const U4 r = philox4x32_10(seed, idx, ctr);
+        const uint32_t x = ii < 2 ? r.x : r.z, y = ii < 2 ? r.y : r.w;
+        const float kInv = 2.3283064e-10f, k2pi = 2.3283064e-10f * 6.2831855f;
+        const float u = fmaf((float)x, kInv, kInv / 2);
+        const float v = fmaf((float)y, k2pi, k2pi / 2);
+        const float s = sqrtf(-2.0f * logf(u));
+        float sn, cs;
+#if defined(__CUDA_ARCH__)
+        __sincosf(v, &sn, &cs);
+#else
+        sn = sinf(v);
+        cs = cosf(v);
+#endif
+        return ((ii & 1) ? cs : sn) * s;
+    }
+};
+template <> struct TorchNormal<double> {
+    static const int UNROLL = 2;
+    static MPPI_HD double one(uint64_t seed, uint64_t idx, uint64_t ctr, int ii) {
+        const U4 r = philox4x32_10(seed, idx, ctr);
+        const unsigned long long zx = (unsigned long long)r.x ^ ((unsigned long long)r.y << 21);
+        const unsigned long long zy = (unsigned long long)r.z ^ ((unsigned long long)r.w << 21);
+        const double kInv = 1.1102230246251565e-16;
+        const double u = zx * kInv + (kInv / 2.0);
+        const double v = zy * (kInv * 2.0) + kInv;
+        const double s = sqrt(-2.0 * log(u));
+        double sn, cs;
+#if defined(__CUDA_ARCH__)
+        sincospi(v, &sn, &cs);
+#else
+        sn = sin(v * 3.1415926535897932);
+        cs = cos(v * 3.1415926535897932);
+#endif
+        return (ii ? cs : sn) * s;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // Noise model: colouring, bounds, action cost (device-side mirror of MppiFusedParams, pre-cast)
 // ------------------------------------------------------------------------------------------------

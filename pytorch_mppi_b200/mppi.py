@@ -95,6 +95,7 @@ class MPPI:
                  noise_abs_cost=False,
                  *,
                  rng_seed: typing.Optional[int] = None,
+                 rng: str = "philox",
                  block_threads: int = 0,
                  threads_per_sample: int = 0,
                  process_group=None,
@@ -174,6 +175,9 @@ class MPPI:
                 self._model = m
                 if hasattr(m, "library_path"):          # user model: its kernels live in a JIT-built variant library
                     self._lib = _cabi.load(m.library_path())
+        if rng not in ("philox", "torch"):
+            raise ValueError("rng must be 'philox' (one subsequence per sample) or 'torch' (the stream torch.randn draws on CUDA)")
+        self._rng_mode = rng
         self._block_threads = int(block_threads)
         self._pdl = os.environ.get("MPPI_B200_PDL", "1") != "0"
         self._threads_per_sample = int(threads_per_sample)
@@ -381,6 +385,15 @@ class MPPI:
         dbg = getattr(self, "_debug_clocks", None)
         p.debug_clocks = None if dbg is None else dbg.data_ptr()
         p.n_env, p.env_u_stride, p.env_ws_stride = 0, 0, 0
+        p.torch_rng_total = 0
+        if self._rng_mode == "torch":
+            # launch policy of ATen's distribution kernel (DistributionTemplates.h:50-62) for K*T*nu elements
+            props = torch.cuda.get_device_properties(self.d)
+            numel = self.K * self._noise_rows()
+            grid = min(props.multi_processor_count * (props.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+            unroll = 4 if self.dtype == torch.float32 else 2
+            self._torch_counter_offset = ((numel - 1) // (256 * grid * unroll) + 1) * 4
+            p.torch_rng_total = 256 * grid
         od = getattr(self, "_offset_dev", None)
         p.offset_dev = None if od is None else od.data_ptr()
         per = 4 if self.dtype == torch.float32 else 2
@@ -460,6 +473,12 @@ class MPPI:
         (torch.manual_seed reseeds it), consumed with the same (seed, offset) protocol ATen ops use."""
         per = 4 if self.dtype == torch.float32 else 2
         chunks = (self._noise_rows() + per - 1) // per
+        if self._rng_mode == "torch":      # consume the torch CUDA generator exactly as torch.randn(K,T,nu) would
+            gen = torch.cuda.default_generators[self.d.index]
+            seed = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF
+            off = gen.get_offset()
+            gen.set_offset(off + self._torch_counter_offset)
+            return seed, off // 4
         if self._rng_seed is not None:
             base = self._rng_counter
             self._rng_counter += chunks

@@ -501,3 +501,44 @@ def test_user_cuda_model_equals_builtin_and_oracle():
         assert float((c.U.cpu() - U).abs().max()) < 1e-10
         np.testing.assert_allclose(c.states.cpu().numpy(), r["states"].numpy(), atol=1e-10)
         x = dyn(x.view(1, -1), r["action"].view(1, -1)).view(-1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("shape", [(16384, 30, 1), (1000, 7, 2), (300000, 20, 1)])
+def test_torch_compatible_rng_reproduces_torch_randn(dtype, shape):
+    """rng="torch": the kernel regenerates, sample by sample, exactly the tensor torch.randn(K,T,nu,
+    device="cuda") would have produced from the same generator state — the stream the reference draws on a
+    CUDA device (mppi.py:203) — and advances the generator by the same amount."""
+    import pytorch_mppi_b200 as eng
+    K, T, nu = shape
+    model = eng.Pendulum() if nu == 1 else eng.LinearPoint.unit_test_env()
+    sigma = torch.tensor(1.0, dtype=dtype) if nu == 1 else torch.eye(2, dtype=dtype)
+    c = eng.MPPI(model.dynamics, model.running_cost, 2, sigma, num_samples=K, horizon=T, U_init=torch.zeros(T, nu, dtype=dtype),
+                 device="cuda", rng="torch")
+    c.record_noise(True)
+    gen = torch.cuda.default_generators[0]
+    for rep in range(2):
+        torch.manual_seed(1234 + rep)
+        torch.rand(17, device="cuda")                       # move the generator off zero
+        state = gen.get_state()
+        want = torch.randn(K, T, nu, device="cuda", dtype=dtype)
+        off_after = gen.get_offset()
+        gen.set_state(state)
+        c.command([1.0, 0.5])
+        assert gen.get_offset() == off_after
+        got = c.z_used
+        if dtype == torch.float32:
+            assert torch.equal(got, want), float((got - want).abs().max())
+        else:
+            assert float((got - want).abs().max()) < 1e-14
+    # and the command run on those draws equals the oracle fed torch.randn's tensor
+    if K <= 20000:
+        from oracle import mppi_oracle as orc
+        m = orc.PendulumModel(numpy_sin=False) if nu == 1 else orc.LinearPointModel(B=model.B, goal=model.goal, dtype=dtype)
+        prob = orc.Problem(m.dynamics, m.running_cost, 2, sigma, K=K, T=T)
+        U0 = torch.zeros(T, nu, dtype=dtype)
+        c.U = U0
+        gen.set_state(state)
+        c.command([1.0, 0.5])
+        r = orc.mppi_command(prob, U0, torch.tensor([1.0, 0.5], dtype=dtype), want.cpu())
+        assert float((c.U.cpu() - r["U"]).abs().max()) < (2e-5 if dtype == torch.float32 else 1e-9)
