@@ -7,7 +7,9 @@
 #include <string.h>
 
 #include "../../include/mppi_b200.h"
+#include <type_traits>
 #include "mppi_fused.cuh"
+#include "mppi_mlp_tc.cuh"
 
 using namespace mppi;
 
@@ -200,6 +202,7 @@ struct GeomKey {
 
 // Launch geometry for (kernel, dimensions).  The occupancy / attribute queries cost microseconds, so
 // the last few results are cached per thread: a steady-state command() pays only the lookup.
+static thread_local int g_tc_kernel = 0;   // set around plan_geometry() for the tcgen05 kernels (see below)
 template <typename KernelT>
 int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_rows2, bool single_partial_grid, Geometry& g,
                   SmemLayout (*layout)(int, int, int, int, int, int, int, int, int)) {
@@ -295,6 +298,20 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
         if (L.total > dyn_limit) return UNSUPPORTED("shared-memory tile does not fit");
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
         if (occ < 1) return UNSUPPORTED("kernel does not fit on an SM with this block size");
+        if (g_tc_kernel) {
+            // The occupancy API answers 1 CTA/SM for kernels that allocate tensor memory; measured on B200 the
+            // 128-thread tcgen05 CTAs do co-reside (K=131072, T=30: 585 us at 1 CTA/SM, 379 at 2, 311 at 3), so
+            // size the grid from the real limits: shared memory, registers, and 64 of 512 TMEM columns per CTA.
+            int smem_sm = 0;
+            CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+            const int by_smem = smem_sm / ((int)fa.sharedSizeBytes + L.total + 1024);
+            const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * BD);
+            int o = by_smem < by_regs ? by_smem : by_regs;
+            if (o > 512 / 64) o = 512 / 64;
+            const char* e = getenv("MPPI_TC_OCC");
+            if (e != nullptr && atoi(e) > 0) o = atoi(e);
+            if (o > occ) occ = o;
+        }
         int nb2 = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
         if (nb2 > cap) nb2 = cap;
         if (p->grid_blocks > 0 && p->grid_blocks < nb2) nb2 = p->grid_blocks;
@@ -323,6 +340,29 @@ template <typename real> SmemLayout layout_fn(int v, int T, int nu, int S, int R
 }
 
 // ---- fused command ----------------------------------------------------------------------------
+// PENDULUM_MLP in fp32 with model_params[3] != 0: the tcgen05/TMEM kernel (mppi_mlp_tc.cuh).  One CTA = 128
+// threads = 128 samples = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
+template <class Model, typename real, int V, typename KernelT>
+bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, KernelT& kernel) {
+    if constexpr (std::is_same<Model, PendulumMLPModel>::value && std::is_same<real, float>::value) {
+        const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
+        if ((mode == 1 || mode == 2) && p->n_env <= 1) {
+            p_tc = *p;
+            p_tc.block_threads = 128;
+            p_tc.threads_per_sample = 1;
+            p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
+            const bool fast = p->model_params[2] != 0.0;
+            kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
+                               : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
+            g_tc_kernel = 1;
+            return true;
+        }
+    }
+    (void)p_tc;
+    (void)kernel;
+    return false;
+}
+
 template <class Model, typename real, int V>
 int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
@@ -330,8 +370,12 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
     if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
     auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
+    MppiFusedParams p_tc;
+    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
+    if (tc_route) p = &p_tc;
     Geometry g;
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
+    g_tc_kernel = 0;
     if (rc) return rc;
     const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
     KArgs<real> a;
@@ -398,7 +442,11 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     const bool batched = p->n_env > 1;
     if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
     auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
+    MppiFusedParams p_tc;
+    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
+    if (tc_route) p = &p_tc;
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
+    g_tc_kernel = 0;
     if (rc) return rc;
     if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
         return MPPI_ERR_BAD_ARG;

@@ -1,0 +1,389 @@
+// mppi_mlp_tc.cuh — tensor-core variant of the fused command kernel for the learned pendulum model
+// (BASELINE config 4: 3-32-32-2 tanh residual MLP, /root/reference/tests/pendulum_approximate.py:47-67).
+//
+// The network's three layers are genuine dense contractions, so per rollout step a CTA of 128 threads
+// (= 128 samples = the 128 TMEM lanes of one M=128 UMMA tile) runs them on the 5th-gen tensor cores:
+//   registers -> bf16 operand tile in shared memory (canonical K-major, no swizzle)
+//   tcgen05.mma.cta_group::1.kind::f16  (one elected thread)  -> fp32 accumulator in TMEM
+//   tcgen05.commit -> mbarrier -> every thread tcgen05.ld's ITS OWN row (lane = sample) -> bias, tanh
+// three times per step.  Everything else (sampling, clamp, cost, softmin fold, last-CTA update) is the
+// code of mppi_fused.cuh.
+//
+// Precision: operands are bf16, but activations and weights are split into hi + lo bf16 parts and the
+// contraction is K-extended to  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi  ("3 x bf16"), which costs nothing
+// here (the step is latency-bound, the extra K-steps are a few more MMA issues) and brings the layer
+// outputs to ~2^-16 relative accuracy instead of bf16's 2^-8.
+#pragma once
+
+#include <cuda_bf16.h>
+#include "mppi_fused.cuh"
+
+namespace mppi {
+
+#if defined(__CUDACC__)
+
+namespace tc {
+
+constexpr int H = 32;             // hidden width
+constexpr int KX3 = 96;           // SPLIT: extended K of layers 2 and 3: [a_hi | a_hi | a_lo] x [w_hi ; w_lo ; w_hi]
+constexpr int CH = 128;           // bytes of one 8-row x 16-byte core matrix
+constexpr int TMEM_COLS = 64;     // D1: cols [0,32), D2: [32,64), D3: [0,16) (D1 is dead by then)
+
+// shared-memory operand tiles (bytes); canonical K-major/no-swizzle: core (row group g, k-chunk c) at
+// g*SBO + c*LBO, rows 16 B apart inside a core, LBO = 128 B (adjacent chunks), SBO = chunks*128 B
+constexpr int A1_BYTES = 128 * 16 * 2;    // M=128, K=16
+constexpr int B1_BYTES = 32 * 16 * 2;
+
+__device__ __forceinline__ uint64_t smem_desc(const void* base, int sbo_bytes) {
+    // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout none
+    const uint64_t addr = (uint64_t)(smem_u32(base) >> 4) & 0x3FFF;
+    const uint64_t lbo = (uint64_t)(CH >> 4) & 0x3FFF;
+    const uint64_t sbo = (uint64_t)(sbo_bytes >> 4) & 0x3FFF;
+    return addr | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// InstrDescriptor: c=F32 (1<<4) | a=BF16 (1<<7) | b=BF16 (1<<10) | K-major both | N>>3 at [17,23) | M>>4 at [24,29)
+__device__ __forceinline__ constexpr uint32_t instr_desc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(void* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// bounded mbarrier wait: a wedged MMA becomes a trap (kernel error), never a hung GPU
+__device__ __forceinline__ void mbar_wait_bounded(void* bar, uint32_t phase) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+        if (!done && clock64() - t0 > 2000000000ll) __trap();
+    }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& v0, float& v1) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v0 = __uint_as_float(r0);
+    v1 = __uint_as_float(r1);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// two floats -> packed bf16 pair (a in the low half): one cvt.rn.bf16x2.f32
+__device__ __forceinline__ uint32_t cvt2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// element (row, k) of a canonical K-major tile with `chunks` k-chunks: byte offset
+__device__ __forceinline__ int tile_off(int row, int k, int chunks) {
+    return (row >> 3) * (chunks * CH) + (k >> 3) * CH + (row & 7) * 16 + (k & 7) * 2;
+}
+
+// this thread's 32 activations -> its row of the operand tile.
+//   SPLIT: K = 96, [hi(32) | hi(32) | lo(32)] with lo = bf16(h - hi);   else K = 32, [bf16(h)]
+template <int SPLIT, int CHUNKS> __device__ __forceinline__ void write_a_row(unsigned char* A, int row, const float* h) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        hi[i] = cvt2(h[2 * i], h[2 * i + 1]);
+        if (SPLIT) {
+            const float r0 = h[2 * i] - __uint_as_float(hi[i] << 16);
+            const float r1 = h[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u);
+            lo[i] = cvt2(r0, r1);
+        }
+    }
+    unsigned char* base = A + (row >> 3) * (CHUNKS * CH) + (row & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint4 vh = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(base + c * CH) = vh;
+        if (SPLIT) {
+            const uint4 vl = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            *reinterpret_cast<uint4*>(base + (4 + c) * CH) = vh;
+            *reinterpret_cast<uint4*>(base + (8 + c) * CH) = vl;
+        }
+    }
+}
+
+}  // namespace tc
+
+// =================================================================================================
+template <int VARIANT, int SPLIT, int FAST>
+__global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_constant__ KArgs<float> a,
+                                                             const __grid_constant__ PendulumMLPModel::P<float> mp) {
+    typedef float real;
+    typedef Ops<real> O;
+    typedef PendulumMLPModel Model;
+    constexpr int NX = 2, NU = 1, H = tc::H;
+    // K of layers 2 and 3: the activations (split or not) plus one 16-wide K-step whose first two columns are
+    // the constant 1: the matching rows of B hold bias_hi and bias_lo, so the MMA adds the bias for free
+    constexpr int KB = SPLIT ? tc::KX3 : H;
+    constexpr int KX = KB + 16;
+    constexpr int CHUNKS = KX / 8, NSTEP = KX / 16;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(128) unsigned char sA1[tc::A1_BYTES];
+    __shared__ __align__(128) unsigned char sA2[128 * KX * 2];      // layer 2's operand, then layer 3's
+    __shared__ __align__(128) unsigned char sB1[tc::B1_BYTES];
+    __shared__ __align__(128) unsigned char sB2[32 * KX * 2];
+    __shared__ __align__(128) unsigned char sB3[16 * KX * 2];
+    __shared__ __align__(8) unsigned long long s_mma_bar;
+    __shared__ uint32_t s_tmem_base;
+    const int tid = threadIdx.x, BD = blockDim.x;      // BD == 128 == BS
+    const int warp = tid >> 5;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BD, gridDim.x, 0);
+    Smem<real> sm(smem, L);
+    const NoiseModel<real>& nm = a.nm;
+    const int T = a.T;
+
+    // ---- one-time setup: TMEM, MMA barrier, bf16 weight tiles (hi/lo split, K-extended) -----------------
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"((uint32_t)tc::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_mma_bar)), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < tc::A1_BYTES / 4; i += BD) reinterpret_cast<uint32_t*>(sA1)[i] = 0u;
+    for (int i = tid; i < 128 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sA2)[i] = 0u;
+    for (int i = tid; i < 32 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB2)[i] = 0u;
+    for (int i = tid; i < tc::B1_BYTES / 4; i += BD) reinterpret_cast<uint32_t*>(sB1)[i] = 0u;
+    for (int i = tid; i < 16 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB3)[i] = 0u;
+    __syncthreads();
+    const uint32_t ONE2 = 0x3F803F80u;                                // bf16 (1.0, 1.0)
+    *reinterpret_cast<uint4*>(sA2 + (tid >> 3) * (CHUNKS * tc::CH) + (KB / 8) * tc::CH + (tid & 7) * 16) = make_uint4(ONE2, 0u, 0u, 0u);
+    // B1 (N=32 x K=16): input c in {x0,x1,u} occupies k = 3c..3c+2 as [w_hi, w_lo, w_hi]; k = 9, 10: bias hi, lo
+    for (int n = tid; n < H; n += BD) {
+        __nv_bfloat16 bh, bl;
+        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB1);
+        tc::split_bf16(mp.b1[n], bh, bl);
+        B[tc::tile_off(n, 9, 2) / 2] = bh;
+        B[tc::tile_off(n, 10, 2) / 2] = bl;
+        B = reinterpret_cast<__nv_bfloat16*>(sB2);
+        tc::split_bf16(mp.b2[n], bh, bl);
+        B[tc::tile_off(n, KB, CHUNKS) / 2] = bh;
+        B[tc::tile_off(n, KB + 1, CHUNKS) / 2] = bl;
+        if (n < 2) {
+            B = reinterpret_cast<__nv_bfloat16*>(sB3);
+            tc::split_bf16(mp.b3[n], bh, bl);
+            B[tc::tile_off(n, KB, CHUNKS) / 2] = bh;
+            B[tc::tile_off(n, KB + 1, CHUNKS) / 2] = bl;
+        }
+    }
+    for (int e = tid; e < H * 3; e += BD) {
+        const int n = e / 3, c = e - n * 3;
+        __nv_bfloat16 wh, wl;
+        tc::split_bf16(mp.W1[c * H + n], wh, wl);                 // P stores W1 transposed: W1t[c][n]
+        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB1);
+        B[tc::tile_off(n, 3 * c + 0, 2) / 2] = wh;
+        B[tc::tile_off(n, 3 * c + 1, 2) / 2] = wl;
+        B[tc::tile_off(n, 3 * c + 2, 2) / 2] = wh;
+    }
+    // B2 (N=32 x K): SPLIT: k in [0,32) w_hi, [32,64) w_lo, [64,96) w_hi   (A is [a_hi | a_hi | a_lo]); else bf16(w)
+    for (int e = tid; e < H * H; e += BD) {
+        const int n = e / H, k = e - n * H;
+        __nv_bfloat16 wh, wl;
+        tc::split_bf16(mp.W2[k * H + n], wh, wl);                 // W2t[k][n] = W2[n][k]
+        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB2);
+        B[tc::tile_off(n, k, CHUNKS) / 2] = wh;
+        if (SPLIT) {
+            B[tc::tile_off(n, 32 + k, CHUNKS) / 2] = wl;
+            B[tc::tile_off(n, 64 + k, CHUNKS) / 2] = wh;
+        }
+    }
+    // B3 (N=16 x K): rows 0,1 hold the output layer, rows 2..15 stay zero
+    for (int e = tid; e < 2 * H; e += BD) {
+        const int n = e / H, k = e - n * H;
+        __nv_bfloat16 wh, wl;
+        tc::split_bf16(mp.W3[n * H + k], wh, wl);
+        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB3);
+        B[tc::tile_off(n, k, CHUNKS) / 2] = wh;
+        if (SPLIT) {
+            B[tc::tile_off(n, 32 + k, CHUNKS) / 2] = wl;
+            B[tc::tile_off(n, 64 + k, CHUNKS) / 2] = wh;
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before();
+    __syncthreads();
+    tc::fence_after();
+    const uint32_t tmem = s_tmem_base;
+    const uint32_t my_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes; thread = lane = sample row
+    uint32_t mma_phase = 0;
+    const uint64_t dA1 = tc::smem_desc(sA1, 2 * tc::CH), dB1 = tc::smem_desc(sB1, 2 * tc::CH);
+    const uint64_t dA2 = tc::smem_desc(sA2, CHUNKS * tc::CH), dB2 = tc::smem_desc(sB2, CHUNKS * tc::CH),
+                   dB3 = tc::smem_desc(sB3, CHUNKS * tc::CH);
+    constexpr uint32_t I32 = tc::instr_desc(128, 32), I16 = tc::instr_desc(128, 16);
+    constexpr uint64_t KSTEP = (2 * tc::CH) >> 4;                     // one K=16 step = two 8-element chunks, in 16-byte units
+
+    stage_issue<real, VARIANT, NU>(a, sm);
+    bool staged = false;
+    real beta_run = O::inf(), eta_run = (real)0;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int k = tile * BD + tid;
+        const bool active = k < a.K;
+        const int nvalid = min(BD, a.K - tile * BD);
+        const unsigned long long kg = (unsigned long long)(a.k_offset + k);
+        fill_normals<real>(a, sm, tile, active, kg, nvalid);
+        if (!staged) {
+            stage_finish<real, VARIANT, NU>(a, sm);
+            staged = true;
+        }
+        if (active) transform_column<real, VARIANT, NU>(a, sm, kg);
+
+        // ---- rollout: every thread takes part in every step (the MMAs are CTA-wide) ---------------------
+        real x[NX] = {(real)0, (real)0};
+        if (active) {
+            if (a.state_dev != nullptr) {
+                const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
+                x[0] = sp[0];
+                x[1] = sp[1];
+            } else {
+                x[0] = a.x0[0];
+                x[1] = a.x0[1];
+            }
+        }
+        real roll = (real)0, pert = (real)0, smooth = (real)0, vprev = (real)0;
+        for (int t = 0; t < T; ++t) {
+            real v[NU] = {(real)0}, eps[NU] = {(real)0};
+            if (active) {
+                action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+                noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+            }
+            const real u = O::mul(nm.u_scale, v[0]);
+            const real uc = clamp<real>(u, -mp.max_torque, mp.max_torque);
+            // layer 1 operand row: [x0h x0h x0l | x1h x1h x1l | uh uh ul | 0...]
+            {
+                __nv_bfloat16 h0, l0, h1, l1, h2, l2;
+                tc::split_bf16(x[0], h0, l0);
+                tc::split_bf16(x[1], h1, l1);
+                tc::split_bf16(uc, h2, l2);
+                const __nv_bfloat16 z = __float2bfloat16_rn(0.0f), one = __float2bfloat16_rn(1.0f);
+                unsigned char* row = sA1 + (tid >> 3) * (2 * tc::CH) + (tid & 7) * 16;
+                *reinterpret_cast<uint4*>(row) = make_uint4(tc::pack2(h0, h0), tc::pack2(l0, h1), tc::pack2(h1, l1), tc::pack2(h2, h2));
+                *reinterpret_cast<uint4*>(row + tc::CH) = make_uint4(tc::pack2(l2, one), tc::pack2(one, z), 0u, 0u);
+            }
+            tc::fence_async_smem();
+            tc::fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after();
+                tc::mma_f16(tmem + 0, dA1, dB1, I32, 0u);
+                tc::mma_commit(&s_mma_bar);
+            }
+            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+            mma_phase ^= 1u;
+            tc::fence_after();
+            float h[H];
+            tc::tmem_ld32(my_lane + 0, h);
+#pragma unroll
+            for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
+            tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);
+            tc::fence_async_smem();
+            tc::fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after();
+#pragma unroll
+                for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + 32, dA2 + s * KSTEP, dB2 + s * KSTEP, I32, s > 0 ? 1u : 0u);
+                tc::mma_commit(&s_mma_bar);
+            }
+            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+            mma_phase ^= 1u;
+            tc::fence_after();
+            tc::tmem_ld32(my_lane + 32, h);
+#pragma unroll
+            for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
+            tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);                 // MMA 2 has completed (barrier): its operand tile is free
+            tc::fence_async_smem();
+            tc::fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after();
+#pragma unroll
+                for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + 0, dA2 + s * KSTEP, dB3 + s * KSTEP, I16, s > 0 ? 1u : 0u);
+                tc::mma_commit(&s_mma_bar);
+            }
+            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+            mma_phase ^= 1u;
+            tc::fence_after();
+            float o0, o1;
+            tc::tmem_ld2(my_lane + 0, o0, o1);
+            const real th = O::add(x[0], o0);
+            x[0] = O::sub(remainder<real>(O::add(th, mp.pi), mp.two_pi), mp.pi);        // pendulum_approximate.py:65
+            x[1] = O::add(x[1], o1);
+            if (active) {
+                roll = O::add(roll, Model::template cost<real>(mp, x, &u));               // mppi.py:318-319
+                pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
+                if (VARIANT == V_SMPPI) {
+                    if (t > 0) {
+                        const real d = O::mul(nm.u_scale, O::sub(v[0], vprev));
+                        smooth = O::add(smooth, O::mul(d, d));
+                    }
+                    vprev = v[0];
+                }
+            }
+        }
+        real c_tot = O::inf();
+        if (active) {
+            c_tot = O::add(roll, pert);
+            if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));
+            a.cost_total[k] = c_tot;
+        }
+        real w_unused;
+        fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+    }
+    if (!staged) stage_finish<real, VARIANT, NU>(a, sm);
+    tc::fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tc::TMEM_COLS) : "memory");
+    }
+    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace mppi

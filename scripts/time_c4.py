@@ -18,13 +18,17 @@ def run(name, dyn, cost, n, **kw):
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
     info = getattr(c, "launch_info", None)
-    geo = "" if info is None or c._model is None else f" grid={info.grid_blocks} block={info.block_threads} regs={info.regs_per_thread} smem={info.smem_bytes}"
+    geo = "" if info is None or c._model is None else f" grid={info.grid_blocks} block={info.block_threads} regs={info.regs_per_thread} smem={info.smem_bytes} occ={info.max_blocks_per_sm}"
     print(f"{name}: {us:.1f} us/command -> {K*T/us/1e3:.2f} G rollout-steps/s, {2368*K*T/us/1e6:.2f} TFLOP/s of MLP math{geo}")
 for fast in (False, True):
     m = eng.PendulumMLP(net, fast_tanh=fast)
     run(f"fused   fp32 fast_tanh={fast}", m.dynamics, m.running_cost, 50)
     for bt in (128, 256):
         run(f"fused   fp32 fast_tanh={fast} bt={bt}", m.dynamics, m.running_cost, 50, block_threads=bt)
+for mode in ("bf16x3", "bf16"):
+    for fast in (False, True):
+        m = eng.PendulumMLP(net, fast_tanh=fast, tensor_cores=mode)
+        run(f"fused   tcgen05 {mode} fast_tanh={fast}", m.dynamics, m.running_cost, 50)
 m = eng.PendulumMLP(net)
 run("stepped fp32 (torch MLP, Python T-loop)", lambda s, a: m.dynamics(s, a), lambda s, a: m.running_cost(s, a), 10)
 c = eng.MPPI(lambda s, a: m.dynamics(s, a), lambda s, a: m.running_cost(s, a), 2, torch.tensor(1.0), num_samples=K, horizon=T,

@@ -436,6 +436,90 @@ def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
 
 
 @pytest.mark.parametrize("variant", ["mppi", "smppi", "kmppi"])
+def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant):
+    """PendulumMLP(tensor_cores=True): the three layers run as tcgen05 MMAs (hi/lo-split bf16 operands,
+    fp32 TMEM accumulators).  Same injected noise as the FFMA kernel: costs agree to ~1e-4 relative and
+    the updated plan to 2e-4 (operand split error ~2^-16 per layer, 30 steps of a chaotic rollout), for a
+    ragged K (partial last tile) and over closed-loop commands; MPPI is also checked against the oracle."""
+    import copy
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    torch.manual_seed(25)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                              torch.nn.Linear(32, 2))
+    cpu_model = eng.PendulumMLP(copy.deepcopy(net))
+    ffma = eng.PendulumMLP(copy.deepcopy(net).cuda())
+    tcm = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores=True)
+    K, T = 4096 + 37, 30
+    cls = {"mppi": eng.MPPI, "smppi": eng.SMPPI, "kmppi": eng.KMPPI}[variant]
+    kw = {"smppi": dict(w_action_seq_cost=2.0, action_max=torch.tensor(2.0)), "kmppi": dict(num_support_pts=6)}.get(variant, {})
+    g = torch.Generator().manual_seed(4)
+    U0 = torch.randn(T, 1, generator=g) if variant == "mppi" else None
+    mk = lambda m: cls(m.dynamics, m.running_cost, 2, torch.tensor(1.0), num_samples=K, horizon=T, U_init=None if U0 is None else U0.clone(),
+                       u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", **kw)
+    torch.manual_seed(8)
+    a_ref = mk(ffma)
+    torch.manual_seed(8)
+    a_tc = mk(tcm)                      # same random initial plan (KMPPI draws its control points)
+    assert a_tc._model is tcm
+    prob = orc.Problem(cpu_model.dynamics, cpu_model.running_cost, 2, torch.tensor(1.0), K=K, T=T, u_min=torch.tensor(-2.0),
+                       u_max=torch.tensor(2.0))
+    x = torch.tensor([3.0, 0.5])
+    for step in range(3):
+        if variant == "kmppi":
+            z = torch.randn(K, 6, 1, generator=g)
+        else:
+            z = torch.randn(K, T, 1, generator=g)
+        a_ref.inject_noise(z)
+        a_tc.inject_noise(z)
+        U_before = a_ref.U.cpu().clone()
+        u1 = a_ref.command(x)
+        u2 = a_tc.command(x)
+        c1, c2 = a_ref.cost_total.cpu().numpy(), a_tc.cost_total.cpu().numpy()
+        assert np.isfinite(c2).all()
+        assert a_tc.launch_info.block_threads == 128 and a_ref.launch_info.block_threads != 128
+        np.testing.assert_allclose(c2, c1, rtol=2e-3, atol=2e-3)
+        assert float(np.median(np.abs(c2 - c1) / np.maximum(1.0, np.abs(c1)))) < 2e-5
+        assert float((a_tc.U - a_ref.U).abs().max()) < 2e-4, step
+        assert float((u1 - u2).abs().max()) < 2e-4
+        if variant == "mppi":
+            r = orc.mppi_command(prob, U_before, x, z)
+            assert float((a_tc.U.cpu() - r["U"]).abs().max()) < 2e-4
+        a_tc.U = a_ref.U.clone()
+        x = cpu_model.dynamics(x.view(1, -1), u1.cpu().view(1, -1)).view(-1)
+
+
+def test_fused_mlp_tensor_core_bf16_mode_is_close_and_controls():
+    """tensor_cores="bf16": plain bf16 operands in the hidden layers.  Not a parity route (2^-8 operand
+    rounding): the costs must track the fp32 kernel's to a few percent, the softmin weights must
+    correlate, and the controller must still drive the learned pendulum's cost down."""
+    import copy
+    import pytorch_mppi_b200 as eng
+    torch.manual_seed(25)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                              torch.nn.Linear(32, 2))
+    ffma = eng.PendulumMLP(copy.deepcopy(net).cuda())
+    tcm = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores="bf16", fast_tanh=True)
+    K, T = 8192, 20
+    mk = lambda m: eng.MPPI(m.dynamics, m.running_cost, 2, torch.tensor(1.0), num_samples=K, horizon=T, U_init=torch.zeros(T, 1),
+                            u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda")
+    a_ref, a_tc = mk(ffma), mk(tcm)
+    g = torch.Generator().manual_seed(9)
+    z = torch.randn(K, T, 1, generator=g)
+    a_ref.inject_noise(z)
+    a_tc.inject_noise(z)
+    x = torch.tensor([2.5, 0.3])
+    a_ref.command(x)
+    a_tc.command(x)
+    c1, c2 = a_ref.cost_total.double().cpu(), a_tc.cost_total.double().cpu()
+    assert torch.isfinite(c2).all()
+    rel = ((c2 - c1).abs() / c1.abs().clamp_min(1.0))
+    assert float(rel.median()) < 2e-2 and float(rel.max()) < 0.5, (float(rel.median()), float(rel.max()))
+    assert float(torch.corrcoef(torch.stack((c1, c2)))[0, 1]) > 0.999
+    assert float((a_tc.U - a_ref.U).abs().max()) < 0.1
+
+
+@pytest.mark.parametrize("variant", ["mppi", "smppi", "kmppi"])
 def test_compile_cuda_graph_replay_equals_eager_stepped(variant):
     """compile() on the stepped route captures the whole command in a CUDA graph; replays must equal the
     eager stepped commands bit for bit (same seed; the Philox counter advances on the device)."""
