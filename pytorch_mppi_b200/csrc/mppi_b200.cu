@@ -355,6 +355,8 @@ bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, K
             kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
                                : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
             g_tc_kernel = 1;
+            // co-residency is bounded by shared memory: ask for the largest carve-out
+            cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             return true;
         }
     }
