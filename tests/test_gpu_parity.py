@@ -307,6 +307,67 @@ def test_stepped_route_M_gt_1_and_action_sampler_match_oracle_semantics():
 
 
 @pytest.mark.parametrize("route", ["fused", "stepped"])
+def test_autotune_parameter_flows_refresh_kernel_constants(route):
+    """The reference's tuner mutates a LIVE controller (autotune.py:158-162 sigma, :184-187 mu, :213-215
+    lambda, :235-237 horizon).  Every such write must reach the kernel's constants: after each one the
+    next command equals the oracle built with the new value (same injected noise)."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    dt = torch.float64
+    lin = eng.LinearPoint.unit_test_env()
+    olin = orc.LinearPointModel(B=lin.B, goal=lin.goal, dtype=dt)
+    g = torch.Generator().manual_seed(12)
+    K, T = 512, 8
+    U0 = torch.randn(T, 2, generator=g, dtype=dt) * 0.3
+    if route == "fused":
+        dyn, cost = lin.dynamics, lin.running_cost
+    else:
+        dyn, cost = (lambda s, a: lin.dynamics(s, a)), (lambda s, a: lin.running_cost(s, a))
+    ctrl = eng.MPPI(dyn, cost, 2, torch.eye(2, dtype=dt), num_samples=K, horizon=T, U_init=U0.clone(), device="cuda",
+                    u_max=torch.tensor([1.5, 1.5], dtype=dt))
+    assert (ctrl._model is not None) == (route == "fused")
+    x = torch.tensor([-1.0, 0.5], dtype=dt)
+    spec = dict(noise_sigma=torch.eye(2, dtype=dt), lambda_=1.0, T=T)
+
+    def check(tag):
+        Tn = spec["T"]
+        prob = orc.Problem(olin.dynamics, olin.running_cost, 2, spec["noise_sigma"].clone(), K=K, T=Tn, lambda_=spec["lambda_"],
+                           u_max=torch.tensor([1.5, 1.5], dtype=dt))
+        U_in = ctrl.U.cpu().clone()
+        z = torch.randn(K, Tn, 2, generator=g, dtype=dt)
+        ctrl.inject_noise(z)
+        a = ctrl.command(x)
+        r = orc.mppi_command(prob, U_in, x, z)
+        assert float((ctrl.U.cpu() - r["U"]).abs().max()) < 1e-10, tag
+        assert float((a.cpu() - r["action"]).abs().max()) < 1e-10, tag
+        assert float((ctrl.cost_total.cpu() - r["cost_total"]).abs().max()) < 1e-8, tag
+
+    check("initial")
+    # SigmaParameter.apply_parameter_value (autotune.py:158-162)
+    sigma = torch.tensor([0.4, 2.5], dtype=dt, device=ctrl.d)
+    ctrl.noise_sigma = torch.diag(sigma)
+    ctrl.noise_dist = torch.distributions.MultivariateNormal(ctrl.noise_mu, covariance_matrix=ctrl.noise_sigma)
+    ctrl.noise_sigma_inv = torch.inverse(ctrl.noise_sigma.detach())
+    spec["noise_sigma"] = torch.diag(sigma).cpu()
+    check("sigma")
+    # a full (non-diagonal) covariance takes the Cholesky path
+    full = torch.tensor([[1.0, 0.3], [0.3, 0.5]], dtype=dt)
+    ctrl.noise_sigma = full.to(ctrl.d)
+    spec["noise_sigma"] = full
+    check("full sigma")
+    # LambdaParameter.apply_parameter_value (autotune.py:213-215)
+    ctrl.lambda_ = 0.2
+    spec["lambda_"] = 0.2
+    check("lambda")
+    # HorizonParameter.apply_parameter_value (autotune.py:235-237): longer, then shorter
+    for Tn in (13, 5):
+        ctrl.change_horizon(Tn)
+        spec["T"] = Tn
+        assert ctrl.U.shape == (Tn, 2)
+        check(f"horizon {Tn}")
+
+
+@pytest.mark.parametrize("route", ["fused", "stepped"])
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 5e-5)])
 def test_mppi_batched_matches_oracle(route, dtype, tol):
     """MPPI_Batched (mppi.py:691-873): N environments share the K noise samples; per-environment softmin.
