@@ -348,8 +348,15 @@ bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, K
         const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
         if ((mode == 1 || mode == 2) && p->n_env <= 1) {
             p_tc = *p;
-            p_tc.block_threads = 128;
-            p_tc.threads_per_sample = 1;
+            // 128-thread CTAs, tiles of 128 samples (every thread rolls one).  The kernel also supports tiles of 64
+            // samples + 64 helper threads (MPPI_TC_TILE=64; twice the CTAs to spread over the SMs), but a CTA's step
+            // time is set by the three MMA round trips, not by its tanh work: measured K=32768, T=30: 132 us with
+            // half tiles against 113 us with full ones, so full tiles are the default at every K.
+            int bs = 128;
+            const char* e_bs = getenv("MPPI_TC_TILE");
+            if (e_bs != nullptr && (atoi(e_bs) == 64 || atoi(e_bs) == 128)) bs = atoi(e_bs);
+            p_tc.block_threads = bs;
+            p_tc.threads_per_sample = 128 / bs;
             p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
             const bool fast = p->model_params[2] != 0.0;
             kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)

@@ -168,9 +168,9 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     __shared__ __align__(128) unsigned char sB3lo[SPLIT ? 16 * H * 2 : 128];
     __shared__ __align__(8) unsigned long long s_mma_bar;
     __shared__ uint32_t s_tmem_base;
-    const int tid = threadIdx.x, BD = blockDim.x;      // BD == 128 == BS
+    const int tid = threadIdx.x, BD = blockDim.x;      // BD == 128
     const int warp = tid >> 5;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BD, gridDim.x, 0);
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BD / a.tps, gridDim.x, 0);
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
@@ -266,19 +266,28 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     bool staged = false;
     real beta_run = O::inf(), eta_run = (real)0;
 
+    // Tile = BS samples.  BS = 128: every thread rolls one sample.  BS = 64 (threads_per_sample = 2, chosen by the
+    // host when 128-sample tiles would leave SMs idle): warps 0-1 roll, warps 2-3 only help with the draws and
+    // the colour/clamp pass and then keep the CTA barriers company; rows 64..127 of the MMA are padding.
+    const int BS = BD / a.tps;
+    const bool roller = tid < BS;                      // warp-uniform (BS is a multiple of 32)
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int k = tile * BD + tid;
-        const bool active = k < a.K;
-        const int nvalid = min(BD, a.K - tile * BD);
+        const int k = tile * BS + (tid % BS);
+        const bool in_range = k < a.K;
+        const bool active = in_range && roller;
+        const int nvalid = min(BS, a.K - tile * BS);
         const unsigned long long kg = (unsigned long long)(a.k_offset + k);
-        fill_normals<real>(a, sm, tile, active, kg, nvalid);
+        fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
         if (!staged) {
             stage_finish<real, VARIANT, NU>(a, sm);
             staged = true;
+        } else if (a.tps > 1) {
+            __syncthreads();
         }
-        if (active) transform_column<real, VARIANT, NU>(a, sm, kg);
+        if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
+        if (a.tps > 1) __syncthreads();
 
-        // ---- rollout: every thread takes part in every step (the MMAs are CTA-wide) ---------------------
+        // ---- rollout: the MMAs are CTA-wide, so every thread keeps the step's three barriers ----------------
         real x[NX] = {(real)0, (real)0};
         if (active) {
             if (a.state_dev != nullptr) {
@@ -293,14 +302,15 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
         real roll = (real)0, pert = (real)0, smooth = (real)0, vprev = (real)0;
         for (int t = 0; t < T; ++t) {
             real v[NU] = {(real)0}, eps[NU] = {(real)0};
-            if (active) {
-                action_at<real, VARIANT, NU>(a, sm, kg, t, v);
-                noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
-            }
-            const real u = O::mul(nm.u_scale, v[0]);
-            const real uc = clamp<real>(u, -mp.max_torque, mp.max_torque);
-            // layer 1 operand row: [x0h x0h x0l | x1h x1h x1l | uh uh ul | 0...]
-            {
+            real u = (real)0;
+            if (roller) {
+                if (active) {
+                    action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+                    noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+                }
+                u = O::mul(nm.u_scale, v[0]);
+                const real uc = clamp<real>(u, -mp.max_torque, mp.max_torque);
+                // layer 1 operand row: [x0h x0h x0l | x1h x1h x1l | uh uh ul | 1 1 0...]
                 __nv_bfloat16 h0, l0, h1, l1, h2, l2;
                 tc::split_bf16(x[0], h0, l0);
                 tc::split_bf16(x[1], h1, l1);
@@ -309,25 +319,27 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
                 unsigned char* row = sA2 + (tid >> 3) * (CHUNKS * tc::CH) + (KB / 8) * tc::CH + (tid & 7) * 16;
                 *reinterpret_cast<uint4*>(row) = make_uint4(tc::pack2(h0, h0), tc::pack2(l0, h1), tc::pack2(h1, l1), tc::pack2(h2, h2));
                 *reinterpret_cast<uint4*>(row + tc::CH) = make_uint4(tc::pack2(l2, one), tc::pack2(one, z), 0u, 0u);
+                tc::fence_async_smem();
+                tc::fence_before();
             }
-            tc::fence_async_smem();
-            tc::fence_before();
             __syncthreads();
             if (tid == 0) {
                 tc::fence_after();
                 tc::mma_f16(tmem + 0, dA1, dB1, I32, 0u);
                 tc::mma_commit(&s_mma_bar);
             }
-            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
-            mma_phase ^= 1u;
-            tc::fence_after();
             float h[H];
-            tc::tmem_ld32(my_lane + 0, h);
+            if (roller) {
+                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+                tc::fence_after();
+                tc::tmem_ld32(my_lane + 0, h);
 #pragma unroll
-            for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
-            tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);
-            tc::fence_async_smem();
-            tc::fence_before();
+                for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
+                tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);
+                tc::fence_async_smem();
+                tc::fence_before();
+            }
+            mma_phase ^= 1u;
             __syncthreads();
             if (tid == 0) {
                 tc::fence_after();
@@ -339,15 +351,17 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
                 }
                 tc::mma_commit(&s_mma_bar);
             }
-            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
-            mma_phase ^= 1u;
-            tc::fence_after();
-            tc::tmem_ld32(my_lane + 32, h);
+            if (roller) {
+                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+                tc::fence_after();
+                tc::tmem_ld32(my_lane + 32, h);
 #pragma unroll
-            for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
-            tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);                 // MMA 2 has completed (barrier): its operand tile is free
-            tc::fence_async_smem();
-            tc::fence_before();
+                for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
+                tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);             // MMA 2 has completed (barrier): its operand tile is free
+                tc::fence_async_smem();
+                tc::fence_before();
+            }
+            mma_phase ^= 1u;
             __syncthreads();
             if (tid == 0) {
                 tc::fence_after();
@@ -359,14 +373,18 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
                 }
                 tc::mma_commit(&s_mma_bar);
             }
-            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+            if (roller) {
+                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+                tc::fence_after();
+                float o0, o1;
+                tc::tmem_ld2(my_lane + 0, o0, o1);
+                const real th = O::add(x[0], o0);
+                x[0] = O::sub(remainder<real>(O::add(th, mp.pi), mp.two_pi), mp.pi);    // pendulum_approximate.py:65
+                x[1] = O::add(x[1], o1);
+                // the next step's layer-1 MMA overwrites D3's columns: order this read before the barrier that releases it
+                tc::fence_before();
+            }
             mma_phase ^= 1u;
-            tc::fence_after();
-            float o0, o1;
-            tc::tmem_ld2(my_lane + 0, o0, o1);
-            const real th = O::add(x[0], o0);
-            x[0] = O::sub(remainder<real>(O::add(th, mp.pi), mp.two_pi), mp.pi);        // pendulum_approximate.py:65
-            x[1] = O::add(x[1], o1);
             if (active) {
                 roll = O::add(roll, Model::template cost<real>(mp, x, &u));               // mppi.py:318-319
                 pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));

@@ -21,4 +21,4 @@ for K in (32768, 131072):
             e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 30 * 1e3
             i = c.launch_info
-            print(f"K={K} tc={mode} fast_tanh={fast}: {us:.1f} us  grid={i.grid_blocks} block={i.block_threads} occ={i.max_blocks_per_sm} cost_mean={float(c.cost_total.mean()):.4f}", flush=True)
+            print(f"K={K} tc={mode} fast_tanh={fast}: {us:.1f} us  grid={i.grid_blocks} block={i.block_threads} occ={i.max_blocks_per_sm} tps={i.threads_per_sample} cost_mean={float(c.cost_total.mean()):.4f}", flush=True)

@@ -496,8 +496,8 @@ def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
         x = cpu_model.dynamics(x.view(1, -1), r["action"].view(1, -1)).view(-1)
 
 
-@pytest.mark.parametrize("variant", ["mppi", "smppi", "kmppi"])
-def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant):
+@pytest.mark.parametrize("variant,tile", [("mppi", 64), ("mppi", 128), ("smppi", 64), ("smppi", 128), ("kmppi", 64), ("kmppi", 128)])
+def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, tile, monkeypatch):
     """PendulumMLP(tensor_cores=True): the three layers run as tcgen05 MMAs (hi/lo-split bf16 operands,
     fp32 TMEM accumulators).  Same injected noise as the FFMA kernel: costs agree to ~1e-4 relative and
     the updated plan to 2e-4 (operand split error ~2^-16 per layer, 30 steps of a chaotic rollout), for a
@@ -505,6 +505,7 @@ def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant):
     import copy
     import pytorch_mppi_b200 as eng
     from oracle import mppi_oracle as orc
+    monkeypatch.setenv("MPPI_TC_TILE", str(tile))      # both tile shapes: 128 samples/CTA, or 64 + 64 helper threads
     torch.manual_seed(25)
     net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
                               torch.nn.Linear(32, 2))
@@ -538,7 +539,8 @@ def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant):
         u2 = a_tc.command(x)
         c1, c2 = a_ref.cost_total.cpu().numpy(), a_tc.cost_total.cpu().numpy()
         assert np.isfinite(c2).all()
-        assert a_tc.launch_info.block_threads == 128 and a_ref.launch_info.block_threads != 128
+        assert a_tc.launch_info.block_threads == 128 and a_tc.launch_info.threads_per_sample == 128 // tile
+        assert a_ref.launch_info.block_threads != 128
         np.testing.assert_allclose(c2, c1, rtol=2e-3, atol=2e-3)
         assert float(np.median(np.abs(c2 - c1) / np.maximum(1.0, np.abs(c1)))) < 2e-5
         assert float((a_tc.U - a_ref.U).abs().max()) < 2e-4, step

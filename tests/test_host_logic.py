@@ -154,3 +154,44 @@ def test_cuda_model_builds_a_variant_library():
     assert m.library_path() == m.library_path()                 # cached
     s = torch.randn(8, 2)
     assert torch.equal(m.dynamics(s, torch.zeros(8, 1)), ref.dynamics(s, torch.zeros(8, 1)))
+
+
+def test_bf16_split_contraction_precision_model():
+    """The arithmetic contract of the tensor-core MLP route (csrc/mppi_mlp_tc.cuh), restated with torch's
+    round-to-nearest bf16 casts:  v = hi + lo (both bf16), layer = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo + b_hi + b_lo
+    accumulated in fp32.  The dropped a_lo*w_lo term and the lo roundings leave ~2^-16 relative error per
+    layer; plain bf16 operands leave ~2^-8.  This pins the tolerances the GPU tests use for the two modes."""
+    torch.manual_seed(25)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                              torch.nn.Linear(32, 2))
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat((torch.rand(4096, 1, generator=g) * 6.28 - 3.14, torch.randn(4096, 1, generator=g) * 3,
+                   torch.rand(4096, 1, generator=g) * 4 - 2), dim=1)
+
+    def split(v):
+        hi = v.to(torch.bfloat16).to(torch.float32)
+        lo = (v - hi).to(torch.bfloat16).to(torch.float32)
+        return hi, lo
+
+    def layer(a, lin, mode):
+        w, b = lin.weight.detach(), lin.bias.detach()
+        wh, wl = split(w)
+        bh, bl = split(b)
+        ah, al = split(a)
+        if mode == "bf16x3":
+            return ah @ wh.T + al @ wh.T + ah @ wl.T + bh + bl
+        return ah @ wh.T + bh + bl
+
+    def forward(mode_hidden):
+        h = torch.tanh(layer(x, net[0], "bf16x3"))               # the state inputs are always split
+        h = torch.tanh(layer(h, net[2], mode_hidden))
+        return layer(h, net[4], mode_hidden)
+
+    with torch.no_grad():
+        want = net.double()(x.double())
+        net.float()
+        e3 = (forward("bf16x3").double() - want).abs().max().item()
+        e1 = (forward("bf16").double() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert e3 < 2e-5 * max(1.0, scale), e3
+    assert 1e-4 < e1 < 2e-2, e1                                   # plain bf16 really is ~2^-8: not a parity route
