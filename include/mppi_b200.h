@@ -226,6 +226,13 @@ uint64_t mppi_xchg_bytes(void);
 int mppi_materialize(const MppiFusedParams* p, void* perturbed_action /*(K,T,nu)*/, void* noise /*(K,T,nu)*/,
                      void* noise_theta /*KMPPI (K,S,nu) or NULL*/, void* states /*(K,T,nx) or NULL*/, void* stream);
 
+/* get_rollouts (mppi.py:425-448) for a registered model: `n_rollouts` start states (n_rollouts,nx) on the device, each
+ * rolled T steps through u_scale * actions[t] — one (T,nu) sequence replayed by every rollout (actions_stride = 0) or a
+ * sequence per rollout (actions_stride = elements between them, e.g. T*nu) — into states_out (n_rollouts,T,nx).
+ * Only model, dtype, nx, nu, u_scale and the model parameters of `p` are read. */
+int mppi_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, int64_t actions_stride,
+                        int32_t n_rollouts, int32_t T, void* states_out, void* stream);
+
 /* ---- Per-step entry points for arbitrary Python dynamics/cost callables ------------------------
  * The T-loop stays in Python (mppi.py:312-322); sampling, cost accumulation and the softmin update
  * are kernels. */

@@ -141,6 +141,7 @@ SYMBOLS = [
     ("mppi_xchg_destroy", C.c_int, [C.c_void_p]),
     ("mppi_xchg_bytes", C.c_uint64, []),
     ("mppi_materialize", C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mppi_rollout_states", C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ("mppi_sample_perturb", C.c_int, [_P, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                       C.c_int32, C.c_void_p]),
     ("mppi_cost_accumulate", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32,

@@ -636,9 +636,35 @@ int run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStrea
     fill_kargs<real>(p, a, 128, 1);
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp);
+    states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp,
+                                                                        (long long)p->T * p->nu);
     CK(cudaGetLastError());
     return MPPI_OK;
+}
+
+// get_rollouts (mppi.py:425-448): n start states, each rolled through an action sequence
+template <class Model, typename real>
+int run_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, long long stride, int n, int T,
+                       void* states, cudaStream_t stream) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    KArgs<real> a;
+    memset(&a, 0, sizeof(a));
+    a.nm.u_scale = (real)p->u_scale;
+    a.K = n;
+    a.T = T;
+    a.state_dev = (const real*)start_states;
+    a.state_per_sample = 1;
+    typename Model::template P<real> mp;
+    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    states_kernel<Model, real><<<(n + 127) / 128, 128, 0, stream>>>((const real*)actions, (real*)states, a, mp, stride);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+template <class Model>
+int run_rollout_states_dtype(const MppiFusedParams* p, const void* x0, const void* act, long long stride, int n, int T, void* out,
+                             cudaStream_t s) {
+    return p->dtype == MPPI_F32 ? run_rollout_states<Model, float>(p, x0, act, stride, n, T, out, s)
+                                : run_rollout_states<Model, double>(p, x0, act, stride, n, T, out, s);
 }
 
 template <typename real, int V>
@@ -860,6 +886,31 @@ int mppi_materialize(const MppiFusedParams* p, void* perturbed_action, void* noi
         case MPPI_MODEL_USER:
             return p->dtype == MPPI_F32 ? run_states<UserModel, float>(p, perturbed_action, states, s)
                                         : run_states<UserModel, double>(p, perturbed_action, states, s);
+#endif
+    }
+    return MPPI_ERR_UNSUPPORTED;
+}
+
+int mppi_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, int64_t actions_stride,
+                        int32_t n_rollouts, int32_t T, void* states_out, void* stream) {
+    if (p == nullptr || start_states == nullptr || actions == nullptr || states_out == nullptr) return MPPI_ERR_BAD_ARG;
+    if (p->struct_size != sizeof(MppiFusedParams)) return MPPI_ERR_ABI;
+    if (n_rollouts < 1 || T < 1 || actions_stride < 0) return MPPI_ERR_BAD_ARG;
+    if (p->dtype != MPPI_F32 && p->dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p->model) {
+#ifndef MPPI_ONLY_USER_MODEL
+        case MPPI_MODEL_PENDULUM:
+            return run_rollout_states_dtype<PendulumModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
+        case MPPI_MODEL_LINEAR_POINT:
+            return run_rollout_states_dtype<LinearPointModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
+        case MPPI_MODEL_PENDULUM_MLP:
+            if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) return MPPI_ERR_BAD_ARG;
+            return run_rollout_states_dtype<PendulumMLPModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
+#endif
+#ifdef MPPI_USER_MODEL_HEADER
+        case MPPI_MODEL_USER:
+            return run_rollout_states_dtype<UserModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
 #endif
     }
     return MPPI_ERR_UNSUPPORTED;

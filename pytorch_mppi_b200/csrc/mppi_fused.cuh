@@ -1083,14 +1083,17 @@ __global__ void __launch_bounds__(512) sample_kernel(const __grid_constant__ KAr
     }
 }
 
-// states along the rollout of given perturbed actions (mppi.py:307-322), for registered models
+// states along the rollout of given perturbed actions (mppi.py:307-322), for registered models.
+// pa_stride = elements between consecutive samples' action sequences: T*nu for a (K,T,nu) tensor, 0 when every
+// sample replays the SAME (T,nu) sequence (get_rollouts, mppi.py:425-448).
 template <class Model, typename real>
 __global__ void states_kernel(const real* __restrict__ pa, real* __restrict__ states, const KArgs<real> a,
-                              const typename Model::template P<real> mp) {
+                              const typename Model::template P<real> mp, long long pa_stride) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
+    pa += (size_t)k * (size_t)pa_stride;
     real x[NX];
     if (a.state_dev != nullptr) {
         const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
@@ -1100,7 +1103,7 @@ __global__ void states_kernel(const real* __restrict__ pa, real* __restrict__ st
     }
     for (int t = 0; t < a.T; ++t) {
         real u[NU];
-        for (int n = 0; n < NU; ++n) u[n] = O::mul(a.nm.u_scale, pa[((size_t)k * a.T + t) * NU + n]);
+        for (int n = 0; n < NU; ++n) u[n] = O::mul(a.nm.u_scale, pa[t * NU + n]);                 // mppi.py:313 / :445
         Model::template step<real>(mp, x, u);
         for (int i = 0; i < NX; ++i) states[((size_t)k * a.T + t) * NX + i] = x[i];
     }

@@ -1024,6 +1024,19 @@ class MPPI:
         if U is None:
             U = self.get_action_sequence()
         T = U.shape[0]
+        if self._model is not None and torch.is_tensor(U) and U.dim() == 2 and U.shape[1] == self.nu and T >= 1:
+            # registered model: one launch of the states kernel (every rollout replays the same sequence)
+            if state.size(0) != num_rollouts:
+                raise ValueError(f"state has {state.size(0)} rows, expected 1 or num_rollouts={num_rollouts}")
+            if self._dirty:
+                self._pack()
+            x0 = state.contiguous()
+            seq = U.to(self.d, self.dtype).contiguous()
+            out = torch.empty((num_rollouts, T, self.nx), dtype=self.dtype, device=self.d)
+            stream = torch.cuda.current_stream(self.d).cuda_stream
+            _cabi.check(self._lib.mppi_rollout_states(C.byref(self._p), x0.data_ptr(), seq.data_ptr(), 0, num_rollouts, T,
+                                                      out.data_ptr(), stream), "mppi_rollout_states")
+            return out
         states = torch.zeros((num_rollouts, T + 1, self.nx), dtype=U.dtype, device=U.device)
         states[:, 0] = state
         for t in range(T):

@@ -43,6 +43,16 @@ def test_bad_arguments_return_status_not_crash(lib):
     assert lib.mppi_fused_command(C.byref(p), None) == -1          # K == 0 -> bad argument
     assert lib.mppi_status_string(-3) == b"workspace too small"
     assert lib.mppi_cost_accumulate(None, None, None, 1, 1, 1.0, 0, None) == -1
+    # every pointer-taking entry point answers a null / empty request with a status, before any CUDA call
+    assert lib.mppi_rollout_states(C.byref(p), None, None, 0, 1, 1, None, None) == -1
+    assert lib.mppi_rollout_states(C.byref(p), 16, 16, 0, 0, 1, 16, None) == -1      # n_rollouts < 1
+    assert lib.mppi_rollout_states(C.byref(p), 16, 16, -1, 1, 1, 16, None) == -1     # negative stride
+    assert lib.mppi_plan_create(C.byref(p), None) == -1
+    assert lib.mppi_plan_destroy(None) == -1
+    assert lib.mppi_plan_command(None, None, None, 0, 0, 0, None, None, None) == -1
+    assert lib.mppi_omega(None, None, None, 1.0, 1, 0, None) == -1
+    assert lib.mppi_softmin_update(C.byref(p), None, None, None) == -1
+    assert lib.mppi_xchg_open(None, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

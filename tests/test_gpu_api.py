@@ -146,6 +146,50 @@ def test_get_rollouts(route):                              # :190-206
     assert torch.allclose(r, torch.zeros_like(r))
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("model", ["pendulum", "linear"])
+def test_get_rollouts_kernel_equals_plugin_replay(model, dtype, tol):   # mppi.py:425-448 on the registered-model route
+    """Registered models replay the sequence in ONE kernel launch (mppi_rollout_states); the result must be the
+    reference's loop `x <- dynamics(x, u_scale * U[t])` over the same model's torch callables."""
+    torch.manual_seed(3)
+    if model == "pendulum":
+        m = eng.Pendulum()
+        sigma, nu, lo, hi = torch.tensor(4.0, dtype=dtype), 1, -1.0, 1.0
+    else:
+        m = eng.LinearPoint.toy2d_nav()
+        sigma, nu, lo, hi = torch.eye(2, dtype=dtype), 2, -3.0, 3.0
+    term = m.terminal_cost if m.has_terminal else None
+    c = eng.MPPI(m.dynamics, m.running_cost, 2, sigma, num_samples=64, horizon=12, device=DEV, u_scale=1.5,
+                 terminal_state_cost=term)
+    assert c._model is m
+
+    def replay(x, U):
+        out = []
+        for t in range(U.shape[0]):
+            x = m.dynamics(x, (c.u_scale * U[t]).expand(x.shape[0], -1))
+            out.append(x)
+        return torch.stack(out, dim=1)
+
+    # (a) the controller's own plan, one start state broadcast to 5 rollouts
+    s = torch.tensor([lo, hi], dtype=dtype, device=DEV)
+    c.command(s)
+    r = c.get_rollouts(s, num_rollouts=5)
+    assert r.shape == (5, c.T, 2) and r.dtype == dtype
+    assert (r - replay(s.view(1, 2).expand(5, 2), c.U)).abs().max().item() <= tol
+    assert torch.equal(r[0], r[4])
+    # (b) one start state per rollout, a caller-supplied sequence of a different length (ragged: 130 rollouts, T=7)
+    S = torch.rand(130, 2, dtype=dtype, device=DEV) * (hi - lo) + lo
+    Useq = torch.randn(7, nu, dtype=dtype, device=DEV)
+    r = c.get_rollouts(S, num_rollouts=130, U=Useq)
+    assert r.shape == (130, 7, 2)
+    assert (r - replay(S, Useq)).abs().max().item() <= tol
+    # (c) a single step, a single rollout
+    r = c.get_rollouts(S[:1], num_rollouts=1, U=Useq[:1])
+    assert (r - replay(S[:1], Useq[:1])).abs().max().item() <= tol
+    with pytest.raises(ValueError):
+        c.get_rollouts(S[:3], num_rollouts=5)
+
+
 @pytest.mark.parametrize("route", ROUTES)
 def test_change_horizon_reset_shift(route):                # :208-230, 293-315
     c = make(route=route, horizon=10)
