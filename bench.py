@@ -172,11 +172,17 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    K, T = wl["K"], wl["T"]
+    # same problem as the engine arm launched with the same flags: under weak scaling the job is K per GPU x N GPUs
+    K, T = wl["K"] * (args.gpus if args.scaling == "weak" else 1), wl["T"]
     cores = pick_cpu_threads(K, T)
     prob, state = make_cpu_problem(K, T)
-    for _ in range(max(args.warmup, 1)):
+    n_warm = max(min(args.warmup, 10), 1)
+    t0 = time.perf_counter()
+    for _ in range(n_warm):
         cpu_port_step(prob, state)
+    t_step = (time.perf_counter() - t0) / n_warm
+    # bounded: the timed region stays under ~2 minutes whatever --steps asks for (at least 20 commands)
+    args.steps = max(min(args.steps, int(120.0 / t_step)), min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_port_step(prob, state)
@@ -185,9 +191,9 @@ def run_reference(args, wl):
     line = {
         "impl": "reference", "metric": "K*T rollout-steps/s through command()", "value": value, "unit": "rollout-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "K": K, "T": T, "nx": NX, "nu": NU, "noise_sigma": SIGMA2, "lambda": LAMBDA,
-                   "device": "cpu", "commands_per_s": args.steps / dt},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "K_global": K, "K": K, "T": T, "nx": NX, "nu": NU, "noise_sigma": SIGMA2,
+                   "lambda": LAMBDA, "u_bounds": [-UMAX, UMAX], "device": "cpu", "commands_per_s": args.steps / dt},
         "cpu_baseline": {"value": value, "unit": "rollout-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} closed-loop command() calls of the oracle port (torch CPU ops, randn included), {cores} threads (fastest of 1..{os.cpu_count()})"},
         "e2e": {"value": value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -371,9 +377,7 @@ def main():
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        if args.steps > 2000:
-            args.steps = 2000      # bounded: ~13 ms per CPU step
-        run_reference(args, wl)
+        run_reference(args, wl)      # bounds its own step count (~13 ms per CPU command at K=16384)
     else:
         run_engine(args, wl)
 
