@@ -77,9 +77,13 @@ enum {
                                              partial_out and do NOT update U (mppi_apply_partials finishes)    */
     MPPI_FLAG_NOMINAL_PADDED = 1u << 7,   /* U (and A) are 16-byte aligned allocations padded to a multiple of
                                              16 bytes: lets the kernel stage them with one TMA bulk copy        */
-    MPPI_FLAG_PDL = 1u << 8               /* programmatic dependent launch: the kernel may start while the previous
+    MPPI_FLAG_PDL = 1u << 8,              /* programmatic dependent launch: the kernel may start while the previous
                                              kernel on the stream is finishing; it draws its Philox normals (shared
                                              memory only) and touches global memory only after griddepcontrol.wait */
+    MPPI_FLAG_SPLIT_COST = 1u << 9        /* small problems (threads_per_sample > 1): the rollout thread runs the bare state
+                                             recurrence, the sample's helper threads evaluate the T running costs in
+                                             parallel from the stored states, summed in the reference's order (same
+                                             operations and rounding as the single-loop rollout; see mppi_fused.cuh)  */
 };
 
 /* One `command()` of a registered analytic model: replaces, in one launch,
@@ -174,6 +178,8 @@ typedef struct MppiLaunchInfo {
     uint64_t workspace_bytes;    /* minimum workspace for these dimensions                               */
     int32_t tma_staging;         /* 1 if the nominal sequence is staged with cp.async.bulk (TMA)         */
     int32_t threads_per_sample;
+    int32_t split_cost;          /* 1 if MPPI_FLAG_SPLIT_COST was honoured for these dimensions          */
+    int32_t _pad;
 } MppiLaunchInfo;
 
 int mppi_b200_abi_version(void);

@@ -31,6 +31,7 @@ FLAG_STATE_PER_SAMPLE = 1 << 5
 FLAG_EXPORT_PARTIAL = 1 << 6
 FLAG_NOMINAL_PADDED = 1 << 7
 FLAG_PDL = 1 << 8
+FLAG_SPLIT_COST = 1 << 9
 
 STATUS = {0: "ok", -1: "bad argument", -2: "unsupported", -3: "workspace too small", -4: "CUDA error",
           -5: "ABI mismatch", -6: "peer exchange timeout"}
@@ -116,6 +117,8 @@ class MppiLaunchInfo(C.Structure):
         ("workspace_bytes", C.c_uint64),
         ("tma_staging", C.c_int32),
         ("threads_per_sample", C.c_int32),
+        ("split_cost", C.c_int32),
+        ("_pad", C.c_int32),
     ]
 
 

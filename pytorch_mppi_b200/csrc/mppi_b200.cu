@@ -372,6 +372,28 @@ bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, K
     return false;
 }
 
+// MPPI_FLAG_SPLIT_COST: problems small enough to run with helper threads (threads_per_sample > 1) may take the
+// split-cost rollout (fused_command_kernel<..., SPLIT = true>) if its per-step state buffer fits in shared memory;
+// the geometry stays the one chosen for the plain kernel.
+template <class Model, typename real, int V, typename KernelT>
+void select_split_cost_rollout(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& split) {
+    split = 0;
+    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
+        if (!eligible || !(p->flags & MPPI_FLAG_SPLIT_COST) || g.tps <= 1) return;
+        KernelT k2 = fused_command_kernel<Model, real, V, false, true>;
+        MppiFusedParams p2 = *p;
+        p2.block_threads = g.BS;
+        p2.threads_per_sample = g.tps;
+        p2.grid_blocks = g.nb;
+        Geometry g2;
+        if (plan_geometry(k2, &p2, (int)sizeof(real), Model::NX << 8, false, g2, layout_fn<real>) != MPPI_OK) return;
+        if (g2.BS != g.BS || g2.tps != g.tps) return;
+        kernel = k2;
+        g = g2;
+        split = 1;
+    }
+}
+
 template <class Model, typename real, int V>
 int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
@@ -386,6 +408,8 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
     g_tc_kernel = 0;
     if (rc) return rc;
+    int split = 0;
+    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, g, split);
     const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
     KArgs<real> a;
     fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
@@ -402,6 +426,7 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
         // report the worst case so one allocation serves any later geometry for these dimensions
         info->workspace_bytes = ws_bytes(di.sm_count * 16, rows_of(p), (int)sizeof(real));
         info->tma_staging = a.tma_ok;
+        info->split_cost = split;
         return MPPI_OK;
     }
     if (p->U == nullptr || p->cost_total == nullptr || p->action_out == nullptr || p->nominal_used == nullptr ||
@@ -457,6 +482,8 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
     g_tc_kernel = 0;
     if (rc) return rc;
+    int split = 0;
+    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, pl->g, split);
     if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
         return MPPI_ERR_BAD_ARG;
     if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;

@@ -95,7 +95,7 @@ template <typename real> struct KArgs {
 // ---- shared-memory carve, computed identically on host and device -------------------------------
 struct SmemLayout {
     int off_uraw, off_araw, off_thraw, off_us, off_as, off_ths, off_w, off_wsh, off_vrun, off_ws, off_red,
-        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, total;
+        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, off_xs, total;
     int LD;
 };
 
@@ -103,9 +103,12 @@ __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a *
 
 // rows2 (a second TN-row tile) is only used by sample_kernel for KMPPI
 // BD = threads per CTA, BS = samples per tile (BD / threads-per-sample)
+// `extra`: bit 0 = rows2 needed; bits 8.. = nx of the split-cost rollout's per-step state buffer xs[T*nx][BS]
+// (0 = none; see fused_command_kernel<..., SPLIT>)
 template <typename real>
-__host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int BS, int nb, int need_rows2) {
+__host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int BS, int nb, int extra) {
     SmemLayout L;
+    const int need_rows2 = extra & 1, nx_split = extra >> 8;
     const int es = (int)sizeof(real);
     const int TN = T * nu, SN = S * nu, nw = BD / 32;
     int o = 16;  // [0,8): mbarrier
@@ -128,6 +131,7 @@ __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, in
     L.off_part2 = o; o = align_up(o + nw * R * 8, 16);
     L.off_numd = o; o = align_up(o + (R + 2) * 8, 16);
     L.off_redd = o; o = align_up(o + 64 * 8, 16);
+    L.off_xs = o; o = align_up(o + T * nx_split * BS * es, 16);
     L.total = o;
     return L;
 }
@@ -213,7 +217,7 @@ template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
 // ---- shared-memory view ---------------------------------------------------------------------
 template <typename real> struct Smem {
     unsigned long long* bar;
-    real *Uraw, *Araw, *thraw, *Us, *As, *ths, *Ws, *Wsh, *Vrun, *w_s, *red, *part, *rows, *rows2, *sS;
+    real *Uraw, *Araw, *thraw, *Us, *As, *ths, *Ws, *Wsh, *Vrun, *w_s, *red, *part, *rows, *rows2, *sS, *xs;
     double *part2, *numd, *redd;
     int LD;
     __device__ Smem(unsigned char* smem, const SmemLayout& L) {
@@ -236,6 +240,7 @@ template <typename real> struct Smem {
         part2 = reinterpret_cast<double*>(smem + L.off_part2);
         numd = reinterpret_cast<double*>(smem + L.off_numd);
         redd = reinterpret_cast<double*>(smem + L.off_redd);
+        xs = reinterpret_cast<real*>(smem + L.off_xs);
         LD = L.LD;
     }
 };
@@ -862,8 +867,15 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
 // =================================================================================================
 // The fused command kernel
 // =================================================================================================
-template <class Model, typename real, int VARIANT, bool BATCHED>
-__global__ void __launch_bounds__(512) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
+// SPLIT (threads_per_sample > 1 only, i.e. problems too small to fill the machine): the rollout is the one
+// phase a sample's helper threads cannot share — the state recurrence is serial.  But only the DYNAMICS are:
+// the running cost of step t depends on x_t alone.  So the rollout thread runs the bare recurrence and parks
+// every x_t in shared memory (xs[T*NX][BS]); then all tps threads of the sample evaluate the T running costs
+// in parallel (in place: cost_t overwrites x_t[0]); then the rollout thread adds them up in the reference's
+// order t = 0..T-1.  Same operations, same rounding, same summation order as the fused loop — the single
+// resident warp just stops carrying the cost's ~45 instructions per step on its critical path.
+template <class Model, typename real, int VARIANT, bool BATCHED, bool SPLIT = false>
+__global__ void __launch_bounds__(512, SPLIT ? 1 : 0) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                             const __grid_constant__ typename Model::template P<real> mp) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;
@@ -873,7 +885,7 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const __grid_constan
     if (BATCHED) make_env_args<real, NX, NU>(a_in, reinterpret_cast<KArgs<real>*>(a_env_raw));
     const KArgs<real>& a = BATCHED ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, 0);
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, SPLIT ? (NX << 8) : 0);
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
@@ -914,7 +926,70 @@ __global__ void __launch_bounds__(512) fused_command_kernel(const __grid_constan
         if (tile == blockIdx.x) stamp(a.dbg, 3);
 
         real c_tot = O::inf();
-        if (active) {
+        if constexpr (SPLIT) {
+            // C'. split rollout: recurrence (rollout thread) | running costs (all tps threads) | ordered sum
+            real* xcol = sm.xs + (tid % BS);
+            real x[NX];
+            real pert = (real)0, smooth = (real)0;
+            if (active) {
+                if (a.state_dev != nullptr) {
+                    const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) x[i] = sp[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) x[i] = a.x0[i];
+                }
+                real vprev[NU];
+#pragma unroll
+                for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
+MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
+                for (int t = 0; t < T; ++t) {
+                    real v[NU], u[NU], eps[NU];
+                    action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+                    noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+#pragma unroll
+                    for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
+                    Model::template step<real>(mp, x, u);                                     // mppi.py:314
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) xcol[(t * NX + i) * BS] = x[i];
+                    pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
+                    if (VARIANT == V_SMPPI) {
+                        if (t > 0) {
+#pragma unroll
+                            for (int n = 0; n < NU; ++n) {
+                                const real d = O::mul(nm.u_scale, O::sub(v[n], vprev[n]));    // mppi.py:559
+                                smooth = O::add(smooth, O::mul(d, d));
+                            }
+                        }
+#pragma unroll
+                        for (int n = 0; n < NU; ++n) vprev[n] = v[n];
+                    }
+                }
+            }
+            __syncthreads();
+            if (in_range) {
+MPPI_UNROLL_N(2)
+                for (int t = tid / BS; t < T; t += a.tps) {      // independent across t: two in flight per thread
+                    real v[NU], u[NU], xt[NX];
+                    action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+#pragma unroll
+                    for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) xt[i] = xcol[(t * NX + i) * BS];
+                    xcol[(t * NX) * BS] = Model::template cost<real>(mp, xt, u);              // mppi.py:318
+                }
+            }
+            __syncthreads();
+            if (active) {
+                real roll = (real)0;
+                for (int t = 0; t < T; ++t) roll = O::add(roll, xcol[(t * NX) * BS]);         // mppi.py:319, t = 0..T-1
+                if (Model::template has_terminal<real>(mp)) roll = O::add(roll, Model::template terminal<real>(mp, x));
+                c_tot = O::add(roll, pert);                                                   // mppi.py:416
+                if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569
+                a.cost_total[k] = c_tot;
+            }
+        } else if (active) {
 
             // C. rollout (mppi.py:297-332) + action cost (mppi.py:409,415) [+ smoothness :559-562]
             real x[NX];

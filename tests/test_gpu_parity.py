@@ -89,6 +89,49 @@ def test_stepped_route_matches_reference_golden(name):
     _run(name, "stepped")
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_split_cost_rollout_is_bit_identical_to_the_single_loop(name, monkeypatch):
+    """MPPI_FLAG_SPLIT_COST (MPPI_B200_SPLIT_COST=1): the rollout thread runs the bare recurrence, the sample's
+    helper threads evaluate the running costs in parallel, the sum is taken in the reference's order.  Same
+    operations, same rounding, same order -> cost_total, U (A, theta) and the action must be BIT-identical to the
+    single-loop kernel on the same draws, for every golden case (all three variants, both dtypes, ragged K)."""
+    from tests.golden.engine import make_engine
+    case, gold = load(name)
+    run = OracleRunner(case)
+    monkeypatch.delenv("MPPI_B200_SPLIT_COST", raising=False)
+    plain = make_engine(case, run.stream.U0)
+    monkeypatch.setenv("MPPI_B200_SPLIT_COST", "1")
+    split = make_engine(case, run.stream.U0)
+    for step in range(min(case["steps"], 3)):
+        x = torch.from_numpy(gold[f"x_{step}"]).to(run.prob.dtype).numpy()
+        z = run.stream.next_z()
+        plain.inject_noise(z)
+        split.inject_noise(z)
+        a0 = plain.command(x)
+        a1 = split.command(x)
+        # the flag is honoured exactly when the problem is small enough to run with helper threads
+        assert plain.launch_info.split_cost == 0
+        assert split.launch_info.split_cost == (1 if split.launch_info.threads_per_sample > 1 else 0)
+        assert split.launch_info.threads_per_sample == plain.launch_info.threads_per_sample
+        assert torch.equal(plain.cost_total, split.cost_total), name
+        assert torch.equal(plain.U, split.U), name
+        assert torch.equal(a0, a1), name
+        if case["variant"] == "smppi":
+            assert torch.equal(plain.action_sequence, split.action_sequence)
+        if case["variant"] == "kmppi":
+            assert torch.equal(plain.theta, split.theta)
+    # every golden case but none is large enough to lose its helper threads on a B200 (<= 148 tiles)
+    assert split.launch_info.split_cost == 1, (name, split.launch_info.threads_per_sample)
+    # and the split kernel meets the reference tolerance on its own (first command, golden U)
+    tol = U_TOL_OVERRIDE.get(name, U_TOL[case["dtype"]])
+    run2 = OracleRunner(case)
+    monkeypatch.setenv("MPPI_B200_SPLIT_COST", "1")
+    again = make_engine(case, run2.stream.U0)
+    again.inject_noise(run2.stream.next_z())
+    again.command(torch.from_numpy(gold["x_0"]).to(run2.prob.dtype).numpy())
+    assert float(np.abs(again.U.cpu().numpy() - gold["U_0"]).max()) <= tol
+
+
 def test_closed_loop_free_running_c2():
     """10 closed-loop commands WITHOUT resynchronising U: error vs the fp32 reference stays at the
     fp32 noise floor (SURVEY.md §8d parity check)."""
