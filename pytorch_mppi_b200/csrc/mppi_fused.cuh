@@ -29,6 +29,11 @@
 #ifndef MPPI_ROLLOUT_UNROLL
 #define MPPI_ROLLOUT_UNROLL 2
 #endif
+// minimum resident CTAs per SM promised to ptxas for the fused kernel: 0 = unspecified (ptxas then keeps 512-thread
+// CTAs at 64 registers, two per SM — what large K wants); 1 lifts the cap (no spills, one 512-thread CTA per SM)
+#ifndef MPPI_FUSED_MIN_BLOCKS
+#define MPPI_FUSED_MIN_BLOCKS 0
+#endif
 #define MPPI_PRAGMA_(x) _Pragma(#x)
 #define MPPI_UNROLL_N(n) MPPI_PRAGMA_(unroll n)
 
@@ -875,7 +880,7 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
 // order t = 0..T-1.  Same operations, same rounding, same summation order as the fused loop — the single
 // resident warp just stops carrying the cost's ~45 instructions per step on its critical path.
 template <class Model, typename real, int VARIANT, bool BATCHED, bool SPLIT = false>
-__global__ void __launch_bounds__(512, SPLIT ? 1 : 0) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
+__global__ void __launch_bounds__(512, SPLIT ? 1 : MPPI_FUSED_MIN_BLOCKS) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                             const __grid_constant__ typename Model::template P<real> mp) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;
