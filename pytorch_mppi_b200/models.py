@@ -232,8 +232,9 @@ class CudaModel(AnalyticModel):
                    bit-level agreement with an eager fp32 torch implementation), sinf/exp/... via O::sin_, O::exp_
 
     `cost_code` and `terminal_code` must `return` a `real`.  `dynamics` / `running_cost` / `terminal_cost`
-    are the torch callables of the same model (used by the stepped route, by `get_rollouts`, and as your
-    simulator); pass ``model.dynamics`` / ``model.running_cost`` to the controller as usual.
+    are the torch callables of the same model (used by the stepped route and as your simulator;
+    `get_rollouts` runs the compiled `step_code`); pass ``model.dynamics`` / ``model.running_cost`` to the
+    controller as usual.
     """
     model_id = _cabi.MODEL_USER
 
