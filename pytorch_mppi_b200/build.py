@@ -20,16 +20,32 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--threads", "4"]
 
 
+STAMP = OUT + ".stamp"
+
+
+def source_hash() -> str:
+    """Hash of everything the library is compiled from (sources, headers, flags).  File times are not used: the
+    snapshot that ships the tree to a GPU box does not promise to keep them, and a spurious rebuild there costs
+    GPU minutes."""
+    import hashlib
+    h = hashlib.sha1(" ".join(NVCC_FLAGS).encode())
+    for d in DEPS:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(OUT):
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return True
-    t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
+    h = source_hash()          # of the sources as compiled (taken before nvcc runs)
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, SRC]
     if verbose:
@@ -40,6 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         print(r.stderr)
+    with open(STAMP, "w") as f:
+        f.write(h)
     return OUT
 
 

@@ -91,14 +91,15 @@ def test_stepped_route_matches_reference_golden(name):
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_split_cost_rollout_is_bit_identical_to_the_single_loop(name, monkeypatch):
-    """MPPI_FLAG_SPLIT_COST (MPPI_B200_SPLIT_COST=1): the rollout thread runs the bare recurrence, the sample's
+    """MPPI_FLAG_SPLIT_COST (the default for single-GPU problems small enough to run with helper threads;
+    MPPI_B200_SPLIT_COST=0 turns it off): the rollout thread runs the bare recurrence, the sample's
     helper threads evaluate the running costs in parallel, the sum is taken in the reference's order.  Same
     operations, same rounding, same order -> cost_total, U (A, theta) and the action must be BIT-identical to the
     single-loop kernel on the same draws, for every golden case (all three variants, both dtypes, ragged K)."""
     from tests.golden.engine import make_engine
     case, gold = load(name)
     run = OracleRunner(case)
-    monkeypatch.delenv("MPPI_B200_SPLIT_COST", raising=False)
+    monkeypatch.setenv("MPPI_B200_SPLIT_COST", "0")
     plain = make_engine(case, run.stream.U0)
     monkeypatch.setenv("MPPI_B200_SPLIT_COST", "1")
     split = make_engine(case, run.stream.U0)
