@@ -195,3 +195,25 @@ def test_bf16_split_contraction_precision_model():
     scale = want.abs().max().item()
     assert e3 < 2e-5 * max(1.0, scale), e3
     assert 1e-4 < e1 < 2e-2, e1                                   # plain bf16 really is ~2^-8: not a parity route
+
+
+def test_build_is_keyed_by_source_hash_not_file_times(tmp_path, monkeypatch):
+    """The in-tree library is rebuilt when (and only when) the sources it was compiled from change: the stamp next to
+    the .so holds their hash, so a snapshot copy that scrambles file times does not trigger a rebuild on the GPU box."""
+    from pytorch_mppi_b200 import build
+    build.build()
+    assert not build.needs_build()
+    h = build.source_hash()
+    assert open(build.STAMP).read().strip() == h and len(h) == 40
+    # older/newer file times alone change nothing
+    os.utime(build.SRC, None)
+    assert not build.needs_build()
+    # a different source does
+    fake = tmp_path / "extra.cuh"
+    fake.write_text("// edited\n")
+    monkeypatch.setattr(build, "DEPS", [*build.DEPS, str(fake)])
+    assert build.source_hash() != h and build.needs_build()
+    # and so does a missing stamp
+    monkeypatch.setattr(build, "DEPS", build.DEPS[:-1])
+    monkeypatch.setattr(build, "STAMP", str(tmp_path / "nope.stamp"))
+    assert build.needs_build()
