@@ -18,7 +18,7 @@ def _problem(K, T, lam=1.0, dtype=torch.float64, **kw):
                        u_min=torch.tensor(-2.0, dtype=dtype), u_max=torch.tensor(2.0, dtype=dtype), **kw)
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(K=st.integers(1, 300), shift=st.floats(-1e3, 1e3), lam=st.floats(0.05, 20.0), seed=st.integers(0, 2 ** 31 - 1))
 def test_softmin_is_shift_invariant_and_normalised(K, shift, lam, seed):       # mppi.py:254-259
     g = torch.Generator().manual_seed(seed)
@@ -31,7 +31,7 @@ def test_softmin_is_shift_invariant_and_normalised(K, shift, lam, seed):       #
     assert abs(float(beta2 - beta) - shift) <= 1e-9 * max(1.0, abs(shift))
 
 
-@settings(max_examples=12, deadline=None)
+@settings(max_examples=12, deadline=None, derandomize=True)
 @given(K=st.integers(1, 200), T=st.integers(1, 12), seed=st.integers(0, 2 ** 31 - 1))
 def test_update_is_a_convex_combination_of_the_sampled_noise_and_respects_bounds(K, T, seed):
     g = torch.Generator().manual_seed(seed)
@@ -51,10 +51,11 @@ def test_update_is_a_convex_combination_of_the_sampled_noise_and_respects_bounds
     perm = torch.randperm(K, generator=g)
     r2 = orc.mppi_command(prob, U, torch.tensor([math.pi, 1.0]), z[perm])
     assert torch.allclose(r2["U"], r["U"], atol=1e-12)
-    assert torch.allclose(r2["cost_total"], r["cost_total"][perm], atol=0, rtol=0)
+    # (a sample's cost may differ in the last bit with its position: ATen's vectorised body vs scalar tail of sin/exp)
+    assert torch.allclose(r2["cost_total"], r["cost_total"][perm], atol=0, rtol=1e-13)
 
 
-@settings(max_examples=12, deadline=None)
+@settings(max_examples=12, deadline=None, derandomize=True)
 @given(K=st.integers(2, 257), world=st.integers(1, 8), T=st.integers(1, 9), lam=st.floats(0.1, 5.0),
        seed=st.integers(0, 2 ** 31 - 1))
 def test_any_k_sharding_combines_to_the_unsharded_update(K, world, T, lam, seed):   # (beta_g, eta_g, V_g)
