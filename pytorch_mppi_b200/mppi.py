@@ -182,7 +182,11 @@ class MPPI:
         self._pdl = os.environ.get("MPPI_B200_PDL", "1") != "0"
         # split-cost rollout for problems that run with helper threads: measured 17.1 -> 14.8 us per command back to
         # back at K=16384, T=30 (bit-identical results); MPPI_B200_SPLIT_COST=0 selects the single-loop kernel
-        self._split_cost = os.environ.get("MPPI_B200_SPLIT_COST", "1") != "0"
+        # (=2 also selects it on multi-GPU controllers, which otherwise stay on the single-loop kernel: that combination
+        # has not been run on two GPUs yet)
+        _mode = os.environ.get("MPPI_B200_SPLIT_COST", "1")
+        self._split_cost = _mode != "0"
+        self._split_cost_multi_gpu = _mode == "2"
         self._threads_per_sample = int(threads_per_sample)
 
         # multi-GPU: K is the GLOBAL sample count, sharded over the group
@@ -371,7 +375,8 @@ class MPPI:
                             | (_cabi.FLAG_DIAG_SIGMA if self._diagonal_sigma else 0)
                             | _cabi.FLAG_NOMINAL_PADDED
                             | (_cabi.FLAG_PDL if (self._pdl and self._model is not None) else 0)
-                            | (_cabi.FLAG_SPLIT_COST if (self._split_cost and self._model is not None and self._world == 1) else 0))
+                            | (_cabi.FLAG_SPLIT_COST if (self._split_cost and self._model is not None
+                                                          and (self._world == 1 or self._split_cost_multi_gpu)) else 0))
         p.U = self._Ubuf.data_ptr()
         p.A = None
         p.theta = None

@@ -11,9 +11,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, split_mode="1"):
     import torch.distributed as dist
     import pytorch_mppi_b200 as eng
+    os.environ["MPPI_B200_SPLIT_COST"] = split_mode     # "2": the sharded controllers take the split-cost rollout too
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -84,12 +85,15 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpu_sharding_matches_single_gpu():
+@pytest.mark.parametrize("split_mode", ["1", "2"])
+def test_two_gpu_sharding_matches_single_gpu(split_mode):
+    if split_mode == "2" and os.environ.get("MPPI_TEST_SPLIT_MULTI_GPU", "0") != "1":
+        pytest.skip("split-cost rollout on sharded controllers: first run it with MPPI_TEST_SPLIT_MULTI_GPU=1 (round 2)")
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29700 + (os.getpid() % 1000)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    port = 29700 + (os.getpid() % 1000) + (50 if split_mode == "2" else 0)
+    mp.spawn(_worker, args=(2, port, out, split_mode), nprocs=2, join=True)
     assert len(out) == 2
     for rank in range(2):
         for key, (err, aerr, same) in out[rank].items():
