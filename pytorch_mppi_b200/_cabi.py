@@ -32,6 +32,7 @@ FLAG_EXPORT_PARTIAL = 1 << 6
 FLAG_NOMINAL_PADDED = 1 << 7
 FLAG_PDL = 1 << 8
 FLAG_SPLIT_COST = 1 << 9
+FLAG_WIDE_REGS = 1 << 10
 
 STATUS = {0: "ok", -1: "bad argument", -2: "unsupported", -3: "workspace too small", -4: "CUDA error",
           -5: "ABI mismatch", -6: "peer exchange timeout"}
@@ -118,7 +119,7 @@ class MppiLaunchInfo(C.Structure):
         ("tma_staging", C.c_int32),
         ("threads_per_sample", C.c_int32),
         ("split_cost", C.c_int32),
-        ("_pad", C.c_int32),
+        ("wide_regs", C.c_int32),
     ]
 
 

@@ -394,6 +394,27 @@ void select_split_cost_rollout(const MppiFusedParams* p, bool eligible, KernelT&
     }
 }
 
+// MPPI_FLAG_WIDE_REGS: a launch that puts at most one CTA on an SM can afford the instantiation compiled without the
+// 64-register cap (fused_command_kernel<..., SPLIT = false, MINB = 1>: no spills in the last-CTA tail).
+template <class Model, typename real, int V, typename KernelT>
+void select_wide_register_kernel(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& wide) {
+    wide = 0;
+    if (!eligible || !(p->flags & MPPI_FLAG_WIDE_REGS)) return;
+    DevInfo di;
+    if (get_dev_info(di) != MPPI_OK || g.nb > di.sm_count) return;
+    KernelT k2 = fused_command_kernel<Model, real, V, false, false, 1>;
+    MppiFusedParams p2 = *p;
+    p2.block_threads = g.BS;
+    p2.threads_per_sample = g.tps;
+    p2.grid_blocks = g.nb;
+    Geometry g2;
+    if (plan_geometry(k2, &p2, (int)sizeof(real), 0, false, g2, layout_fn<real>) != MPPI_OK) return;
+    if (g2.BS != g.BS || g2.tps != g.tps || g2.nb != g.nb) return;
+    kernel = k2;
+    g = g2;
+    wide = 1;
+}
+
 template <class Model, typename real, int V>
 int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
     if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
@@ -408,8 +429,9 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
     g_tc_kernel = 0;
     if (rc) return rc;
-    int split = 0;
+    int split = 0, wide = 0;
     select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, g, split);
+    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, g, wide);
     const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
     KArgs<real> a;
     fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
@@ -427,6 +449,7 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
         info->workspace_bytes = ws_bytes(di.sm_count * 16, rows_of(p), (int)sizeof(real));
         info->tma_staging = a.tma_ok;
         info->split_cost = split;
+        info->wide_regs = wide;
         return MPPI_OK;
     }
     if (p->U == nullptr || p->cost_total == nullptr || p->action_out == nullptr || p->nominal_used == nullptr ||
@@ -482,8 +505,9 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
     g_tc_kernel = 0;
     if (rc) return rc;
-    int split = 0;
+    int split = 0, wide = 0;
     select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, pl->g, split);
+    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, pl->g, wide);
     if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
         return MPPI_ERR_BAD_ARG;
     if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;

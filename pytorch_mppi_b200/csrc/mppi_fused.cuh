@@ -879,8 +879,12 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
 // in parallel (in place: cost_t overwrites x_t[0]); then the rollout thread adds them up in the reference's
 // order t = 0..T-1.  Same operations, same rounding, same summation order as the fused loop — the single
 // resident warp just stops carrying the cost's ~45 instructions per step on its critical path.
-template <class Model, typename real, int VARIANT, bool BATCHED, bool SPLIT = false>
-__global__ void __launch_bounds__(512, SPLIT ? 1 : MPPI_FUSED_MIN_BLOCKS) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
+//
+// MINB: minimum resident CTAs per SM promised to ptxas.  0 (the default) keeps 512-thread CTAs at 64 registers, which the
+// two-CTA-per-SM geometry of large K needs but which spills the tail's prefetch array; 1 lifts the cap (96 registers, no
+// spills) for launches that place at most one CTA on an SM (MPPI_FLAG_WIDE_REGS; the split-cost variant always has it).
+template <class Model, typename real, int VARIANT, bool BATCHED, bool SPLIT = false, int MINB = (SPLIT ? 1 : MPPI_FUSED_MIN_BLOCKS)>
+__global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                             const __grid_constant__ typename Model::template P<real> mp) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;

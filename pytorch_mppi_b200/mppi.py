@@ -187,6 +187,9 @@ class MPPI:
         _mode = os.environ.get("MPPI_B200_SPLIT_COST", "1")
         self._split_cost = _mode != "0"
         self._split_cost_multi_gpu = _mode == "2"
+        # opt-in (not yet the default: to be measured at mid-size K and on sharded controllers): the single-loop kernel
+        # compiled without the 64-register cap for launches of at most one CTA per SM
+        self._wide_regs = os.environ.get("MPPI_B200_WIDE_REGS", "0") != "0"
         self._threads_per_sample = int(threads_per_sample)
 
         # multi-GPU: K is the GLOBAL sample count, sharded over the group
@@ -375,6 +378,7 @@ class MPPI:
                             | (_cabi.FLAG_DIAG_SIGMA if self._diagonal_sigma else 0)
                             | _cabi.FLAG_NOMINAL_PADDED
                             | (_cabi.FLAG_PDL if (self._pdl and self._model is not None) else 0)
+                            | (_cabi.FLAG_WIDE_REGS if (self._wide_regs and self._model is not None) else 0)
                             | (_cabi.FLAG_SPLIT_COST if (self._split_cost and self._model is not None
                                                           and (self._world == 1 or self._split_cost_multi_gpu)) else 0))
         p.U = self._Ubuf.data_ptr()

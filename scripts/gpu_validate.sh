@@ -1,20 +1,16 @@
 #!/bin/bash
-# One-call GPU validation used at the end of round 1 (run under gpurun from the repo root):
-#   1. A/B timing of the split-cost rollout and of the uncapped-register build of the default kernel
-#   2. the whole GPU suite with MPPI_B200_SPLIT_COST=1 (small problems take the split kernel, large K the default one;
-#      the bit-identity test builds its `plain` engines with the variable removed)
-#   3. bench lines for both settings
-# Everything lands in gpurun_out/.
+# One-call GPU validation (run under gpurun from the repo root; everything lands in gpurun_out/):
+#   1. A/B timing of the fused kernel's rollout variants (single loop / uncapped registers / split cost)
+#   2. the whole GPU suite, including the opt-in bit-identity test of the wide-register instantiation
+#      (with --gpus 2 also the sharded controllers on the split-cost rollout: MPPI_TEST_SPLIT_MULTI_GPU=1)
+#   3. the bench line
+# Round 1 ran an earlier form of this script as its last GPU call (profiles/r01_ab_split_cost.txt).
 set -u
 export PYTHONUNBUFFERED=1
 mkdir -p gpurun_out
-V=$PWD/pytorch_mppi_b200/csrc/_variants/libmppi_b200_minblocks1.so
-( time timeout 150 python scripts/ab_split.py ) > gpurun_out/ab_split.txt 2>&1
-if [ -f "$V" ]; then ( MPPI_B200_LIB=$V timeout 60 python scripts/ab_split.py 16384 30 ) > gpurun_out/ab_minblocks1.txt 2>&1; fi
-( time MPPI_B200_SPLIT_COST=1 timeout 420 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_split1.txt 2>&1
-( timeout 150 python bench.py --steps 3000 --warmup 20 ) > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-( MPPI_B200_SPLIT_COST=1 timeout 100 python bench.py --steps 3000 --warmup 20 --no-cpu-baseline ) > gpurun_out/bench_split.json 2> gpurun_out/bench_split.err
-echo "== ab_split"; cat gpurun_out/ab_split.txt | tail -12
-echo "== ab_minblocks1"; cat gpurun_out/ab_minblocks1.txt 2>/dev/null | tail -4
-echo "== pytest"; tail -5 gpurun_out/pytest_gpu_split1.txt
-echo "== bench"; cut -c1-300 gpurun_out/bench_default.json; cut -c1-300 gpurun_out/bench_split.json
+( time timeout 200 python scripts/ab_split.py ) > gpurun_out/ab_split.txt 2>&1
+( time MPPI_TEST_WIDE_REGS=1 MPPI_TEST_SPLIT_MULTI_GPU=1 timeout 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.txt 2>&1
+( timeout 200 python bench.py --steps 3000 --warmup 20 ) > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "== ab_split"; tail -20 gpurun_out/ab_split.txt
+echo "== pytest"; tail -5 gpurun_out/pytest_gpu.txt
+echo "== bench"; cut -c1-400 gpurun_out/bench.json
