@@ -46,9 +46,10 @@ def b2b(c, n):
 for kind in ("kmppi", "mppi", "smppi"):
     for split in (0, 1):
         c = make(kind, split)
-        li = c.launch_info
+        t_us = b2b(c, 500)
+        li = c.launch_info   # set when the first command packs the launch parameters
         print(f"{kind:5s} fused split={li.split_cost} grid={li.grid_blocks} block={li.block_threads} tps={li.threads_per_sample} "
-              f"regs={li.regs_per_thread} smem={li.smem_bytes}: {b2b(c, 500):.2f} us/command back to back", flush=True)
+              f"regs={li.regs_per_thread} smem={li.smem_bytes}: {t_us:.2f} us/command back to back", flush=True)
     c = make(kind, 0, stepped=True)
     print(f"{kind:5s} stepped (Python T-loop + kernels): {b2b(c, 20):.1f} us/command", flush=True)
     c.compile()
