@@ -300,6 +300,22 @@ def run_engine(args, wl):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
     e2e_value = K_global * T * n_e2e / e2e_s
+    # ---- the same host loop served by a resident grid (opt-in: --resident; single GPU) -----------------
+    e2e_res = None
+    if args.resident and world == 1:
+        ctrl.start_resident(idle_us=2000)
+        for _ in range(50):
+            ctrl.command_host(x_host)
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            a_res = ctrl.command_host(x_host)
+        ctrl.stop_resident()               # inside the timed region: the grid is gone when the clock stops
+        torch.cuda.synchronize()
+        res_s = time.perf_counter() - t0
+        e2e_res = {"value": K_global * T * n_e2e / res_s, "unit": "rollout-steps/s", "ms_per_step": res_s / n_e2e * 1e3,
+                   "steps": n_e2e, "h2d_bytes_per_step": 8 * (3 + NX), "d2h_bytes_per_step": NU * 8 + 8,
+                   "api": "MPPI.start_resident(); MPPI.command_host(state)", "kernel_launches": ctrl.resident_launches,
+                   "last_action": [float(v) for v in a_res.reshape(-1)]}
     clocks = stop_clock_sampler(sampler, sfile, local_rank, t_begin, t_end) if rank == 0 else None
     ranks_agree = True
     if world > 1:      # every rank must hold the bit-identical nominal sequence (no broadcast is ever issued)
@@ -339,6 +355,8 @@ def run_engine(args, wl):
             "gpu_launches": args.steps,
             "clocks": clocks,
         }
+        if e2e_res is not None:
+            line["e2e_resident"] = e2e_res
         # ---- CPU baseline on this host's cores, bounded sample ------------------------------------
         if world == 1 and not args.no_cpu_baseline:
             pick_cpu_threads(K_gpu, T)
@@ -374,6 +392,8 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident", action="store_true",
+                    help="also time the host loop on a resident grid (csrc/mppi_resident.cuh) and report it as e2e_resident")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

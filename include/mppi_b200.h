@@ -215,6 +215,37 @@ int mppi_plan_command(void* plan, const double* state, const void* state_dev, ui
 int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset,
                            const void* z, void* action_out_dev, void* host_mailbox, void* action_host_out, void* stream);
 
+/* ---- Resident mode: command() without a kernel launch ---------------------------------------------
+ * For a host control loop (mppi.py:240-252 called once per control step).  One cooperative launch leaves the
+ * command's grid on the SMs; each following command is a record (flags, Philox counter, start state) written into
+ * pinned host memory that the grid polls, and the action comes back the way mppi_plan_command_host returns it.
+ * The grid prepares the next command's noise and perturbed actions while the host turns around, and leaves by
+ * itself after `idle_us` without a command (the next command relaunches it), so a device-wide synchronise is
+ * never blocked for longer than that.  Results are bit-identical to mppi_plan_command_host with the same
+ * (state, flags, seed, offset).  Available for single-GPU plans that run the split-cost rollout (one tile per SM;
+ * MPPI_FLAG_SPLIT_COST honoured — MppiLaunchInfo.split_cost) of the analytic registry models; others: MPPI_ERR_UNSUPPORTED.
+ *
+ *   host_box      pinned host memory, zero-initialised, 64 + u_per_command*nu (x2 for f64) 8-byte words:
+ *                 [0,32) command record | [32] sequence number of the last finished command | [33] exit word |
+ *                 [64,..) action words (payload32 | seq32 << 32)
+ *   board_dev     device memory, 128 8-byte words (the record re-published for all CTAs + the done word)
+ *   action_out_dev device (u_per_command,nu) of the controller dtype (the action as on the launch route)
+ *   stream        a NON-BLOCKING stream used for nothing else: work on other streams is not ordered against the
+ *                 resident grid; call mppi_resident_sync before reading U / cost_total / stats, mppi_resident_stop
+ *                 before writing U or launching mppi_plan_command on the same controller.
+ * While resident, the controller's parameters are frozen (they are kernel arguments of the resident launch). */
+int mppi_resident_start(void* plan, void* host_box, void* board_dev, void* action_out_dev, uint64_t idle_us, void* stream);
+/* One command(): `state` = nx host doubles; flags: MPPI_FLAG_SHIFT is read; returns the action in action_host_out
+ * (u_per_command*nu elements of the controller dtype). */
+int mppi_resident_command(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset,
+                          void* action_host_out);
+/* Wait until everything the last command wrote to device memory (U, cost_total, nominal_used, stats) is complete. */
+int mppi_resident_sync(void* plan);
+/* Send the grid away and wait for it; mppi_plan_destroy does this too. */
+int mppi_resident_stop(void* plan);
+/* Kernel launches made by resident mode so far (the first command, and each wake-up after an idle exit). */
+uint64_t mppi_resident_launches(void* plan);
+
 /* Multi-GPU, library-collective route: after every rank exported its partial and the caller
  * all-gathered them (NCCL), finish the update on each rank: beta=min, rescale, U += sum/eta
  * (mppi.py:254-259, 268-270 across shards).  `partials` is (world, 2+R) doubles on device. */

@@ -649,8 +649,9 @@ __device__ void finish_update(const KArgs<real>& a, const double* numd, const re
 }
 
 // ---- tail: publish the CTA partial; the last CTA combines, exchanges, updates ----------------------
+// Returns true in the CTA that finished the command (the last arrival), false in all the others.
 template <typename real, int VARIANT, int NU>
-__device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real beta_run, real eta_run) {
+__device__ bool publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real beta_run, real eta_run) {
     typedef Ops<real> O;
     const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
     const int R = a.R, TN = a.TN;
@@ -675,7 +676,7 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
     }
     __syncthreads();
     stamp(a.dbg, 6);
-    if (!s_is_last) return;
+    if (!s_is_last) return false;
     stamp(a.dbg, 8);
 
     // The partials were written by other SMs before their ticket increments; this CTA has not
@@ -821,17 +822,18 @@ __device__ void publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
             a.stats[1] = sm.numd[1];
             a.stats[3] = 0.0;
         }
-        return;
+        return true;
     }
     if (a.world > 1) {
         double* scratch = reinterpret_cast<double*>(sm.rows);   // the tile is free now
         if (exchange_partials<real>(a, sm.numd, scratch, (double)nfl)) {
             if (tid == 0) a.stats[3] = -6.0;   // MPPI_ERR_TIMEOUT
-            return;
+            return true;
         }
     }
     finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);
     if (tid == 0) a.stats[3] = 0.0;
+    return true;
 }
 
 // ---- per-environment view of the kernel arguments (batched launches) -------------------------------
@@ -867,6 +869,86 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
         if (in.in_eps) out->in_eps = in.in_eps + e * K * R;
     }
     __syncthreads();
+}
+
+// ---- stage C', split-cost rollout as a function: recurrence on the rollout thread | running costs on all tps
+// threads of the sample | ordered sum.  Returns the sample's total cost on its rollout thread (+inf elsewhere) and
+// stores it to cost_total[k].  Contains two CTA barriers: every thread must call it.
+// This is the SAME code as the `if constexpr (SPLIT)` block of fused_command_kernel, kept as a second copy on purpose:
+// calling the function from that kernel changes ptxas' register allocation of the default kernel at BASELINE
+// config 2 (checked with cuobjdump), and that kernel's SASS is the one every GPU measurement of round 1 was taken
+// on.  The resident kernel (mppi_resident.cuh) uses this copy; tests/test_gpu_resident.py checks both against each
+// other bit for bit.
+template <class Model, typename real, int VARIANT>
+__device__ __forceinline__ real split_cost_rollout(const KArgs<real>& a, const typename Model::template P<real>& mp, Smem<real>& sm,
+                                                   int k, unsigned long long kg, bool in_range, bool active) {
+    typedef Ops<real> O;
+    constexpr int NX = Model::NX, NU = Model::NU;
+    const NoiseModel<real>& nm = a.nm;
+    const int tid = threadIdx.x, BS = blockDim.x / a.tps, T = a.T;
+    real c_tot = O::inf();
+    real* xcol = sm.xs + (tid % BS);
+    real x[NX];
+    real pert = (real)0, smooth = (real)0;
+    if (active) {
+        if (a.state_dev != nullptr) {
+            const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = sp[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = a.x0[i];
+        }
+        real vprev[NU];
+#pragma unroll
+        for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
+MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
+        for (int t = 0; t < T; ++t) {
+            real v[NU], u[NU], eps[NU];
+            action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+            noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+#pragma unroll
+            for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
+            Model::template step<real>(mp, x, u);                                     // mppi.py:314
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xcol[(t * NX + i) * BS] = x[i];
+            pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
+            if (VARIANT == V_SMPPI) {
+                if (t > 0) {
+#pragma unroll
+                    for (int n = 0; n < NU; ++n) {
+                        const real d = O::mul(nm.u_scale, O::sub(v[n], vprev[n]));    // mppi.py:559
+                        smooth = O::add(smooth, O::mul(d, d));
+                    }
+                }
+#pragma unroll
+                for (int n = 0; n < NU; ++n) vprev[n] = v[n];
+            }
+        }
+    }
+    __syncthreads();
+    if (in_range) {
+MPPI_UNROLL_N(2)
+        for (int t = tid / BS; t < T; t += a.tps) {      // independent across t: two in flight per thread
+            real v[NU], u[NU], xt[NX];
+            action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+#pragma unroll
+            for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xt[i] = xcol[(t * NX + i) * BS];
+            xcol[(t * NX) * BS] = Model::template cost<real>(mp, xt, u);              // mppi.py:318
+        }
+    }
+    __syncthreads();
+    if (active) {
+        real roll = (real)0;
+        for (int t = 0; t < T; ++t) roll = O::add(roll, xcol[(t * NX) * BS]);         // mppi.py:319, t = 0..T-1
+        if (Model::template has_terminal<real>(mp)) roll = O::add(roll, Model::template terminal<real>(mp, x));
+        c_tot = O::add(roll, pert);                                                   // mppi.py:416
+        if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569
+        a.cost_total[k] = c_tot;
+    }
+    return c_tot;
 }
 
 // =================================================================================================

@@ -221,6 +221,8 @@ class MPPI:
         self._host_box = None
         self._plan = None
         self._last = None
+        self._resident = False          # a resident grid is armed for command_host (start_resident)
+        self._resident_wanted = 0       # idle_us to re-enter resident mode with, after something made the grid leave
 
         # device state
         self._alloc_nominal(U_init)
@@ -304,6 +306,7 @@ class MPPI:
 
     @property
     def U(self):
+        self._resident_sync()
         return self._Ubuf[: self.T * self.nu].view(self.T, self.nu)
 
     @U.setter
@@ -311,7 +314,18 @@ class MPPI:
         value = torch.as_tensor(value).to(self.d, self.dtype).reshape(-1, self.nu)
         if value.shape[0] != self.T:
             raise ValueError(f"U must have T={self.T} rows, got {value.shape[0]}")
+        self._leave_resident()
         self._Ubuf[: self.T * self.nu].copy_(value.reshape(-1))
+
+    @property
+    def cost_total(self):
+        """(K) total cost per sample of the last command (mppi.py:180, 416)"""
+        self._resident_sync()
+        return self._cost_total
+
+    @cost_total.setter
+    def cost_total(self, value):
+        self._cost_total = value
 
     def _sample_noise(self, shape):
         """N(noise_mu, noise_sigma) draws for U initialisation / reset (mppi.py:201-206).  Off the hot
@@ -451,6 +465,8 @@ class MPPI:
     def _drop_plan(self):
         plan = getattr(self, "_plan", None)
         if plan is not None:
+            if getattr(self, "_resident", False):        # mppi_plan_destroy sends the resident grid away
+                self._resident, self._resident_wanted = False, self._resident_idle_us
             self._lib.mppi_plan_destroy(plan)
             self._plan = None
 
@@ -533,6 +549,87 @@ class MPPI:
     @property
     def z_used(self):
         return None if self._z_out is None else self._z_out.view(self._K_local, -1, self.nu)
+
+    # ------------------------------------------------------------------------------------------
+    # resident mode: command_host() without a kernel launch (csrc/mppi_resident.cuh)
+    # ------------------------------------------------------------------------------------------
+    def start_resident(self, idle_us=1000):
+        """Keep the command's grid on the GPU between `command_host()` calls: each command becomes a record in
+        pinned host memory that the grid polls, and the action comes back the same way — no kernel launch on the
+        control loop's critical path, and the next command's noise / perturbed actions are prepared while the host
+        turns around.  Results are bit-identical to the launch route.  The grid leaves by itself after `idle_us`
+        microseconds without a command (the next command relaunches it), so `torch.cuda.synchronize()` never waits
+        longer than that.  While resident: reading `U` / `cost_total` / `omega` / ... waits for the last command
+        to finish; anything that writes controller state or launches (`command()`, setting `U`, `reset()`, parameter
+        setters) makes the grid leave first and the next `command_host()` brings it back.  Write through the
+        setters, not through views obtained earlier.
+        Requires a registered analytic model on the split-cost rollout (a problem of at most one tile per SM, e.g.
+        BASELINE config 2), one GPU, host states."""
+        if self._dirty:
+            self._pack()
+        if self._model is None or self._plan is None:
+            raise _cabi.MppiLibraryError("resident mode needs a registered model (the fused route)")
+        if self._z_out is not None:
+            raise _cabi.MppiLibraryError("resident mode does not record noise; call record_noise(False) first")
+        words = 64 + self.u_per_command * self.nu * (2 if self.dtype == torch.float64 else 1)
+        if getattr(self, "_res_box", None) is None or self._res_box.numel() != words:
+            self._res_box = torch.zeros(words, dtype=torch.int64).pin_memory()
+            self._res_board = torch.zeros(128, dtype=torch.int64, device=self.d)
+            self._res_stream = torch.cuda.Stream(device=self.d)       # non-blocking, used for nothing else
+        torch.cuda.synchronize(self.d)     # whatever wrote U / parameters on other streams is complete
+        _cabi.check(self._lib.mppi_resident_start(self._plan, self._res_box.data_ptr(), self._res_board.data_ptr(),
+                                                  self._scratch_action.data_ptr(), int(idle_us), self._res_stream.cuda_stream),
+                    "mppi_resident_start")
+        self._resident, self._resident_wanted, self._resident_idle_us = True, 0, int(idle_us)
+
+    def stop_resident(self):
+        """Send the resident grid away and stay on the launch route."""
+        if self._resident and self._plan is not None:
+            _cabi.check(self._lib.mppi_resident_stop(self._plan), "mppi_resident_stop")
+        self._resident, self._resident_wanted = False, 0
+
+    def resident(self, idle_us=1000):
+        """`with ctrl.resident(): ... ctrl.command_host(x) ...`"""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            self.start_resident(idle_us)
+            try:
+                yield self
+            finally:
+                self.stop_resident()
+        return cm()
+
+    @property
+    def resident_launches(self):
+        """Kernel launches resident mode has made on the current plan (first command + wake-ups after idle exits)."""
+        return 0 if self._plan is None else int(self._lib.mppi_resident_launches(self._plan))
+
+    def _resident_sync(self):
+        """Reads of device-side results: wait until the resident grid finished writing the last command's."""
+        if getattr(self, "_resident", False):
+            _cabi.check(self._lib.mppi_resident_sync(self._plan), "mppi_resident_sync")
+
+    def _leave_resident(self):
+        """Writes to controller state / launch-route commands: the grid leaves now, the next command_host() re-enters."""
+        if getattr(self, "_resident", False):
+            _cabi.check(self._lib.mppi_resident_stop(self._plan), "mppi_resident_stop")
+            self._resident, self._resident_wanted = False, self._resident_idle_us
+
+    def _command_resident(self, shift):
+        flags = self._base_flags | (_cabi.FLAG_SHIFT if shift else 0)
+        _, seed, off = self._noise_source()
+        self._last = (flags, seed, off, None, None)
+        self._cmd_count += 1
+        rc = self._lib.mppi_resident_command(self._plan, self._state_arr, flags, seed, off, self._host_res_ptr)
+        if rc != 0:
+            _cabi.check(rc, "mppi_resident_command")
+        self._cost_total = self._cost_buf
+        self._states = None
+        self._actions = None
+        out = self._host_res.clone()
+        return out[0] if self.u_per_command == 1 else out
 
     # ------------------------------------------------------------------------------------------
     # public API (mppi.py:208-290)
@@ -646,6 +743,7 @@ class MPPI:
         self._resize_horizon(horizon, U)
 
     def _resize_horizon(self, horizon, U):
+        self._leave_resident()              # the buffers the resident grid reads are about to be replaced
         self.T = int(horizon)
         self._alloc_nominal(U)
         self._alloc_results()
@@ -654,6 +752,7 @@ class MPPI:
     def command(self, state, shift_nominal_trajectory=True, info=None):
         """mppi.py:240-252: returns the first `u_per_command` actions of the updated sequence."""
         self.info = info
+        self._leave_resident()
         if self._dirty:
             self._pack()
         if self._model is not None:
@@ -793,6 +892,12 @@ class MPPI:
         sflags, sdev = self._host_state(state)
         if sdev is not None:
             return self.command(state, shift_nominal_trajectory, info).cpu()
+        if self._resident or self._resident_wanted:
+            if self._z_inject is None and getattr(self, "_offset_dev", None) is None:
+                if not self._resident:
+                    self.start_resident(self._resident_wanted)
+                return self._command_resident(shift_nominal_trajectory)
+            self._leave_resident()         # injected noise / device-resident counter: a launch-route command
         flags = self._base_flags | (_cabi.FLAG_SHIFT if shift_nominal_trajectory else 0)
         zptr, seed, off = self._noise_source()
         stream = torch._C._cuda_getCurrentRawStream(self.d.index)
@@ -1099,11 +1204,13 @@ class SMPPI(MPPI):
 
     @property
     def action_sequence(self):
+        self._resident_sync()
         return self._Abuf[: self.T * self.nu].view(self.T, self.nu)
 
     @action_sequence.setter
     def action_sequence(self, value):
         value = torch.as_tensor(value).to(self.d, self.dtype).reshape(-1, self.nu)
+        self._leave_resident()
         self._Abuf[: self.T * self.nu].copy_(value.reshape(-1))
 
     def _variant_pack(self, p):
@@ -1131,6 +1238,7 @@ class SMPPI(MPPI):
 
     def reset(self):
         """mppi.py:498-500"""
+        self._leave_resident()
         self._Ubuf.zero_()
         self._Abuf.zero_()
 
@@ -1138,6 +1246,7 @@ class SMPPI(MPPI):
         """mppi.py:502-512"""
         U = self.U.clone()
         A = self.action_sequence.clone()
+        self._leave_resident()
         if horizon < U.shape[0]:
             U, A = U[:horizon], A[:horizon]
         elif horizon > U.shape[0]:
@@ -1202,10 +1311,12 @@ class KMPPI(MPPI):
 
     @property
     def theta(self):
+        self._resident_sync()
         return self._theta
 
     @theta.setter
     def theta(self, v):
+        self._leave_resident()
         self._theta.copy_(torch.as_tensor(v).to(self.d, self.dtype).reshape(self.num_support_pts, self.nu))
 
     def _noise_rows(self):
@@ -1248,11 +1359,13 @@ class KMPPI(MPPI):
     def reset(self):
         """mppi.py:613-615"""
         super().reset()
+        self._leave_resident()
         self._theta.zero_()
 
     def shift_nominal_trajectory(self):
         """mppi.py:617-619"""
         super().shift_nominal_trajectory()
+        self._leave_resident()
         self._theta.copy_(self._Wshift @ self._theta)
 
     def _ensure_step_buffers(self):

@@ -53,6 +53,12 @@ def test_bad_arguments_return_status_not_crash(lib):
     assert lib.mppi_omega(None, None, None, 1.0, 1, 0, None) == -1
     assert lib.mppi_softmin_update(C.byref(p), None, None, None) == -1
     assert lib.mppi_xchg_open(None, None) == -1
+    # resident mode: a null plan / unarmed plan is an argument error, never a launch
+    assert lib.mppi_resident_start(None, None, None, None, 1000, None) == -1
+    assert lib.mppi_resident_command(None, None, 0, 0, 0, None) == -1
+    assert lib.mppi_resident_sync(None) == -1
+    assert lib.mppi_resident_stop(None) == -1
+    assert lib.mppi_resident_launches(None) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
