@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SRC = os.path.join(CSRC, "mppi_b200.cu")
 OUT = os.path.join(CSRC, "libmppi_b200.so")
-HEADERS = [os.path.join(CSRC, h) for h in ("mppi_fused.cuh", "mppi_math.cuh", "mppi_mlp_tc.cuh", "mppi_resident.cuh")]
+HEADERS = [os.path.join(CSRC, h) for h in ("mppi_fused.cuh", "mppi_math.cuh", "mppi_mlp_tc.cuh", "mppi_resident.cuh", "mppi_resident_host.h")]
 DEPS = [SRC, *HEADERS, os.path.join(os.path.dirname(HERE), "include", "mppi_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
@@ -65,7 +65,7 @@ def build_user_model(header_text: str, verbose: bool = False) -> str:
     """JIT-build a variant of the library with a user model compiled in (the built-in models are
     compiled out to keep the build short).  Cached by the hash of the header text under csrc/_user/."""
     import hashlib
-    tag = hashlib.sha1((header_text + "".join(open(h).read() for h in (HEADERS[0], HEADERS[1], HEADERS[3])) + open(SRC).read()).encode()).hexdigest()[:16]
+    tag = hashlib.sha1((header_text + "".join(open(h).read() for h in (HEADERS[0], HEADERS[1], HEADERS[3], HEADERS[4])) + open(SRC).read()).encode()).hexdigest()[:16]
     udir = os.path.join(CSRC, "_user")
     os.makedirs(udir, exist_ok=True)
     hdr = os.path.join(udir, f"user_model_{tag}.cuh")

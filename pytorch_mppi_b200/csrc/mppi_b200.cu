@@ -11,7 +11,7 @@
 #include "mppi_fused.cuh"
 #include "mppi_mlp_tc.cuh"
 #include "mppi_resident.cuh"
-#include <chrono>
+#include "mppi_resident_host.h"
 
 using namespace mppi;
 
@@ -486,21 +486,14 @@ template <class Model> int run_fused_dtype(const MppiFusedParams* p, cudaStream_
 }
 
 // ---- plans ---------------------------------------------------------------------------------------
-// Resident mode (mppi_resident.cuh): host-side state of one controller's resident kernel.
-// host_box (pinned host memory, u64 words): [0,32) command record | [32] seq of the last finished command |
-// [33] exit word (launch generation << 32 | reason) | [64, ...) action words.
-struct Resident {
-    int armed = 0, launched = 0;
-    unsigned int gen = 0;
-    unsigned long long seq = 0;        // last sequence number handed out (commands and stop records)
-    unsigned long long cmd_seq = 0;    // sequence number of the last COMMAND (what host_box[32] converges to)
-    unsigned long long seed = 0;
-    unsigned long long idle_ns = 0;
+// Resident mode: the host side of the protocol (struct Resident, res_*) is csrc/mppi_resident_host.h; this file supplies its
+// backend (cooperative launch / stream synchronise / stream query).
+struct ResidentDevice {
     unsigned long long* host_box = nullptr;
     unsigned long long* board = nullptr;
     void* action_dev = nullptr;
     cudaStream_t stream = nullptr;
-    unsigned long long launches = 0;   // kernel launches so far (the first command and every wake-up after an idle exit)
+    unsigned long long idle_ns = 0;
 };
 
 struct Plan {
@@ -508,6 +501,7 @@ struct Plan {
     const void* kernel;
     const void* res_kernel;            // resident_command_kernel<Model, real, V>, or nullptr when this plan cannot run resident
     Resident res;
+    ResidentDevice resdev;
     Geometry g;
     int is_double, nx, upc_nu, pdl;
     unsigned long long epoch, host_epoch;
@@ -596,32 +590,27 @@ inline int plan_launch(Plan* pl, cudaStream_t stream) {
     return MPPI_OK;
 }
 
-// ---- resident mode: host side ----------------------------------------------------------------------
-inline void cpu_relax() {
-#if defined(__x86_64__)
-    __builtin_ia32_pause();
-#endif
-}
-
-template <typename real> int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_pred) {
-    Resident& r = pl->res;
+// ---- resident mode: the device backend of csrc/mppi_resident_host.h ---------------------------------
+template <typename real>
+int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_pred, uint64_t seq_start, uint32_t gen) {
+    ResidentDevice& d = pl->resdev;
     KArgs<real> a = *reinterpret_cast<KArgs<real>*>(pl->kargs);
     a.seed = seed;
     a.z = nullptr;
     a.z_out = nullptr;
     a.state_dev = nullptr;
-    a.action_out = (real*)r.action_dev;
-    a.host_mailbox = r.host_box + 64;
+    a.action_out = (real*)d.action_dev;
+    a.host_mailbox = d.host_box + RES_BOX_ACTION;
     a.pdl = 0;
     ResidentArgs ra;
     memset(&ra, 0, sizeof(ra));
-    ra.host_cmd = r.host_box;
-    ra.host_status = r.host_box + 32;
-    ra.board = r.board;
-    ra.seq_start = r.seq;
+    ra.host_cmd = d.host_box + RES_BOX_RECORD;
+    ra.host_status = d.host_box + RES_BOX_DONE;
+    ra.board = d.board;
+    ra.seq_start = seq_start;
     ra.offset_pred = offset_pred;
-    ra.idle_ns = r.idle_ns;
-    ra.gen = ++r.gen;
+    ra.idle_ns = d.idle_ns;
+    ra.gen = gen;
     ra.shift_pred = shift_pred;
     ra.n_words = 3 + pl->nx * (pl->is_double ? 2 : 1);
     DevInfo di;
@@ -632,38 +621,31 @@ template <typename real> int resident_launch_t(Plan* pl, uint64_t seed, uint64_t
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
     if (pl->g.smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
     CK(cudaFuncSetAttribute(pl->res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
-    CK(cudaMemsetAsync(r.board, 0, MPPI_RES_BOARD_WORDS * sizeof(unsigned long long), r.stream));
+    CK(cudaMemsetAsync(d.board, 0, MPPI_RES_BOARD_WORDS * sizeof(unsigned long long), d.stream));
     void* argv[3] = {(void*)&a, (void*)pl->mparams, (void*)&ra};
     // cooperative: every CTA is resident or the launch fails — the CTAs wait for each other through the board
-    cudaError_t e = cudaLaunchCooperativeKernel(pl->res_kernel, dim3(pl->g.nb), dim3(pl->g.BD), argv, (size_t)pl->g.smem, r.stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(pl->res_kernel, dim3(pl->g.nb), dim3(pl->g.BD), argv, (size_t)pl->g.smem, d.stream);
     if (e != cudaSuccess) return cuda_fail(e, "resident launch");
-    r.launched = 1;
-    r.seed = seed;
-    ++r.launches;
     return MPPI_OK;
 }
-inline int resident_launch(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_pred) {
-    return pl->is_double ? resident_launch_t<double>(pl, seed, offset_pred, shift_pred)
-                         : resident_launch_t<float>(pl, seed, offset_pred, shift_pred);
+int resident_be_launch(void* ctx, uint64_t seed, uint64_t offset_pred, int shift_pred, uint64_t seq_start, uint32_t gen) {
+    Plan* pl = reinterpret_cast<Plan*>(ctx);
+    return pl->is_double ? resident_launch_t<double>(pl, seed, offset_pred, shift_pred, seq_start, gen)
+                         : resident_launch_t<float>(pl, seed, offset_pred, shift_pred, seq_start, gen);
 }
-
-inline bool resident_exited(const Resident& r) {
-    return (unsigned int)(reinterpret_cast<volatile unsigned long long*>(r.host_box)[33] >> 32) == r.gen;
-}
-
-// a STOP record (it consumes a sequence number), then wait for the grid to leave
-int resident_halt(Plan* pl) {
-    Resident& r = pl->res;
-    if (!r.launched) return MPPI_OK;
-    volatile unsigned long long* box = reinterpret_cast<volatile unsigned long long*>(r.host_box);
-    const unsigned long long seq = ++r.seq, tag = (seq & 0xffffffffull) << 32;
-    const int nw = 3 + pl->nx * (pl->is_double ? 2 : 1);
-    for (int w = nw - 1; w >= 1; --w) box[w] = tag;
-    box[0] = tag | MPPI_RES_CMD_STOP;
-    r.launched = 0;
-    CK(cudaStreamSynchronize(r.stream));
+int resident_be_drain(void* ctx) {
+    Plan* pl = reinterpret_cast<Plan*>(ctx);
+    CK(cudaStreamSynchronize(pl->resdev.stream));
     return MPPI_OK;
 }
+int resident_be_health(void* ctx) {
+    Plan* pl = reinterpret_cast<Plan*>(ctx);
+    cudaError_t q = cudaStreamQuery(pl->resdev.stream);
+    if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery while waiting for the resident grid");
+    return MPPI_OK;
+}
+static_assert(MPPI_RES_CMD_SHIFT == RES_CMD_SHIFT && MPPI_RES_CMD_STOP == RES_CMD_STOP, "record flags: host and device disagree");
+static_assert(RES_ERR_BAD_ARG == MPPI_ERR_BAD_ARG && RES_ERR_TIMEOUT == MPPI_ERR_TIMEOUT, "status codes of the protocol header");
 
 int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
     int rc = validate(p, true);
@@ -958,125 +940,34 @@ int mppi_resident_start(void* plan, void* host_box, void* board_dev, void* actio
     if (pl->res_kernel == nullptr)
         return UNSUPPORTED("resident mode needs a single-GPU plan on the split-cost rollout (one tile per SM, registered analytic model)");
     if (pl->p.z_out != nullptr) return UNSUPPORTED("resident mode does not record the noise it draws (z_out)");
-    if (pl->res.launched) {
-        int rc = resident_halt(pl);
+    if (pl->res.launched) {                 // re-arming: the old grid leaves first (it polls the box that is about to be cleared)
+        int rc = res_halt(pl->res);
         if (rc) return rc;
     }
-    Resident& r = pl->res;
-    r.host_box = reinterpret_cast<unsigned long long*>(host_box);
-    // no grid is polling now: clear the box, so that no word left by an earlier plan (whose sequence numbers and launch
-    // generations also started at 1) can pass for one of this plan's
-    {
-        volatile unsigned long long* box = reinterpret_cast<volatile unsigned long long*>(host_box);
-        const int words = 64 + pl->upc_nu * (pl->is_double ? 2 : 1);
-        for (int w = 0; w < words; ++w) box[w] = 0ull;
-    }
-    r.board = reinterpret_cast<unsigned long long*>(board_dev);
-    r.action_dev = action_out_dev;
-    r.idle_ns = idle_us * 1000ull;
-    r.stream = (cudaStream_t)stream;
-    r.armed = 1;
-    return MPPI_OK;
+    ResidentDevice& d = pl->resdev;
+    d.host_box = reinterpret_cast<unsigned long long*>(host_box);
+    d.board = reinterpret_cast<unsigned long long*>(board_dev);
+    d.action_dev = action_out_dev;
+    d.idle_ns = idle_us * 1000ull;
+    d.stream = (cudaStream_t)stream;
+    const ResidentBackend be{pl, resident_be_launch, resident_be_drain, resident_be_health};
+    return res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be);
 }
 
 int mppi_resident_command(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset, void* action_host_out) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
-    if (pl == nullptr || state == nullptr || action_host_out == nullptr) return MPPI_ERR_BAD_ARG;
-    Resident& r = pl->res;
-    if (!r.armed) return MPPI_ERR_BAD_ARG;
-    const int shift = (flags & MPPI_FLAG_SHIFT) ? 1 : 0;
-    volatile unsigned long long* box = reinterpret_cast<volatile unsigned long long*>(r.host_box);
-    int rc;
-    if (r.launched && resident_exited(r)) r.launched = 0;              // it left on its idle clock
-    if (r.launched && seed != r.seed && (rc = resident_halt(pl)) != MPPI_OK) return rc;   // reseeded generator
-    if (!r.launched && (rc = resident_launch(pl, seed, offset, shift)) != MPPI_OK) return rc;
-    // the record: every word carries the sequence number, so the order of these stores does not matter
-    const unsigned long long seq = r.seq + 1, tag = (seq & 0xffffffffull) << 32;
-    if (pl->is_double) {
-        for (int i = 0; i < pl->nx; ++i) {
-            unsigned long long bits;
-            memcpy(&bits, &state[i], 8);
-            box[3 + 2 * i] = tag | (bits & 0xffffffffull);
-            box[3 + 2 * i + 1] = tag | (bits >> 32);
-        }
-    } else {
-        for (int i = 0; i < pl->nx; ++i) {
-            const float f = (float)state[i];
-            uint32_t bits;
-            memcpy(&bits, &f, 4);
-            box[3 + i] = tag | bits;
-        }
-    }
-    box[1] = tag | (offset & 0xffffffffull);
-    box[2] = tag | (offset >> 32);
-    box[0] = tag | (shift ? MPPI_RES_CMD_SHIFT : 0u);
-    r.seq = seq;
-    r.cmd_seq = seq;
-    // the action: self-validating words, as on the launch route
-    const unsigned long long want = seq & 0xffffffffull;
-    volatile unsigned long long* act = box + 64;
-    const int nwords = pl->upc_nu * (pl->is_double ? 2 : 1);
-    unsigned long long spins = 0;
-    int relaunches = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    for (int w = 0; w < nwords; ++w) {
-        while ((act[w] >> 32) != want) {
-            cpu_relax();
-            if ((++spins & 0x3FFF) != 0) continue;
-            if (resident_exited(r) && (act[w] >> 32) != want) {
-                // the grid left (idle clock) before it saw this record: wake it up; the record is still in the box
-                if (++relaunches > 3) return MPPI_ERR_TIMEOUT;
-                r.seq = seq - 1;
-                rc = resident_launch(pl, seed, offset, shift);
-                r.seq = seq;
-                if (rc) return rc;
-            }
-            if ((spins & 0xFFFFF) == 0) {
-                cudaError_t q = cudaStreamQuery(r.stream);
-                if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery while waiting for the resident kernel");
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return MPPI_ERR_TIMEOUT;
-            }
-        }
-    }
-    if (pl->is_double) {
-        unsigned long long* out = reinterpret_cast<unsigned long long*>(action_host_out);
-        for (int i = 0; i < pl->upc_nu; ++i) out[i] = (act[2 * i] & 0xffffffffull) | (act[2 * i + 1] << 32);
-    } else {
-        uint32_t* out = reinterpret_cast<uint32_t*>(action_host_out);
-        for (int i = 0; i < pl->upc_nu; ++i) out[i] = (uint32_t)act[i];
-    }
-    return MPPI_OK;
+    if (pl == nullptr) return MPPI_ERR_BAD_ARG;
+    return res_command(pl->res, state, (flags & MPPI_FLAG_SHIFT) ? 1 : 0, seed, offset, action_host_out);
 }
 
 int mppi_resident_sync(void* plan) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
-    if (pl == nullptr) return MPPI_ERR_BAD_ARG;
-    Resident& r = pl->res;
-    if (!r.armed || r.cmd_seq == 0) return MPPI_OK;
-    volatile unsigned long long* box = reinterpret_cast<volatile unsigned long long*>(r.host_box);
-    unsigned long long spins = 0;
-    const auto t0 = std::chrono::steady_clock::now();
-    while (box[32] != r.cmd_seq) {
-        cpu_relax();
-        if ((++spins & 0xFFFFF) == 0) {
-            cudaError_t q = cudaStreamQuery(r.stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery in mppi_resident_sync");
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(10)) return MPPI_ERR_TIMEOUT;
-        }
-    }
-    return MPPI_OK;
+    return pl == nullptr ? (int)MPPI_ERR_BAD_ARG : res_sync(pl->res);
 }
 
 int mppi_resident_stop(void* plan) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
-    if (pl == nullptr) return MPPI_ERR_BAD_ARG;
-    int rc = resident_halt(pl);
-    if (pl->res.armed && pl->res.stream != nullptr && rc == MPPI_OK) {
-        cudaError_t e = cudaStreamSynchronize(pl->res.stream);   // also covers a grid that is leaving on its idle clock
-        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize in mppi_resident_stop");
-    }
-    pl->res.armed = 0;
-    return rc;
+    return pl == nullptr ? (int)MPPI_ERR_BAD_ARG : res_stop(pl->res);
 }
 
 uint64_t mppi_resident_launches(void* plan) {

@@ -3,9 +3,9 @@
 The contract is bit-identity with the launch route: the resident kernel runs the same stage functions on the same
 (state, seed, Philox counter, flags), so every action, the nominal sequence and cost_total must be EQUAL, not close.
 
-Opt-in (MPPI_TEST_RESIDENT=1) until the mode has been validated on a B200: a resident kernel is a spin-waiting
-kernel, and an unvalidated one does not belong in the default GPU suite.  Every test carries a timeout; the kernel
-itself leaves after `idle_us` without a command.
+Validated on B200 in round 1 (profiles/r01_pytest_gpu_resident.txt).  A resident kernel is a spin-waiting kernel, so
+every test carries a timeout, the host side gives up after 10 s, and the kernel itself leaves after `idle_us` without a
+command.
 """
 import os
 import time
@@ -15,8 +15,7 @@ import torch
 
 import pytorch_mppi_b200 as eng
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120),
-              pytest.mark.skipif(os.environ.get("MPPI_TEST_RESIDENT") != "1", reason="opt-in: MPPI_TEST_RESIDENT=1")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(120)]
 
 
 def _pendulum(K=2048, T=15, dtype=torch.float32, seed=11):
@@ -45,7 +44,7 @@ def _pend_step(x, u):
 def test_resident_equals_launch_route_pendulum_closed_loop():
     a, b = _pendulum(), _pendulum()
     xa, xb = [3.0, 1.0], [3.0, 1.0]
-    with b.resident(idle_us=20000):
+    with b.resident(idle_us=500000):             # long idle clock: the launch count below must not depend on host jitter
         for i in range(40):
             ua, ub = a.command_host(xa), b.command_host(xb)
             assert torch.equal(ua, ub), (i, ua, ub)
