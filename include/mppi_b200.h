@@ -222,8 +222,11 @@ int mppi_plan_command_host(void* plan, const double* state, uint32_t flags, uint
  * The grid prepares the next command's noise and perturbed actions while the host turns around, and leaves by
  * itself after `idle_us` without a command (the next command relaunches it), so a device-wide synchronise is
  * never blocked for longer than that.  Results are bit-identical to mppi_plan_command_host with the same
- * (state, flags, seed, offset).  Available for single-GPU plans that run the split-cost rollout (one tile per SM;
+ * (state, flags, seed, offset).  Available for plans that run the split-cost rollout (one tile per SM;
  * MPPI_FLAG_SPLIT_COST honoured — MppiLaunchInfo.split_cost) of the analytic registry models; others: MPPI_ERR_UNSUPPORTED.
+ * A plan that is one shard of a multi-GPU controller with the in-kernel exchange (peer_slots set) runs the instantiation
+ * whose records also carry the exchange epoch: every rank's host posts its own record, the finishers exchange over
+ * NVLink inside the resident grids (validated on one GPU in round 1; the sharded instantiation is to be run on two).
  *
  *   host_box      pinned host memory, zero-initialised, 64 + u_per_command*nu (x2 for f64) 8-byte words:
  *                 [0,32) command record | [32] sequence number of the last finished command | [33] exit word |

@@ -499,7 +499,8 @@ struct ResidentDevice {
 struct Plan {
     MppiFusedParams p;
     const void* kernel;
-    const void* res_kernel;            // resident_command_kernel<Model, real, V>, or nullptr when this plan cannot run resident
+    const void* res_kernel;            // resident_command_kernel<Model, real, V, sharded>, or nullptr when this plan cannot run resident
+    int res_xchg;                      // the plan is one shard of a multi-GPU controller: records carry the exchange epoch
     Resident res;
     ResidentDevice resdev;
     Geometry g;
@@ -534,10 +535,14 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     Model::template load<real>(*mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
     pl->kernel = (const void*)kernel;
     pl->res_kernel = nullptr;
+    pl->res_xchg = 0;
     if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {
-        // resident mode runs the split-cost rollout with one tile per CTA on one GPU: exactly the plans that took it
-        if (split && !batched && a->world == 1 && !a->export_partial && pl->g.nb == a->n_tiles)
-            pl->res_kernel = (const void*)resident_command_kernel<Model, real, V>;
+        // resident mode runs the split-cost rollout with one tile per CTA: exactly the plans that took it; a sharded
+        // controller (in-kernel NVLink exchange) gets the instantiation whose records carry the exchange epoch
+        if (split && !batched && !a->export_partial && pl->g.nb == a->n_tiles)
+            pl->res_kernel = a->world > 1 ? (const void*)resident_command_kernel<Model, real, V, true>
+                                          : (const void*)resident_command_kernel<Model, real, V, false>;
+        pl->res_xchg = a->world > 1 ? 1 : 0;
     }
     pl->is_double = sizeof(real) == 8;
     pl->nx = Model::NX;
@@ -612,7 +617,7 @@ int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_p
     ra.idle_ns = d.idle_ns;
     ra.gen = gen;
     ra.shift_pred = shift_pred;
-    ra.n_words = 3 + pl->nx * (pl->is_double ? 2 : 1);
+    ra.n_words = 3 + pl->nx * (pl->is_double ? 2 : 1) + (pl->res_xchg ? 2 : 0);
     DevInfo di;
     int rc = get_dev_info(di);
     if (rc) return rc;
@@ -644,8 +649,8 @@ int resident_be_health(void* ctx) {
     if (q != cudaSuccess && q != cudaErrorNotReady) return cuda_fail(q, "cudaStreamQuery while waiting for the resident grid");
     return MPPI_OK;
 }
-static_assert(MPPI_RES_CMD_SHIFT == RES_CMD_SHIFT && MPPI_RES_CMD_STOP == RES_CMD_STOP, "record flags: host and device disagree");
-static_assert(RES_ERR_BAD_ARG == MPPI_ERR_BAD_ARG && RES_ERR_TIMEOUT == MPPI_ERR_TIMEOUT, "status codes of the protocol header");
+static_assert(MPPI_RES_CMD_SHIFT == (unsigned)RES_CMD_SHIFT && MPPI_RES_CMD_STOP == (unsigned)RES_CMD_STOP, "record flags: host and device disagree");
+static_assert((int)RES_ERR_BAD_ARG == (int)MPPI_ERR_BAD_ARG && (int)RES_ERR_TIMEOUT == (int)MPPI_ERR_TIMEOUT, "status codes of the protocol header");
 
 int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
     int rc = validate(p, true);
@@ -938,7 +943,7 @@ int mppi_resident_start(void* plan, void* host_box, void* board_dev, void* actio
     if (pl == nullptr || host_box == nullptr || board_dev == nullptr || action_out_dev == nullptr || idle_us == 0)
         return MPPI_ERR_BAD_ARG;
     if (pl->res_kernel == nullptr)
-        return UNSUPPORTED("resident mode needs a single-GPU plan on the split-cost rollout (one tile per SM, registered analytic model)");
+        return UNSUPPORTED("resident mode needs a plan on the split-cost rollout (one tile per SM, registered analytic model, in-kernel exchange if sharded)");
     if (pl->p.z_out != nullptr) return UNSUPPORTED("resident mode does not record the noise it draws (z_out)");
     if (pl->res.launched) {                 // re-arming: the old grid leaves first (it polls the box that is about to be cleared)
         int rc = res_halt(pl->res);
@@ -951,13 +956,15 @@ int mppi_resident_start(void* plan, void* host_box, void* board_dev, void* actio
     d.idle_ns = idle_us * 1000ull;
     d.stream = (cudaStream_t)stream;
     const ResidentBackend be{pl, resident_be_launch, resident_be_drain, resident_be_health};
-    return res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be);
+    return res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be, pl->res_xchg);
 }
 
 int mppi_resident_command(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset, void* action_host_out) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
     if (pl == nullptr) return MPPI_ERR_BAD_ARG;
-    return res_command(pl->res, state, (flags & MPPI_FLAG_SHIFT) ? 1 : 0, seed, offset, action_host_out);
+    // a sharded controller advances its exchange epoch once per command, on whichever route the command takes
+    const uint64_t epoch = pl->res_xchg ? ++pl->epoch : 0;
+    return res_command(pl->res, state, (flags & MPPI_FLAG_SHIFT) ? 1 : 0, seed, offset, action_host_out, epoch);
 }
 
 int mppi_resident_sync(void* plan) {

@@ -25,7 +25,12 @@
 // Safety: the kernel cannot outlive its usefulness.  CTA 0 exits after `idle_ns` without a record (it tells the
 // board, so every CTA leaves, and writes an exit word the host sees: the next command simply relaunches); every
 // other spin loop carries the same clock check with a margin.  Launched cooperatively, so all CTAs are resident or
-// the launch fails.  Single GPU, one tile per CTA (the small-problem geometry the split-cost rollout serves).
+// the launch fails.  One tile per CTA (the small-problem geometry the split-cost rollout serves).
+//
+// XCHG = true is the instantiation for controllers sharded over the GPUs of one box (in-kernel NVLink exchange,
+// exchange_partials in the shared tail): every rank's host posts its own record, which then also carries the exchange
+// epoch (two more words after the state).  XCHG = false compiles to the single-GPU kernel validated in round 1
+// (byte-identical SASS, checked with cuobjdump); the sharded instantiation is opt-in until it has run on two GPUs.
 //
 // Reference lines replaced: the same as fused_command_kernel (mppi.py:232-275, 297-417 and the SMPPI / KMPPI forms).
 #pragma once
@@ -34,7 +39,7 @@
 
 namespace mppi {
 
-#define MPPI_RES_MAX_WORDS 32             // command record: 3 + nx (f32) or 3 + 2 nx (f64) words
+#define MPPI_RES_MAX_WORDS 32             // command record: 3 + nx (f32) or 3 + 2 nx (f64) words (+ 2: exchange epoch, XCHG)
 #define MPPI_RES_BOARD_DONE 64            // board[64] = seq of the last finished command
 #define MPPI_RES_BOARD_WORDS 128
 #define MPPI_RES_CMD_SHIFT 1u
@@ -92,14 +97,14 @@ __device__ __forceinline__ void resident_prepare(const KArgs<real>& a, Smem<real
 // __launch_bounds__(640, 1): CTAs have at most 512 threads; promising 640 makes ptxas stop at 96 registers
 // (65,536 / 640), so a resident 512-thread CTA leaves a quarter of its SM's register file to the kernels other
 // streams launch meanwhile (torch ops reading U or cost_total) instead of taking all of it at 128.
-template <class Model, typename real, int VARIANT>
+template <class Model, typename real, int VARIANT, bool XCHG = false>
 __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                                   const __grid_constant__ typename Model::template P<real> mp,
                                                                   const __grid_constant__ ResidentArgs ra) {
     typedef Ops<real> O;
     constexpr int NX = Model::NX, NU = Model::NU;
     constexpr int WPV = sizeof(real) / 4;             // record words per state value
-    static_assert(3 + 2 * MPPI_MAX_NX <= MPPI_RES_MAX_WORDS, "command record does not fit one warp");
+    static_assert(5 + 2 * MPPI_MAX_NX <= MPPI_RES_MAX_WORDS, "command record does not fit one warp");
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(16) unsigned char a_raw[sizeof(KArgs<real>)];
     __shared__ unsigned int s_cmd[MPPI_RES_MAX_WORDS];
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             a.dbg = nullptr;
             a.offset_dev = nullptr;
             a.state_dev = nullptr;
-            a.world = 1;
+            if (!XCHG) a.world = 1;
             a.export_partial = 0;
             a.offset = ra.offset_pred;
             a.shift = ra.shift_pred;
@@ -202,6 +207,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             a.host_epoch = seq + 1;
             uint32_t* x0w = reinterpret_cast<uint32_t*>(a.x0);
             for (int i = 0; i < NX * WPV; ++i) x0w[i] = s_cmd[3 + i];
+            if (XCHG) a.epoch = (unsigned long long)s_cmd[3 + NX * WPV] | ((unsigned long long)s_cmd[4 + NX * WPV] << 32);
         }
         __syncthreads();
         if (offset != offset_pred || shift != shift_pred) resident_prepare<real, VARIANT, NU>(a, sm, in_range, kg, nvalid);

@@ -6,7 +6,8 @@
 //
 // host_box (pinned host memory, 8-byte words):
 //   [0, 32)   the command record: word w = payload32 | seq32 << 32;  w0 = flags (bit 0 shift, bit 1 stop),
-//             w1 / w2 = Philox counter lo / hi, w3.. = the start state (f32: one word per value, f64: lo, hi)
+//             w1 / w2 = Philox counter lo / hi, w3.. = the start state (f32: one word per value, f64: lo, hi),
+//             then, for controllers sharded over several GPUs, the exchange epoch lo / hi
 //   [32]      sequence number of the last command whose device-side results are complete
 //   [33]      exit word: launch generation << 32 | reason (1 idle clock, 2 stop record, 3 lost the finisher)
 //   [64, ..)  the action: payload32 | seq32 << 32 per word (f64: lo, hi)
@@ -43,6 +44,7 @@ struct Resident {
     uint64_t launches = 0;     // grids launched so far: the first command and every wake-up after an idle exit
     volatile uint64_t* box = nullptr;
     int nx = 0, n_action = 0, is_double = 0;
+    int xchg = 0;              // sharded controller: the record also carries the exchange epoch
     int timeout_s = 10;
     ResidentBackend be{};
 };
@@ -53,7 +55,7 @@ inline void res_cpu_relax() {
 #endif
 }
 
-inline int res_record_words(const Resident& r) { return 3 + r.nx * (r.is_double ? 2 : 1); }
+inline int res_record_words(const Resident& r) { return 3 + r.nx * (r.is_double ? 2 : 1) + (r.xchg ? 2 : 0); }
 inline int res_box_words(int n_action, int is_double) { return RES_BOX_ACTION + n_action * (is_double ? 2 : 1); }
 
 inline bool res_exited(const Resident& r) { return (uint32_t)(r.box[RES_BOX_EXIT] >> 32) == r.gen; }
@@ -77,8 +79,8 @@ inline int res_halt(Resident& r) {
     return r.be.drain(r.be.ctx);
 }
 
-inline int res_arm(Resident& r, void* host_box, int nx, int n_action, int is_double, const ResidentBackend& be) {
-    if (host_box == nullptr || nx < 1 || n_action < 1 || 3 + nx * (is_double ? 2 : 1) > 32) return RES_ERR_BAD_ARG;
+inline int res_arm(Resident& r, void* host_box, int nx, int n_action, int is_double, const ResidentBackend& be, int xchg = 0) {
+    if (host_box == nullptr || nx < 1 || n_action < 1 || 3 + nx * (is_double ? 2 : 1) + (xchg ? 2 : 0) > 32) return RES_ERR_BAD_ARG;
     if (r.launched) {
         const int rc = res_halt(r);
         if (rc) return rc;
@@ -87,6 +89,7 @@ inline int res_arm(Resident& r, void* host_box, int nx, int n_action, int is_dou
     r.nx = nx;
     r.n_action = n_action;
     r.is_double = is_double;
+    r.xchg = xchg ? 1 : 0;
     r.be = be;
     // no grid is polling now: clear the box, so that no word left by an earlier controller (whose sequence numbers and
     // launch generations also started at 1) can pass for one of this controller's
@@ -96,7 +99,8 @@ inline int res_arm(Resident& r, void* host_box, int nx, int n_action, int is_dou
 }
 
 // One command: post the record, wait for the action words, copy the action out (controller dtype).
-inline int res_command(Resident& r, const double* state, int shift, uint64_t seed, uint64_t offset, void* action_out) {
+inline int res_command(Resident& r, const double* state, int shift, uint64_t seed, uint64_t offset, void* action_out,
+                       uint64_t epoch = 0) {
     if (!r.armed || state == nullptr || action_out == nullptr) return RES_ERR_BAD_ARG;
     int rc;
     if (r.launched && res_exited(r)) r.launched = 0;                             // it left on its idle clock
@@ -118,6 +122,11 @@ inline int res_command(Resident& r, const double* state, int shift, uint64_t see
             memcpy(&bits, &f, 4);
             box[3 + i] = tag | bits;
         }
+    }
+    if (r.xchg) {
+        const int e0 = 3 + r.nx * (r.is_double ? 2 : 1);
+        box[e0] = tag | (epoch & 0xffffffffull);
+        box[e0 + 1] = tag | (epoch >> 32);
     }
     box[1] = tag | (offset & 0xffffffffull);
     box[2] = tag | (offset >> 32);

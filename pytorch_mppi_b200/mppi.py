@@ -459,8 +459,9 @@ class MPPI:
         self._plan = plan
         self._state_arr = (C.c_double * _cabi.MPPI_MAX_NX)()
         self._scratch_action = torch.empty((self.u_per_command, self.nu), device=self.d, dtype=self.dtype)
-        self._host_res = torch.empty((self.u_per_command, self.nu), dtype=self.dtype)
-        self._host_res_ptr = self._host_res.data_ptr()
+        # command_host() hands every action back in a fresh CPU tensor the C side writes into directly
+        # ((nu,) or (u_per_command, nu), mppi.py:273-274): `torch.empty` + `data_ptr` costs 1.6 us, a clone + index 4.1
+        self._host_out_shape = (self.nu,) if self.u_per_command == 1 else (self.u_per_command, self.nu)
 
     def _drop_plan(self):
         plan = getattr(self, "_plan", None)
@@ -564,7 +565,8 @@ class MPPI:
         setters) makes the grid leave first and the next `command_host()` brings it back.  Write through the
         setters, not through views obtained earlier.
         Requires a registered analytic model on the split-cost rollout (a problem of at most one tile per SM, e.g.
-        BASELINE config 2), one GPU, host states."""
+        BASELINE config 2) and host states.  Sharded controllers (process_group=..., exchange="p2p") need the split-cost
+        rollout on the shards (MPPI_B200_SPLIT_COST=2) — both opt-in until they have run on two GPUs."""
         if self._dirty:
             self._pack()
         if self._model is None or self._plan is None:
@@ -622,14 +624,16 @@ class MPPI:
         _, seed, off = self._noise_source()
         self._last = (flags, seed, off, None, None)
         self._cmd_count += 1
-        rc = self._lib.mppi_resident_command(self._plan, self._state_arr, flags, seed, off, self._host_res_ptr)
+        out = torch.empty(self._host_out_shape, dtype=self.dtype)
+        rc = self._lib.mppi_resident_command(self._plan, self._state_arr, flags, seed, off, out.data_ptr())
         if rc != 0:
             _cabi.check(rc, "mppi_resident_command")
+        if self._world > 1:
+            self._epoch += 1           # mirrors the plan's exchange epoch, as on the launch route
         self._cost_total = self._cost_buf
         self._states = None
         self._actions = None
-        out = self._host_res.clone()
-        return out[0] if self.u_per_command == 1 else out
+        return out
 
     # ------------------------------------------------------------------------------------------
     # public API (mppi.py:208-290)
@@ -903,17 +907,17 @@ class MPPI:
         stream = torch._C._cuda_getCurrentRawStream(self.d.index)
         self._last = (flags, seed, off, zptr, None)
         self._cmd_count += 1
+        out = torch.empty(self._host_out_shape, dtype=self.dtype)
         rc = self._lib.mppi_plan_command_host(self._plan, self._state_arr, flags, seed, off, zptr,
-                                              self._scratch_action.data_ptr(), self._host_box.data_ptr(), self._host_res_ptr, stream)
+                                              self._scratch_action.data_ptr(), self._host_box.data_ptr(), out.data_ptr(), stream)
         if rc != 0:
             _cabi.check(rc, "mppi_plan_command_host")
         if self._world > 1:
             self._epoch += 1
-        self.cost_total = self._cost_buf
+        self._cost_total = self._cost_buf
         self._states = None
         self._actions = None
-        out = self._host_res.clone()
-        return out[0] if self.u_per_command == 1 else out
+        return out
 
     # ------------------------------------------------------------------------------------------
     # stepped route (arbitrary callables): mppi.py:297-373 with kernels around the T-loop

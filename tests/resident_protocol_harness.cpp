@@ -25,13 +25,13 @@ struct Taken {
     uint64_t seq, offset;
     int shift;
     double state[8];
-    uint64_t seed;
+    uint64_t seed, epoch;
     uint32_t gen;
 };
 
 struct Sim {
     volatile uint64_t* box = nullptr;
-    int nx = 2, n_action = 1, is_double = 0;
+    int nx = 2, n_action = 1, is_double = 0, xchg = 0;
     uint64_t idle_ns = 50000000ull;
     int compute_us_max = 0;          // emulated command duration: uniform in [0, compute_us_max]
     int done_lag_us = 0;             // extra time between the action words and the done word
@@ -56,7 +56,8 @@ static double expected_action(const double* st, int nx, uint64_t seed, uint64_t 
 
 static void grid_main(Sim* sim, uint64_t seed, uint64_t offset_pred, int shift_pred, uint64_t seq, uint32_t gen) {
     volatile uint64_t* box = sim->box;
-    const int nw = 3 + sim->nx * (sim->is_double ? 2 : 1);
+    const int nxw = sim->nx * (sim->is_double ? 2 : 1);
+    const int nw = 3 + nxw + (sim->xchg ? 2 : 0);
     std::mt19937 rng(gen * 7919u + 13u);
     uint64_t t_idle0 = now_ns();
     int reason = 0;
@@ -92,6 +93,7 @@ static void grid_main(Sim* sim, uint64_t seed, uint64_t offset_pred, int shift_p
                 t.state[i] = f;
             }
         }
+        if (sim->xchg) t.epoch = (uint64_t)payload[3 + nxw] | ((uint64_t)payload[4 + nxw] << 32);
         if (t.offset != offset_pred || t.shift != shift_pred) ++sim->redo;
         sim->log.push_back(t);
         if (sim->compute_us_max > 0) spin_us((int)(rng() % (unsigned)(sim->compute_us_max + 1)));
@@ -265,7 +267,28 @@ int main() {
         CHECK(res_stop(r2) == 0, "stop 2");
         printf("4 ok: stop/re-arm, fresh controller on a used box, reseed\n");
     }
-    // 5. argument errors
+    // 5. sharded controller: the record carries the exchange epoch (f64, nx = 8: the longest record, 21 words)
+    {
+        Sim sim;
+        sim.box = boxmem;
+        sim.nx = 8;
+        sim.is_double = 1;
+        sim.xchg = 1;
+        be.ctx = &sim;
+        Resident r;
+        CHECK(res_arm(r, boxmem, 8, 1, 1, be, 1) == 0, "arm");
+        double st[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+        double out[1];
+        for (int c = 0; c < 50; ++c) {
+            const uint64_t epoch = (1ull << 33) + 17 + c;
+            CHECK(res_command(r, st, 1, 5, 8ull * c, out, epoch) == 0, "command");
+            CHECK(sim.log.back().epoch == epoch, "epoch %llu != %llu", (unsigned long long)sim.log.back().epoch, (unsigned long long)epoch);
+            CHECK(out[0] == expected_action(st, 8, 5, 8ull * c, 1, 0, 1), "action");
+        }
+        CHECK(res_stop(r) == 0, "stop");
+        printf("5 ok: exchange epoch in the record\n");
+    }
+    // 6. argument errors
     {
         Resident r;
         unsigned char out[16];
@@ -274,7 +297,7 @@ int main() {
         CHECK(res_arm(r, nullptr, 2, 1, 0, be) == RES_ERR_BAD_ARG, "null box");
         CHECK(res_arm(r, boxmem, 20, 1, 1, be) == RES_ERR_BAD_ARG, "record too long");
         CHECK(res_sync(r) == 0 && res_stop(r) == 0, "sync/stop on an unarmed controller are no-ops");
-        printf("5 ok: argument errors\n");
+        printf("6 ok: argument errors\n");
     }
     printf("ALL OK\n");
     return 0;

@@ -79,6 +79,29 @@ def _worker(rank, world, port, out, split_mode="1"):
             one.command([3.0, 0.5])
             many.command([3.0, 0.5])
         results["philox"] = (float((one.U - many.U).abs().max()), 0.0, True)
+        # Resident mode on sharded controllers (opt-in until it has run on two GPUs; needs the split-cost rollout on the
+        # shards, split_mode "2"): every rank's host loop posts its own record, the finishers exchange over NVLink inside
+        # the resident grid; actions and U must equal the launch route's, on every rank.
+        if split_mode == "2" and os.environ.get("MPPI_TEST_RESIDENT_MULTI_GPU", "0") == "1":
+            def shard():
+                torch.manual_seed(5)
+                return eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=8192, horizon=30, device=dev,
+                                u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), U_init=torch.zeros(30, 1), rng_seed=99,
+                                process_group=dist.group.WORLD)
+            a, b = shard(), shard()
+            x = [3.0, 0.5]
+            worst = 0.0
+            b.start_resident(idle_us=200000)
+            try:
+                for _ in range(10):
+                    ua, ub = a.command_host(x), b.command_host(x)
+                    worst = max(worst, float((ua - ub).abs().max()))
+                Ua, Ub = a.U.clone(), b.U.clone()
+            finally:
+                b.stop_resident()
+            lst = [torch.zeros_like(Ub) for _ in range(world)]
+            dist.all_gather(lst, Ub.contiguous())
+            results["resident"] = (float((Ua - Ub).abs().max()), worst, all(torch.equal(lst[0], t) for t in lst))
         out[rank] = results
     finally:
         dist.destroy_process_group()
