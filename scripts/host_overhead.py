@@ -22,7 +22,7 @@ for K, T in ((32, 2), (1024, 5), (16384, 30)):
     pre = (time.perf_counter() - t0) / n * 1e6
     t0 = time.perf_counter()
     for _ in range(n):
-        torch.empty(c._host_out_shape, dtype=c.dtype).data_ptr()
+        torch.empty_like(c._host_template).data_ptr()
     post = (time.perf_counter() - t0) / n * 1e6
     # device-side: launch + sync round trip without mailbox
     t0 = time.perf_counter()
