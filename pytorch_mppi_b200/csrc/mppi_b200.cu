@@ -543,6 +543,11 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
             pl->res_kernel = a->world > 1 ? (const void*)resident_command_kernel<Model, real, V, true>
                                           : (const void*)resident_command_kernel<Model, real, V, false>;
         pl->res_xchg = a->world > 1 ? 1 : 0;
+        // the one instantiation with %globaltimer stamps (a profiling aid, scripts/resident_timeline.py)
+        if constexpr (std::is_same<Model, PendulumModel>::value && std::is_same<real, float>::value && V == V_MPPI) {
+            if (pl->res_kernel != nullptr && !pl->res_xchg && p->debug_clocks != nullptr)
+                pl->res_kernel = (const void*)resident_command_kernel<Model, real, V, false, true>;
+        }
     }
     pl->is_double = sizeof(real) == 8;
     pl->nx = Model::NX;

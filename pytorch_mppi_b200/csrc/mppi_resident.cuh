@@ -97,7 +97,13 @@ __device__ __forceinline__ void resident_prepare(const KArgs<real>& a, Smem<real
 // __launch_bounds__(640, 1): CTAs have at most 512 threads; promising 640 makes ptxas stop at 96 registers
 // (65,536 / 640), so a resident 512-thread CTA leaves a quarter of its SM's register file to the kernels other
 // streams launch meanwhile (torch ops reading U or cost_total) instead of taking all of it at 128.
-template <class Model, typename real, int VARIANT, bool XCHG = false>
+//
+// STAMPS = true (one debug instantiation: pendulum, fp32, MPPI; chosen when the plan carries debug_clocks): %globaltimer
+// stamps of the last command's phases per CTA, slots of the (grid, 16) debug_clocks array:
+//   14 previous update visible | 0 prepared, polling | 13 (CTA 0) record seen in host memory | 1 record seen by this CTA |
+//   2 decoded | 3 rolled out | 4 folded | 6 ticket taken | 8, 10, 11 finisher: partials acquired, eta, numerators |
+//   12 finisher: action stored, fence done, done word written.   scripts/resident_timeline.py reads them.
+template <class Model, typename real, int VARIANT, bool XCHG = false, bool STAMPS = false>
 __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                                   const __grid_constant__ typename Model::template P<real> mp,
                                                                   const __grid_constant__ ResidentArgs ra) {
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             a.pdl = 0;
             a.z = nullptr;
             a.z_out = nullptr;
-            a.dbg = nullptr;
+            if (!STAMPS) a.dbg = nullptr;
             a.offset_dev = nullptr;
             a.state_dev = nullptr;
             if (!XCHG) a.world = 1;
@@ -166,9 +172,11 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             __syncthreads();
             if (s_stop) { exit_reason = 3; break; }
         }
+        if constexpr (STAMPS) stamp(a.dbg, 14);
 
         // (2) state-independent work, on the predicted counter / shift flag
         resident_prepare<real, VARIANT, NU>(a, sm, in_range, kg, nvalid);
+        if constexpr (STAMPS) stamp(a.dbg, 0);
 
         // (3) the record of command seq + 1
         const unsigned int want = (unsigned int)((seq + 1) & 0xffffffffull);
@@ -190,6 +198,9 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
                 if (timed_out) break;
             }
             if (timed_out) payload = lane == 0 ? MPPI_RES_CMD_STOP : 0u;
+            if constexpr (STAMPS) {
+                if (!timed_out && !(payload & MPPI_RES_CMD_STOP)) stamp(a.dbg, blockIdx.x == 0 ? 13 : 1);   // lane 0 == thread 0
+            }
             if (blockIdx.x == 0 && lane < nw) st_peer(ra.board + lane, ((unsigned long long)want << 32) | payload);
             if (lane < nw) s_cmd[lane] = payload;
             if (lane == 0) s_stop = timed_out ? 1 : ((payload & MPPI_RES_CMD_STOP) ? 2 : 0);
@@ -211,11 +222,14 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
         }
         __syncthreads();
         if (offset != offset_pred || shift != shift_pred) resident_prepare<real, VARIANT, NU>(a, sm, in_range, kg, nvalid);
+        if constexpr (STAMPS) stamp(a.dbg, 2);
 
         // (5) rollout, fold, tail — the launched kernel's stages
         const real c_tot = split_cost_rollout<Model, real, VARIANT>(a, mp, sm, k, kg, in_range, active);
+        if constexpr (STAMPS) stamp(a.dbg, 3);
         real beta_run = O::inf(), eta_run = (real)0, w_unused;
         fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+        if constexpr (STAMPS) stamp(a.dbg, 4);
         const bool finisher = publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
         if (finisher) {
             __syncthreads();           // every store of the update precedes thread 0's fence
@@ -223,6 +237,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
                 __threadfence_system();
                 st_peer(ra.board + MPPI_RES_BOARD_DONE, seq + 1);
                 st_peer(ra.host_status, seq + 1);
+                if constexpr (STAMPS) stamp(a.dbg, 12);
             }
         }
         ++seq;

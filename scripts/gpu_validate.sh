@@ -15,6 +15,7 @@ mkdir -p gpurun_out
 ( time MPPI_TEST_WIDE_REGS=1 MPPI_TEST_SPLIT_MULTI_GPU=1 MPPI_TEST_RESIDENT_MULTI_GPU=1 timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.txt 2>&1
 ( time timeout 200 python scripts/ab_split.py ) > gpurun_out/ab_split.txt 2>&1
 ( timeout 120 python scripts/time_c3.py ) > gpurun_out/time_c3.txt 2>&1
+( timeout 120 python scripts/resident_timeline.py 16384 30 300 ) > gpurun_out/resident_timeline.txt 2>&1
 ( timeout 300 python bench.py --steps 3000 --warmup 20 ) > gpurun_out/bench.json 2> gpurun_out/bench.err
 ( timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 150 --warmup 20 --no-cpu-baseline --no-resident ) > gpurun_out/bench_under_ncu.log 2>&1
@@ -23,5 +24,5 @@ mkdir -p gpurun_out
 echo "== pytest"; tail -5 gpurun_out/pytest_gpu.txt
 echo "== ab_split"; tail -12 gpurun_out/ab_split.txt
 echo "== c3"; cat gpurun_out/time_c3.txt
-echo "== resident"; cat gpurun_out/resident_latency.txt 2>/dev/null
+echo "== resident"; cat gpurun_out/resident_latency.txt 2>/dev/null; cat gpurun_out/resident_timeline.txt
 echo "== bench"; cut -c1-400 gpurun_out/bench.json
