@@ -76,7 +76,7 @@ for K, T, bt, tps in ((16384, 30, 0, 0), (16384, 30, 128, 1), (16384, 30, 128, 2
     try:
         ctrl = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=K, horizon=T,
                         u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=1, block_threads=bt, threads_per_sample=tps)
-        x = [math.pi, 1.0] if False else [3.14159, 1.0]
+        x = [3.14159, 1.0]
         for _ in range(20):
             ctrl.command(x)
         torch.cuda.synchronize()

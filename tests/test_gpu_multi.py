@@ -4,7 +4,6 @@ NVLink peer mailboxes, (b) with an NCCL all-gather + mppi_apply_partials; both m
 unsharded update, identically on every rank."""
 import os
 
-import numpy as np
 import pytest
 import torch
 
@@ -22,7 +21,7 @@ def _worker(rank, world, port, out, split_mode="1"):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         g = torch.Generator().manual_seed(11)
-        K, T = 4096 + 64, 25            # uneven split across ranks on purpose? (4160 / 2 = 2080: even; remainder path below)
+        K, T = 4096 + 64, 25            # 4160 splits evenly over 2 ranks; K + 1 below exercises the remainder path
         results = {}
         for variant in ("mppi", "kmppi", "smppi"):
             for K_ in (K, K + 1):
@@ -61,8 +60,6 @@ def _worker(rank, world, port, out, split_mode="1"):
                     err = float((c.U.cpu() - U_ref).abs().max())
                     aerr = float((a - a_ref).abs().max())
                     # all ranks must hold bit-identical U
-                    gathered = [torch.zeros_like(U_ref) for _ in range(world)]
-                    dist.all_gather(gathered, c.U.contiguous()) if False else None
                     Ucat = c.U.detach().clone().contiguous()
                     lst = [torch.zeros_like(Ucat) for _ in range(world)]
                     dist.all_gather(lst, Ucat)

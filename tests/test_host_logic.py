@@ -1,6 +1,5 @@
 """CPU: host-side logic — model registry resolution, torch model definitions vs the oracle,
 K-sharding arithmetic, cross-rank combination (incl. a world_size-2 gloo run), Philox oracle KATs."""
-import math
 import os
 
 import numpy as np
