@@ -562,7 +562,8 @@ class MPPI:
         control loop's critical path, and the next command's noise / perturbed actions are prepared while the host
         turns around.  Results are bit-identical to the launch route.  The grid leaves by itself after `idle_us`
         microseconds without a command (the next command relaunches it), so `torch.cuda.synchronize()` never waits
-        longer than that.  While resident: reading `U` / `cost_total` / `omega` / ... waits for the last command
+        longer than that — choose `idle_us` above the control period (a 100 Hz loop wants idle_us > 10000), or every
+        command pays a relaunch, which is slower than the launch route.  While resident: reading `U` / `cost_total` / `omega` / ... waits for the last command
         to finish; anything that writes controller state or launches (`command()`, setting `U`, `reset()`, parameter
         setters) makes the grid leave first and the next `command_host()` brings it back.  Write through the
         setters, not through views obtained earlier.
