@@ -16,6 +16,7 @@ mkdir -p gpurun_out
 ( time timeout 200 python scripts/ab_split.py ) > gpurun_out/ab_split.txt 2>&1
 ( timeout 120 python scripts/time_c3.py ) > gpurun_out/time_c3.txt 2>&1
 ( timeout 120 python scripts/resident_timeline.py 16384 30 300 ) > gpurun_out/resident_timeline.txt 2>&1
+for v in mppi smppi kmppi; do ( timeout 60 python scripts/phase_clocks.py 8192 40 0 0 nav $v ) > gpurun_out/phase_c3_$v.txt 2>&1; done
 ( timeout 300 python bench.py --steps 3000 --warmup 20 ) > gpurun_out/bench.json 2> gpurun_out/bench.err
 ( timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 400 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 150 --warmup 20 --no-cpu-baseline --no-resident ) > gpurun_out/bench_under_ncu.log 2>&1
