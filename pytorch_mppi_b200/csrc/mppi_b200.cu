@@ -1,574 +1,48 @@
 // mppi_b200.cu — C-ABI entry points (include/mppi_b200.h) and kernel dispatch.
 // Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC
 // No torch types cross this boundary; the Python side binds it with ctypes.
-#include <cuda_runtime.h>
-#include <new>
-#include <stdio.h>
-#include <string.h>
+//
+// Translation units of the library (built in parallel by pytorch_mppi_b200/build.py):
+//   mppi_b200.cu        this file: the C ABI, the model-independent kernels (sampling, softmin update, cost
+//                       accumulation, omega, apply-partials), plan commands, resident-mode backend, peer mailboxes
+//   mppi_model_tu.cu    compiled once per (registered model, dtype): fused / resident / states kernels of that model
+#include "mppi_host.cuh"
 
-#include "../../include/mppi_b200.h"
-#include <type_traits>
-#include "mppi_fused.cuh"
-#include "mppi_mlp_tc.cuh"
-#include "mppi_resident.cuh"
-#include "mppi_resident_host.h"
+namespace mppi_host {
+thread_local char g_cuda_err[512] = "";
 
-using namespace mppi;
+// one getter per (model, dtype) translation unit; the user-model getters exist only in a variant library built by
+// pytorch_mppi_b200.build.build_user_model (weak: absent from the stock library)
+const ModelOps* model_ops_pendulum_f32();
+const ModelOps* model_ops_pendulum_f64();
+const ModelOps* model_ops_linear_point_f32();
+const ModelOps* model_ops_linear_point_f64();
+const ModelOps* model_ops_pendulum_mlp_f32();
+const ModelOps* model_ops_pendulum_mlp_f64();
+const ModelOps* model_ops_user_f32() __attribute__((weak));
+const ModelOps* model_ops_user_f64() __attribute__((weak));
+}  // namespace mppi_host
 
 namespace {
 
-thread_local char g_cuda_err[512] = "";
-
-int cuda_fail(cudaError_t e, const char* what) {
-    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
-    return MPPI_ERR_CUDA;
-}
-int unsupported_at(const char* why, int line) {
-    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s (mppi_b200.cu:%d)", why, line);
-    return MPPI_ERR_UNSUPPORTED;
-}
-#define UNSUPPORTED(why) unsupported_at(why, __LINE__)
-#define CK(call)                                              \
-    do {                                                      \
-        cudaError_t _e = (call);                              \
-        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
-    } while (0)
-
-struct DevInfo {
-    int sm_count = 0;
-    int max_smem_optin = 0;
-};
-int get_dev_info(DevInfo& d) {
-    static thread_local int cached_dev = -1;
-    static thread_local DevInfo cached;
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (dev != cached_dev) {
-        CK(cudaDeviceGetAttribute(&cached.sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaDeviceGetAttribute(&cached.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        cached_dev = dev;
-    }
-    d = cached;
-    return MPPI_OK;
-}
-
-int validate(const MppiFusedParams* p, bool fused = false) {
-    if (p == nullptr) return MPPI_ERR_BAD_ARG;
-    if (p->struct_size != sizeof(MppiFusedParams)) return MPPI_ERR_ABI;
-    if (p->K <= 0 || p->T <= 0 || p->nu <= 0 || p->nu > MPPI_MAX_NU || p->nx <= 0) return MPPI_ERR_BAD_ARG;
-    if (fused && p->nx > MPPI_MAX_NX) return MPPI_ERR_BAD_ARG;      // state by value; the per-step entry points never touch the state
-    if (p->variant < 0 || p->variant > 2) return MPPI_ERR_BAD_ARG;
-    if (p->dtype != MPPI_F32 && p->dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
-    if (p->variant == MPPI_VARIANT_KMPPI && (p->S <= 0 || p->W == nullptr || p->theta == nullptr)) return MPPI_ERR_BAD_ARG;
-    if (p->variant == MPPI_VARIANT_SMPPI && (p->A == nullptr || p->T < 2)) return MPPI_ERR_BAD_ARG;
-    if ((p->flags & MPPI_FLAG_SHIFT) && p->variant == MPPI_VARIANT_KMPPI && p->Wshift == nullptr) return MPPI_ERR_BAD_ARG;
-    if (p->lambda_ <= 0.0) return MPPI_ERR_BAD_ARG;
-    if (p->world < 0 || p->world > MPPI_MAX_RANKS) return MPPI_ERR_BAD_ARG;
-    if (p->u_per_command < 1 || p->u_per_command > p->T) return MPPI_ERR_BAD_ARG;
-    return MPPI_OK;
-}
-
-inline int rows_of(const MppiFusedParams* p) { return (p->variant == MPPI_VARIANT_KMPPI ? p->S : p->T) * p->nu; }
-
-template <typename real> void fill_noise_model(const MppiFusedParams* p, NoiseModel<real>& nm) {
-    for (int i = 0; i < MPPI_MAX_NU; ++i) {
-        nm.mu[i] = (real)p->noise_mu[i];
-        nm.u_min[i] = (real)p->u_min[i];
-        nm.u_max[i] = (real)p->u_max[i];
-        nm.a_min[i] = (real)p->action_min[i];
-        nm.a_max[i] = (real)p->action_max[i];
-    }
-    for (int i = 0; i < MPPI_MAX_NU * MPPI_MAX_NU; ++i) {
-        nm.L[i] = (real)p->chol[i];
-        nm.Sinv[i] = (real)p->sigma_inv[i];
-    }
-    nm.lambda_ = (real)p->lambda_;
-    nm.neg_inv_lambda = (real)(-(1.0 / p->lambda_));   // mppi.py:256: -factor * (cost - beta), factor = 1/lambda
-    nm.u_scale = (real)p->u_scale;
-    nm.w_smooth = (real)p->w_action_seq_cost;
-    nm.delta_t = (real)p->delta_t;
-    nm.diag = (p->flags & MPPI_FLAG_DIAG_SIGMA) ? 1 : 0;
-    nm.abs_cost = (p->flags & MPPI_FLAG_ABS_COST) ? 1 : 0;
-}
-
-inline uint64_t ws_bytes(int nb, int R, int es) {
-    return 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
-}
-
-template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BS, int nb, int tps = 1) {
-    memset(&a, 0, sizeof(a));
-    fill_noise_model<real>(p, a.nm);
-    for (int i = 0; i < MPPI_MAX_NU; ++i) a.u_init[i] = (real)p->u_init[i];
-    for (int i = 0; i < MPPI_MAX_NX; ++i) a.x0[i] = (real)p->state[i];
-    a.state_dev = (p->flags & MPPI_FLAG_STATE_DEVICE) ? (const real*)p->state_dev : nullptr;
-    a.state_per_sample = (p->flags & MPPI_FLAG_STATE_PER_SAMPLE) ? 1 : 0;
-    a.U = (real*)p->U;
-    a.A = (real*)p->A;
-    a.theta = (real*)p->theta;
-    a.W = (const real*)p->W;
-    a.Wshift = (const real*)p->Wshift;
-    a.cost_total = (real*)p->cost_total;
-    a.action_out = (real*)p->action_out;
-    a.nominal_used = (real*)p->nominal_used;
-    a.stats = (double*)p->stats;
-    a.z = (const real*)p->z;
-    a.z_out = (real*)p->z_out;
-    a.K = p->K;
-    a.T = p->T;
-    a.S = p->S;
-    a.R = rows_of(p);
-    a.TN = p->T * p->nu;
-    a.upc = p->u_per_command;
-    a.n_tiles = (p->K + BS - 1) / BS;
-    a.tps = tps;
-    a.k_offset = p->k_offset;
-    a.seed = p->seed;
-    a.offset = p->offset;
-    a.shift = (p->flags & MPPI_FLAG_SHIFT) ? 1 : 0;
-    a.null_action = (p->flags & MPPI_FLAG_NULL_ACTION) ? 1 : 0;
-    a.pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
-    const int es = (int)sizeof(real);
-    const bool padded = (p->flags & MPPI_FLAG_NOMINAL_PADDED) || ((a.TN * es) % 16 == 0);
-    a.tma_ok = padded && ((uintptr_t)p->U % 16 == 0) && (p->variant != MPPI_VARIANT_SMPPI || (uintptr_t)p->A % 16 == 0);
-    // workspace carve
-    if (p->workspace != nullptr) {
-        unsigned char* w = (unsigned char*)p->workspace;
-        a.ticket = (unsigned int*)w;
-        a.betaP = (real*)(w + 16);
-        a.etaP = (real*)(w + 16 + align_up(nb * es, 16));
-        a.VP = (real*)(w + 16 + 2 * align_up(nb * es, 16));
-    }
-    a.rank = p->rank;
-    a.world = p->world <= 0 ? 1 : p->world;
-    a.epoch = p->epoch;
-    a.export_partial = (p->flags & MPPI_FLAG_EXPORT_PARTIAL) ? 1 : 0;
-    a.partial_out = (double*)p->partial_out;
-    a.torch_total = p->torch_rng_total;
-    a.offset_dev = (unsigned long long*)p->offset_dev;
-    a.offset_inc = p->offset_inc;
-    a.n_env = p->n_env > 1 ? p->n_env : 1;
-    a.env_u_stride = p->env_u_stride;
-    a.env_ws_stride = (long long)p->env_ws_stride;
-    a.dbg = (unsigned long long*)p->debug_clocks;
-    a.host_mailbox = (unsigned long long*)p->host_mailbox;
-    a.host_epoch = p->host_epoch;
-    bool any_peer = false;
-    for (int g = 0; g < MPPI_MAX_RANKS; ++g) {
-        a.peers[g] = (unsigned long long*)p->peer_slots[g];
-        any_peer = any_peer || p->peer_slots[g] != nullptr;
-    }
-    if (!any_peer || a.export_partial) a.world = a.export_partial ? a.world : 1;
-    return MPPI_OK;
-}
-
-inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cudaStream_t stream, void** argv, bool pdl, int ny = 1) {
-    if (!pdl) return cudaLaunchKernel(kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(nb, ny);
-    cfg.blockDim = dim3(BD);
-    cfg.dynamicSmemBytes = (size_t)smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelExC(&cfg, kernel, argv);
-}
-
-template <typename... Args>
-int launch_kernel(void (*kernel)(Args...), int nb, int BD, int smem, cudaStream_t stream, int ny, Args... args) {
-    void* argv[] = {(void*)&args...};
-    cudaError_t e = cudaLaunchKernel((const void*)kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
-    if (e != cudaSuccess) {
-        snprintf(g_cuda_err, sizeof(g_cuda_err), "launch grid=%d block=%d smem=%d: %s (%s)", nb, BD, smem,
-                 cudaGetErrorName(e), cudaGetErrorString(e));
-        return MPPI_ERR_CUDA;
-    }
-    return MPPI_OK;
-}
-
-struct Geometry {
-    int BD, BS, tps, nb, smem, occ, regs;   // BD = BS * tps threads per CTA, BS samples per tile
-};
-
-struct GeomKey {
-    const void* kernel;
-    int dev, variant, K, T, nu, S, bt, tp, gb, r2, single, ne;
-    bool operator==(const GeomKey& o) const {
-        return kernel == o.kernel && dev == o.dev && variant == o.variant && K == o.K && T == o.T && nu == o.nu && S == o.S &&
-               bt == o.bt && tp == o.tp && gb == o.gb && r2 == o.r2 && single == o.single && ne == o.ne;
-    }
-};
-
-// Launch geometry for (kernel, dimensions).  The occupancy / attribute queries cost microseconds, so
-// the last few results are cached per thread: a steady-state command() pays only the lookup.
-static thread_local int g_tc_kernel = 0;   // set around plan_geometry() for the tcgen05 kernels (see below)
-template <typename KernelT>
-int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_rows2, bool single_partial_grid, Geometry& g,
-                  SmemLayout (*layout)(int, int, int, int, int, int, int, int, int)) {
-    static thread_local GeomKey keys[8];
-    static thread_local Geometry vals[8];
-    static thread_local int n_cached = 0, next_slot = 0;
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    const GeomKey key{(const void*)kernel, dev, p->variant, p->K, p->T, p->nu, p->S, p->block_threads, p->threads_per_sample,
-                      p->grid_blocks, need_rows2, single_partial_grid ? 1 : 0, p->n_env > 1 ? p->n_env : 1};
-    for (int i = 0; i < n_cached; ++i)
-        if (keys[i] == key) {
-            g = vals[i];
-            return MPPI_OK;
-        }
-    DevInfo di;
-    int rc = get_dev_info(di);
-    if (rc) return rc;
-    const int R = rows_of(p);
-    // BS samples per tile; tps threads share one sample's sampling/transform work.
-    //
-    // Automatic geometry (block_threads == 0): blocks are statically assigned tiles (determinism:
-    // the reduction order must not depend on scheduling), so the finish time follows the most
-    // loaded SM.  Enumerate BS in steps of a warp and j = resident CTAs per SM, size the grid as
-    // min(n_tiles, SMs*j), and keep the candidate with the smallest worst-case samples per SM
-    // (ties: fewer passes, then more threads).  Measured on B200 (scripts/geom_sweep.py) this picks
-    // the winners of an exhaustive sweep within ~3 %: e.g. K=131072 -> BS=448, 293 CTAs, one pass.
-    int BS = p->block_threads;
-    int tps = p->threads_per_sample;
-    int grid_hint = 0;
-    if (BS <= 0) {
-        cudaFuncAttributes fa0;
-        CK(cudaFuncGetAttributes(&fa0, kernel));
-        const int dyn0 = di.max_smem_optin - (int)fa0.sharedSizeBytes;
-        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn0));
-        long long best_load = -1;
-        int best_bs = 128, best_passes = 0, best_grid = 0;
-        // latency hiding needs ~24 resident warps per SM when the problem is large enough to supply them
-        const long long per_sm = ((long long)p->K + di.sm_count - 1) / di.sm_count;
-        const long long want_threads = per_sm < 768 ? per_sm : 768;
-        for (int bs = 128; bs <= 512; bs += 32) {
-            SmemLayout Lc = layout(p->variant, p->T, p->nu, p->S, R, bs, bs, single_partial_grid ? 1 : di.sm_count * 4, need_rows2);
-            if (Lc.total > dyn0) continue;
-            int occ_c = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, kernel, bs, Lc.total));
-            if (occ_c < 1) continue;
-            const int nt = (p->K + bs - 1) / bs;
-            for (int j = 1; j <= occ_c && j <= 8; ++j) {
-                const int nbc = nt < di.sm_count * j ? nt : di.sm_count * j;
-                const int passes = (nt + nbc - 1) / nbc;
-                const int bps = (nbc + di.sm_count - 1) / di.sm_count;
-                long long load = (long long)bps * passes * bs;
-                const long long resident = (long long)bps * bs;
-                if (resident < want_threads) load = load * want_threads / resident;   // under-occupied: proportionally slower
-                const bool better = best_load < 0 || load < best_load ||
-                                    (load == best_load && (passes < best_passes || (passes == best_passes && bs > best_bs)));
-                if (better) {
-                    best_load = load;
-                    best_bs = bs;
-                    best_passes = passes;
-                    best_grid = nbc;
-                }
+// the (model, dtype) unit that serves these parameters, or nullptr
+const ModelOps* find_ops(const MppiFusedParams* p, int* rc) {
+    *rc = MPPI_ERR_UNSUPPORTED;
+    const bool f32 = p->dtype == MPPI_F32;
+    switch (p->model) {
+        case MPPI_MODEL_PENDULUM: return f32 ? model_ops_pendulum_f32() : model_ops_pendulum_f64();
+        case MPPI_MODEL_LINEAR_POINT: return f32 ? model_ops_linear_point_f32() : model_ops_linear_point_f64();
+        case MPPI_MODEL_PENDULUM_MLP:
+            if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) {
+                *rc = MPPI_ERR_BAD_ARG;
+                return nullptr;
             }
-        }
-        BS = best_bs;
-        grid_hint = best_grid;
+            return f32 ? model_ops_pendulum_mlp_f32() : model_ops_pendulum_mlp_f64();
+        case MPPI_MODEL_USER:
+            if (f32) return model_ops_user_f32 != nullptr ? model_ops_user_f32() : nullptr;
+            return model_ops_user_f64 != nullptr ? model_ops_user_f64() : nullptr;
     }
-    if (BS % 32 != 0 || BS < 32 || BS > 512) return MPPI_ERR_BAD_ARG;
-    const int n_tiles = (p->K + BS - 1) / BS;
-    if (tps <= 0) {
-        // helper threads only pay off while an SM hosts a single small CTA
-        tps = 1;
-        const int envs = p->n_env > 1 ? p->n_env : 1;
-        if ((long long)n_tiles * envs <= di.sm_count) tps = 512 / BS >= 4 ? 4 : (512 / BS >= 2 ? 2 : 1);
-    }
-    while (tps > 1 && BS * tps > 512) tps >>= 1;
-    if (tps != 1 && tps != 2 && tps != 4) return MPPI_ERR_BAD_ARG;
-    const int BD = BS * tps;
-    const int cap = di.sm_count * 16;
-    cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, kernel));
-    const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;   // static + dynamic <= opt-in maximum
-    // The attribute is a per-kernel LIMIT (setting a smaller value later lowers it), so raise it
-    // once to the device maximum; the carve-out actually used follows each launch's request.
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
-    // The layout depends on the grid (rescale factors of nb partials live in shared memory) and the
-    // grid on the occupancy the layout allows: iterate from an optimistic guess to a fixed point.
-    int nb = n_tiles < cap ? n_tiles : cap;
-    int occ = 0;
-    SmemLayout L;
-    for (int it = 0; it < 4; ++it) {
-        L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : nb, need_rows2);
-        if (L.total > dyn_limit) return UNSUPPORTED("shared-memory tile does not fit");
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BD, L.total));
-        if (occ < 1) return UNSUPPORTED("kernel does not fit on an SM with this block size");
-        if (g_tc_kernel) {
-            // The occupancy API answers 1 CTA/SM for kernels that allocate tensor memory; measured on B200 the
-            // 128-thread tcgen05 CTAs do co-reside (K=131072, T=30: 585 us at 1 CTA/SM, 379 at 2, 311 at 3), so
-            // size the grid from the real limits: shared memory, registers, and 64 of 512 TMEM columns per CTA.
-            int smem_sm = 0;
-            CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-            const int by_smem = smem_sm / ((int)fa.sharedSizeBytes + L.total + 1024);
-            const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * BD);
-            int o = by_smem < by_regs ? by_smem : by_regs;
-            if (o > 512 / 64) o = 512 / 64;
-            const char* e = getenv("MPPI_TC_OCC");
-            if (e != nullptr && atoi(e) > 0) o = atoi(e);
-            if (o > occ) occ = o;
-        }
-        int nb2 = n_tiles < di.sm_count * occ ? n_tiles : di.sm_count * occ;
-        if (nb2 > cap) nb2 = cap;
-        if (p->grid_blocks > 0 && p->grid_blocks < nb2) nb2 = p->grid_blocks;
-        if (grid_hint > 0 && grid_hint < nb2) nb2 = grid_hint;
-        if (nb2 == nb) break;
-        nb = nb2;
-    }
-    L = layout(p->variant, p->T, p->nu, p->S, R, BD, BS, single_partial_grid ? 1 : nb, need_rows2);
-    g.BS = BS;
-    g.tps = tps;
-    g.BD = BD;
-    g.nb = nb;
-    g.smem = L.total;
-    g.occ = occ;
-    g.regs = fa.numRegs;
-    (void)es;
-    keys[next_slot] = key;
-    vals[next_slot] = g;
-    next_slot = (next_slot + 1) % 8;
-    if (n_cached < 8) ++n_cached;
-    return MPPI_OK;
-}
-
-template <typename real> SmemLayout layout_fn(int v, int T, int nu, int S, int R, int BD, int BS, int nb, int r2) {
-    return make_layout<real>(v, T, nu, S, R, BD, BS, nb, r2);
-}
-
-// ---- fused command ----------------------------------------------------------------------------
-// PENDULUM_MLP in fp32 with model_params[3] != 0: the tcgen05/TMEM kernel (mppi_mlp_tc.cuh).  One CTA = 128
-// threads = 128 samples = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
-template <class Model, typename real, int V, typename KernelT>
-bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, KernelT& kernel) {
-    if constexpr (std::is_same<Model, PendulumMLPModel>::value && std::is_same<real, float>::value) {
-        const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
-        if ((mode == 1 || mode == 2) && p->n_env <= 1) {
-            p_tc = *p;
-            // 128-thread CTAs, tiles of 128 samples (every thread rolls one).  The kernel also supports tiles of 64
-            // samples + 64 helper threads (MPPI_TC_TILE=64; twice the CTAs to spread over the SMs), but a CTA's step
-            // time is set by the three MMA round trips, not by its tanh work: measured K=32768, T=30: 132 us with
-            // half tiles against 113 us with full ones, so full tiles are the default at every K.
-            int bs = 128;
-            const char* e_bs = getenv("MPPI_TC_TILE");
-            if (e_bs != nullptr && (atoi(e_bs) == 64 || atoi(e_bs) == 128)) bs = atoi(e_bs);
-            p_tc.block_threads = bs;
-            p_tc.threads_per_sample = 128 / bs;
-            p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
-            const bool fast = p->model_params[2] != 0.0;
-            kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
-                               : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
-            g_tc_kernel = 1;
-            // co-residency is bounded by shared memory: ask for the largest carve-out
-            cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            return true;
-        }
-    }
-    (void)p_tc;
-    (void)kernel;
-    return false;
-}
-
-// MPPI_FLAG_SPLIT_COST: problems small enough to run with helper threads (threads_per_sample > 1) may take the
-// split-cost rollout (fused_command_kernel<..., SPLIT = true>) if its per-step state buffer fits in shared memory;
-// the geometry stays the one chosen for the plain kernel.
-template <class Model, typename real, int V, typename KernelT>
-void select_split_cost_rollout(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& split) {
-    split = 0;
-    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
-        if (!eligible || !(p->flags & MPPI_FLAG_SPLIT_COST) || g.tps <= 1) return;
-        KernelT k2 = fused_command_kernel<Model, real, V, false, true>;
-        MppiFusedParams p2 = *p;
-        p2.block_threads = g.BS;
-        p2.threads_per_sample = g.tps;
-        p2.grid_blocks = g.nb;
-        Geometry g2;
-        if (plan_geometry(k2, &p2, (int)sizeof(real), Model::NX << 8, false, g2, layout_fn<real>) != MPPI_OK) return;
-        if (g2.BS != g.BS || g2.tps != g.tps) return;
-        kernel = k2;
-        g = g2;
-        split = 1;
-    }
-}
-
-// MPPI_FLAG_WIDE_REGS: a launch that puts at most one CTA on an SM can afford the instantiation compiled without the
-// 64-register cap (fused_command_kernel<..., SPLIT = false, MINB = 1>: no spills in the last-CTA tail).
-template <class Model, typename real, int V, typename KernelT>
-void select_wide_register_kernel(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& wide) {
-    wide = 0;
-    if (!eligible || !(p->flags & MPPI_FLAG_WIDE_REGS)) return;
-    DevInfo di;
-    if (get_dev_info(di) != MPPI_OK || g.nb > di.sm_count) return;
-    KernelT k2 = fused_command_kernel<Model, real, V, false, false, 1>;
-    MppiFusedParams p2 = *p;
-    p2.block_threads = g.BS;
-    p2.threads_per_sample = g.tps;
-    p2.grid_blocks = g.nb;
-    Geometry g2;
-    if (plan_geometry(k2, &p2, (int)sizeof(real), 0, false, g2, layout_fn<real>) != MPPI_OK) return;
-    if (g2.BS != g.BS || g2.tps != g.tps || g2.nb != g.nb) return;
-    kernel = k2;
-    g = g2;
-    wide = 1;
-}
-
-template <class Model, typename real, int V>
-int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    const bool batched = p->n_env > 1;
-    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
-    if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
-    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
-    MppiFusedParams p_tc;
-    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
-    if (tc_route) p = &p_tc;
-    Geometry g;
-    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
-    g_tc_kernel = 0;
-    if (rc) return rc;
-    int split = 0, wide = 0;
-    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, g, split);
-    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, g, wide);
-    const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
-    KArgs<real> a;
-    fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
-    if (info != nullptr) {
-        DevInfo di;
-        get_dev_info(di);
-        info->block_threads = g.BD;
-        info->threads_per_sample = g.tps;
-        info->grid_blocks = g.nb;
-        info->smem_bytes = g.smem;
-        info->regs_per_thread = g.regs;
-        info->max_blocks_per_sm = g.occ;
-        info->sm_count = di.sm_count;
-        // report the worst case so one allocation serves any later geometry for these dimensions
-        info->workspace_bytes = ws_bytes(di.sm_count * 16, rows_of(p), (int)sizeof(real));
-        info->tma_staging = a.tma_ok;
-        info->split_cost = split;
-        info->wide_regs = wide;
-        return MPPI_OK;
-    }
-    if (p->U == nullptr || p->cost_total == nullptr || p->action_out == nullptr || p->nominal_used == nullptr ||
-        p->stats == nullptr || p->workspace == nullptr)
-        return MPPI_ERR_BAD_ARG;
-    if (p->workspace_bytes < need_ws) return MPPI_ERR_WORKSPACE;
-    if (batched && (p->env_ws_stride < need_ws || p->workspace_bytes < p->env_ws_stride * (uint64_t)p->n_env ||
-                    p->env_u_stride < p->T * p->nu))
-        return MPPI_ERR_WORKSPACE;
-    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
-    if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
-    typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    void* argv2[2] = {(void*)&a, (void*)&mp};
-    cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env);
-    if (e != cudaSuccess) return cuda_fail(e, "fused launch");
-    return MPPI_OK;
-}
-
-template <class Model, typename real>
-int run_fused_variant(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
-    switch (p->variant) {
-        case MPPI_VARIANT_MPPI: return run_fused<Model, real, V_MPPI>(p, s, info);
-        case MPPI_VARIANT_SMPPI: return run_fused<Model, real, V_SMPPI>(p, s, info);
-        case MPPI_VARIANT_KMPPI: return run_fused<Model, real, V_KMPPI>(p, s, info);
-    }
-    return MPPI_ERR_BAD_ARG;
-}
-
-template <class Model> int run_fused_dtype(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
-    return p->dtype == MPPI_F32 ? run_fused_variant<Model, float>(p, s, info) : run_fused_variant<Model, double>(p, s, info);
-}
-
-// ---- plans ---------------------------------------------------------------------------------------
-// Resident mode: the host side of the protocol (struct Resident, res_*) is csrc/mppi_resident_host.h; this file supplies its
-// backend (cooperative launch / stream synchronise / stream query).
-struct ResidentDevice {
-    unsigned long long* host_box = nullptr;
-    unsigned long long* board = nullptr;
-    void* action_dev = nullptr;
-    cudaStream_t stream = nullptr;
-    unsigned long long idle_ns = 0;
-};
-
-struct Plan {
-    MppiFusedParams p;
-    const void* kernel;
-    const void* res_kernel;            // resident_command_kernel<Model, real, V, sharded>, or nullptr when this plan cannot run resident
-    int res_xchg;                      // the plan is one shard of a multi-GPU controller: records carry the exchange epoch
-    Resident res;
-    ResidentDevice resdev;
-    Geometry g;
-    int is_double, nx, upc_nu, pdl;
-    unsigned long long epoch, host_epoch;
-    alignas(16) unsigned char kargs[sizeof(KArgs<double>)];
-    alignas(16) unsigned char mparams[12288];
-};
-
-template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    const bool batched = p->n_env > 1;
-    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
-    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
-    MppiFusedParams p_tc;
-    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
-    if (tc_route) p = &p_tc;
-    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
-    g_tc_kernel = 0;
-    if (rc) return rc;
-    int split = 0, wide = 0;
-    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, pl->g, split);
-    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, pl->g, wide);
-    if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
-        return MPPI_ERR_BAD_ARG;
-    if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
-    static_assert(sizeof(typename Model::template P<real>) <= sizeof(pl->mparams), "model parameter block too large");
-    KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
-    fill_kargs<real>(p, *a, pl->g.BS, pl->g.nb, pl->g.tps);
-    if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
-    typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
-    Model::template load<real>(*mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    pl->kernel = (const void*)kernel;
-    pl->res_kernel = nullptr;
-    pl->res_xchg = 0;
-    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {
-        // resident mode runs the split-cost rollout with one tile per CTA: exactly the plans that took it; a sharded
-        // controller (in-kernel NVLink exchange) gets the instantiation whose records carry the exchange epoch
-        if (split && !batched && !a->export_partial && pl->g.nb == a->n_tiles)
-            pl->res_kernel = a->world > 1 ? (const void*)resident_command_kernel<Model, real, V, true>
-                                          : (const void*)resident_command_kernel<Model, real, V, false>;
-        pl->res_xchg = a->world > 1 ? 1 : 0;
-        // the one instantiation with %globaltimer stamps (a profiling aid, scripts/resident_timeline.py)
-        if constexpr (std::is_same<Model, PendulumModel>::value && std::is_same<real, float>::value && V == V_MPPI) {
-            if (pl->res_kernel != nullptr && !pl->res_xchg && p->debug_clocks != nullptr)
-                pl->res_kernel = (const void*)resident_command_kernel<Model, real, V, false, true>;
-        }
-    }
-    pl->is_double = sizeof(real) == 8;
-    pl->nx = Model::NX;
-    pl->upc_nu = p->u_per_command * p->nu;
-    pl->pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
-    pl->epoch = p->epoch;
-    pl->host_epoch = 0;
-    pl->p = *p;
-    return MPPI_OK;
-}
-
-template <class Model, typename real> int build_plan_variant(const MppiFusedParams* p, Plan* pl) {
-    switch (p->variant) {
-        case MPPI_VARIANT_MPPI: return build_plan<Model, real, V_MPPI>(p, pl);
-        case MPPI_VARIANT_SMPPI: return build_plan<Model, real, V_SMPPI>(p, pl);
-        case MPPI_VARIANT_KMPPI: return build_plan<Model, real, V_KMPPI>(p, pl);
-    }
-    return MPPI_ERR_BAD_ARG;
-}
-template <class Model> int build_plan_dtype(const MppiFusedParams* p, Plan* pl) {
-    return p->dtype == MPPI_F32 ? build_plan_variant<Model, float>(p, pl) : build_plan_variant<Model, double>(p, pl);
+    return nullptr;
 }
 
 template <typename real>
@@ -660,19 +134,8 @@ static_assert((int)RES_ERR_BAD_ARG == (int)MPPI_ERR_BAD_ARG && (int)RES_ERR_TIME
 int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
     int rc = validate(p, true);
     if (rc) return rc;
-    switch (p->model) {
-#ifndef MPPI_ONLY_USER_MODEL
-        case MPPI_MODEL_PENDULUM: return run_fused_dtype<PendulumModel>(p, s, info);
-        case MPPI_MODEL_LINEAR_POINT: return run_fused_dtype<LinearPointModel>(p, s, info);
-        case MPPI_MODEL_PENDULUM_MLP:
-            if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) return MPPI_ERR_BAD_ARG;
-            return run_fused_dtype<PendulumMLPModel>(p, s, info);
-#endif
-#ifdef MPPI_USER_MODEL_HEADER
-        case MPPI_MODEL_USER: return run_fused_dtype<UserModel>(p, s, info);
-#endif
-    }
-    return MPPI_ERR_UNSUPPORTED;
+    const ModelOps* ops = find_ops(p, &rc);
+    return ops != nullptr ? ops->run_fused(p, s, info) : rc;
 }
 
 // ---- generic path: sample / softmin -------------------------------------------------------------
@@ -768,44 +231,6 @@ template <typename real> int run_softmin_any(const MppiFusedParams* p, const voi
     return MPPI_ERR_BAD_ARG;
 }
 
-template <class Model, typename real>
-int run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStream_t stream) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    KArgs<real> a;
-    fill_kargs<real>(p, a, 128, 1);
-    typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp,
-                                                                        (long long)p->T * p->nu);
-    CK(cudaGetLastError());
-    return MPPI_OK;
-}
-
-// get_rollouts (mppi.py:425-448): n start states, each rolled through an action sequence
-template <class Model, typename real>
-int run_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, long long stride, int n, int T,
-                       void* states, cudaStream_t stream) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    KArgs<real> a;
-    memset(&a, 0, sizeof(a));
-    a.nm.u_scale = (real)p->u_scale;
-    a.K = n;
-    a.T = T;
-    a.state_dev = (const real*)start_states;
-    a.state_per_sample = 1;
-    typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    states_kernel<Model, real><<<(n + 127) / 128, 128, 0, stream>>>((const real*)actions, (real*)states, a, mp, stride);
-    CK(cudaGetLastError());
-    return MPPI_OK;
-}
-template <class Model>
-int run_rollout_states_dtype(const MppiFusedParams* p, const void* x0, const void* act, long long stride, int n, int T, void* out,
-                             cudaStream_t s) {
-    return p->dtype == MPPI_F32 ? run_rollout_states<Model, float>(p, x0, act, stride, n, T, out, s)
-                                : run_rollout_states<Model, double>(p, x0, act, stride, n, T, out, s);
-}
-
 template <typename real, int V>
 int run_apply(const MppiFusedParams* p, const void* partials, cudaStream_t stream) {
     KArgs<real> a;
@@ -866,20 +291,8 @@ int mppi_plan_create(const MppiFusedParams* p, void** plan_out) {
     if (rc) return rc;
     Plan* pl = new (std::nothrow) Plan();
     if (pl == nullptr) return MPPI_ERR_BAD_ARG;
-    switch (p->model) {
-#ifndef MPPI_ONLY_USER_MODEL
-        case MPPI_MODEL_PENDULUM: rc = build_plan_dtype<PendulumModel>(p, pl); break;
-        case MPPI_MODEL_LINEAR_POINT: rc = build_plan_dtype<LinearPointModel>(p, pl); break;
-        case MPPI_MODEL_PENDULUM_MLP:
-            rc = (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr)
-                     ? (int)MPPI_ERR_BAD_ARG : build_plan_dtype<PendulumMLPModel>(p, pl);
-            break;
-#endif
-#ifdef MPPI_USER_MODEL_HEADER
-        case MPPI_MODEL_USER: rc = build_plan_dtype<UserModel>(p, pl); break;
-#endif
-        default: rc = MPPI_ERR_UNSUPPORTED;
-    }
+    const ModelOps* ops = find_ops(p, &rc);
+    if (ops != nullptr) rc = ops->build_plan(p, pl);
     if (rc) {
         delete pl;
         return rc;
@@ -1058,22 +471,8 @@ int mppi_materialize(const MppiFusedParams* p, void* perturbed_action, void* noi
              ? run_sample_any<float>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s)
              : run_sample_any<double>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s);
     if (rc || states == nullptr) return rc;
-    switch (p->model) {
-#ifndef MPPI_ONLY_USER_MODEL
-        case MPPI_MODEL_PENDULUM:
-            return p->dtype == MPPI_F32 ? run_states<PendulumModel, float>(p, perturbed_action, states, s)
-                                        : run_states<PendulumModel, double>(p, perturbed_action, states, s);
-        case MPPI_MODEL_LINEAR_POINT:
-            return p->dtype == MPPI_F32 ? run_states<LinearPointModel, float>(p, perturbed_action, states, s)
-                                        : run_states<LinearPointModel, double>(p, perturbed_action, states, s);
-#endif
-#ifdef MPPI_USER_MODEL_HEADER
-        case MPPI_MODEL_USER:
-            return p->dtype == MPPI_F32 ? run_states<UserModel, float>(p, perturbed_action, states, s)
-                                        : run_states<UserModel, double>(p, perturbed_action, states, s);
-#endif
-    }
-    return MPPI_ERR_UNSUPPORTED;
+    const ModelOps* ops = find_ops(p, &rc);
+    return ops != nullptr ? ops->run_states(p, perturbed_action, states, s) : rc;
 }
 
 int mppi_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, int64_t actions_stride,
@@ -1083,22 +482,9 @@ int mppi_rollout_states(const MppiFusedParams* p, const void* start_states, cons
     if (n_rollouts < 1 || T < 1 || actions_stride < 0) return MPPI_ERR_BAD_ARG;
     if (p->dtype != MPPI_F32 && p->dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (p->model) {
-#ifndef MPPI_ONLY_USER_MODEL
-        case MPPI_MODEL_PENDULUM:
-            return run_rollout_states_dtype<PendulumModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
-        case MPPI_MODEL_LINEAR_POINT:
-            return run_rollout_states_dtype<LinearPointModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
-        case MPPI_MODEL_PENDULUM_MLP:
-            if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) return MPPI_ERR_BAD_ARG;
-            return run_rollout_states_dtype<PendulumMLPModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
-#endif
-#ifdef MPPI_USER_MODEL_HEADER
-        case MPPI_MODEL_USER:
-            return run_rollout_states_dtype<UserModel>(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
-#endif
-    }
-    return MPPI_ERR_UNSUPPORTED;
+    int rc = MPPI_ERR_UNSUPPORTED;
+    const ModelOps* ops = find_ops(p, &rc);
+    return ops != nullptr ? ops->rollout_states(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s) : rc;
 }
 
 int mppi_sample_perturb(const MppiFusedParams* p, void* perturbed_action, void* noise, void* noise_theta, void* cost_init,

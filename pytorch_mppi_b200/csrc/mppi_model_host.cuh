@@ -1,0 +1,240 @@
+// mppi_model_host.cuh — the launch / plan templates of one registered model (instantiated by mppi_model_tu.cu).
+#pragma once
+#include "mppi_host.cuh"
+#include "mppi_mlp_tc.cuh"
+
+namespace {
+
+// ---- fused command ----------------------------------------------------------------------------
+// PENDULUM_MLP in fp32 with model_params[3] != 0: the tcgen05/TMEM kernel (mppi_mlp_tc.cuh).  One CTA = 128
+// threads = 128 samples = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
+template <class Model, typename real, int V, typename KernelT>
+bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, KernelT& kernel) {
+    if constexpr (std::is_same<Model, PendulumMLPModel>::value && std::is_same<real, float>::value) {
+        const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
+        if ((mode == 1 || mode == 2) && p->n_env <= 1) {
+            p_tc = *p;
+            // 128-thread CTAs, tiles of 128 samples (every thread rolls one).  The kernel also supports tiles of 64
+            // samples + 64 helper threads (MPPI_TC_TILE=64; twice the CTAs to spread over the SMs), but a CTA's step
+            // time is set by the three MMA round trips, not by its tanh work: measured K=32768, T=30: 132 us with
+            // half tiles against 113 us with full ones, so full tiles are the default at every K.
+            int bs = 128;
+            const char* e_bs = getenv("MPPI_TC_TILE");
+            if (e_bs != nullptr && (atoi(e_bs) == 64 || atoi(e_bs) == 128)) bs = atoi(e_bs);
+            p_tc.block_threads = bs;
+            p_tc.threads_per_sample = 128 / bs;
+            p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
+            const bool fast = p->model_params[2] != 0.0;
+            kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
+                               : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
+            g_tc_kernel = 1;
+            // co-residency is bounded by shared memory: ask for the largest carve-out
+            cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            return true;
+        }
+    }
+    (void)p_tc;
+    (void)kernel;
+    return false;
+}
+
+// MPPI_FLAG_SPLIT_COST: problems small enough to run with helper threads (threads_per_sample > 1) may take the
+// split-cost rollout (fused_command_kernel<..., SPLIT = true>) if its per-step state buffer fits in shared memory;
+// the geometry stays the one chosen for the plain kernel.
+template <class Model, typename real, int V, typename KernelT>
+void select_split_cost_rollout(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& split) {
+    split = 0;
+    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
+        if (!eligible || !(p->flags & MPPI_FLAG_SPLIT_COST) || g.tps <= 1) return;
+        KernelT k2 = fused_command_kernel<Model, real, V, false, true>;
+        MppiFusedParams p2 = *p;
+        p2.block_threads = g.BS;
+        p2.threads_per_sample = g.tps;
+        p2.grid_blocks = g.nb;
+        Geometry g2;
+        if (plan_geometry(k2, &p2, (int)sizeof(real), Model::NX << 8, false, g2, layout_fn<real>) != MPPI_OK) return;
+        if (g2.BS != g.BS || g2.tps != g.tps) return;
+        kernel = k2;
+        g = g2;
+        split = 1;
+    }
+}
+
+// MPPI_FLAG_WIDE_REGS: a launch that puts at most one CTA on an SM can afford the instantiation compiled without the
+// 64-register cap (fused_command_kernel<..., SPLIT = false, MINB = 1>: no spills in the last-CTA tail).
+template <class Model, typename real, int V, typename KernelT>
+void select_wide_register_kernel(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& wide) {
+    wide = 0;
+    if (!eligible || !(p->flags & MPPI_FLAG_WIDE_REGS)) return;
+    DevInfo di;
+    if (get_dev_info(di) != MPPI_OK || g.nb > di.sm_count) return;
+    KernelT k2 = fused_command_kernel<Model, real, V, false, false, 1>;
+    MppiFusedParams p2 = *p;
+    p2.block_threads = g.BS;
+    p2.threads_per_sample = g.tps;
+    p2.grid_blocks = g.nb;
+    Geometry g2;
+    if (plan_geometry(k2, &p2, (int)sizeof(real), 0, false, g2, layout_fn<real>) != MPPI_OK) return;
+    if (g2.BS != g.BS || g2.tps != g.tps || g2.nb != g.nb) return;
+    kernel = k2;
+    g = g2;
+    wide = 1;
+}
+
+template <class Model, typename real, int V>
+int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    const bool batched = p->n_env > 1;
+    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
+    if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
+    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
+    MppiFusedParams p_tc;
+    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
+    if (tc_route) p = &p_tc;
+    Geometry g;
+    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
+    g_tc_kernel = 0;
+    if (rc) return rc;
+    int split = 0, wide = 0;
+    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, g, split);
+    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, g, wide);
+    const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
+    KArgs<real> a;
+    fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
+    if (info != nullptr) {
+        DevInfo di;
+        get_dev_info(di);
+        info->block_threads = g.BD;
+        info->threads_per_sample = g.tps;
+        info->grid_blocks = g.nb;
+        info->smem_bytes = g.smem;
+        info->regs_per_thread = g.regs;
+        info->max_blocks_per_sm = g.occ;
+        info->sm_count = di.sm_count;
+        // report the worst case so one allocation serves any later geometry for these dimensions
+        info->workspace_bytes = ws_bytes(di.sm_count * 16, rows_of(p), (int)sizeof(real));
+        info->tma_staging = a.tma_ok;
+        info->split_cost = split;
+        info->wide_regs = wide;
+        return MPPI_OK;
+    }
+    if (p->U == nullptr || p->cost_total == nullptr || p->action_out == nullptr || p->nominal_used == nullptr ||
+        p->stats == nullptr || p->workspace == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    if (p->workspace_bytes < need_ws) return MPPI_ERR_WORKSPACE;
+    if (batched && (p->env_ws_stride < need_ws || p->workspace_bytes < p->env_ws_stride * (uint64_t)p->n_env ||
+                    p->env_u_stride < p->T * p->nu))
+        return MPPI_ERR_WORKSPACE;
+    if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
+    if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
+    typename Model::template P<real> mp;
+    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    void* argv2[2] = {(void*)&a, (void*)&mp};
+    cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env);
+    if (e != cudaSuccess) return cuda_fail(e, "fused launch");
+    return MPPI_OK;
+}
+
+template <class Model, typename real>
+int run_fused_variant(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
+    switch (p->variant) {
+        case MPPI_VARIANT_MPPI: return run_fused<Model, real, V_MPPI>(p, s, info);
+        case MPPI_VARIANT_SMPPI: return run_fused<Model, real, V_SMPPI>(p, s, info);
+        case MPPI_VARIANT_KMPPI: return run_fused<Model, real, V_KMPPI>(p, s, info);
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+
+
+template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    const bool batched = p->n_env > 1;
+    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
+    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
+    MppiFusedParams p_tc;
+    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
+    if (tc_route) p = &p_tc;
+    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
+    g_tc_kernel = 0;
+    if (rc) return rc;
+    int split = 0, wide = 0;
+    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, pl->g, split);
+    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, pl->g, wide);
+    if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
+        return MPPI_ERR_BAD_ARG;
+    if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
+    static_assert(sizeof(typename Model::template P<real>) <= sizeof(pl->mparams), "model parameter block too large");
+    KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
+    fill_kargs<real>(p, *a, pl->g.BS, pl->g.nb, pl->g.tps);
+    if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
+    typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
+    Model::template load<real>(*mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    pl->kernel = (const void*)kernel;
+    pl->res_kernel = nullptr;
+    pl->res_xchg = 0;
+    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {
+        // resident mode runs the split-cost rollout with one tile per CTA: exactly the plans that took it; a sharded
+        // controller (in-kernel NVLink exchange) gets the instantiation whose records carry the exchange epoch
+        if (split && !batched && !a->export_partial && pl->g.nb == a->n_tiles)
+            pl->res_kernel = a->world > 1 ? (const void*)resident_command_kernel<Model, real, V, true>
+                                          : (const void*)resident_command_kernel<Model, real, V, false>;
+        pl->res_xchg = a->world > 1 ? 1 : 0;
+        // the one instantiation with %globaltimer stamps (a profiling aid, scripts/resident_timeline.py)
+        if constexpr (std::is_same<Model, PendulumModel>::value && std::is_same<real, float>::value && V == V_MPPI) {
+            if (pl->res_kernel != nullptr && !pl->res_xchg && p->debug_clocks != nullptr)
+                pl->res_kernel = (const void*)resident_command_kernel<Model, real, V, false, true>;
+        }
+    }
+    pl->is_double = sizeof(real) == 8;
+    pl->nx = Model::NX;
+    pl->upc_nu = p->u_per_command * p->nu;
+    pl->pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
+    pl->epoch = p->epoch;
+    pl->host_epoch = 0;
+    pl->p = *p;
+    return MPPI_OK;
+}
+
+template <class Model, typename real> int build_plan_variant(const MppiFusedParams* p, Plan* pl) {
+    switch (p->variant) {
+        case MPPI_VARIANT_MPPI: return build_plan<Model, real, V_MPPI>(p, pl);
+        case MPPI_VARIANT_SMPPI: return build_plan<Model, real, V_SMPPI>(p, pl);
+        case MPPI_VARIANT_KMPPI: return build_plan<Model, real, V_KMPPI>(p, pl);
+    }
+    return MPPI_ERR_BAD_ARG;
+}
+
+template <class Model, typename real>
+int run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStream_t stream) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    KArgs<real> a;
+    fill_kargs<real>(p, a, 128, 1);
+    typename Model::template P<real> mp;
+    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp,
+                                                                        (long long)p->T * p->nu);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+// get_rollouts (mppi.py:425-448): n start states, each rolled through an action sequence
+template <class Model, typename real>
+int run_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, long long stride, int n, int T,
+                       void* states, cudaStream_t stream) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    KArgs<real> a;
+    memset(&a, 0, sizeof(a));
+    a.nm.u_scale = (real)p->u_scale;
+    a.K = n;
+    a.T = T;
+    a.state_dev = (const real*)start_states;
+    a.state_per_sample = 1;
+    typename Model::template P<real> mp;
+    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    states_kernel<Model, real><<<(n + 127) / 128, 128, 0, stream>>>((const real*)actions, (real*)states, a, mp, stride);
+    CK(cudaGetLastError());
+    return MPPI_OK;
+}
+
+}  // namespace
+

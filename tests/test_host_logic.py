@@ -205,14 +205,16 @@ def test_build_is_keyed_by_source_hash_not_file_times(tmp_path, monkeypatch):
     h = build.source_hash()
     assert open(build.STAMP).read().strip() == h and len(h) == 40
     # older/newer file times alone change nothing
-    os.utime(build.SRC, None)
+    os.utime(os.path.join(build.CSRC, "mppi_b200.cu"), None)
     assert not build.needs_build()
-    # a different source does
+    # a different source does (here: one more header in the C-ABI unit's dependency list)
     fake = tmp_path / "extra.cuh"
     fake.write_text("// edited\n")
-    monkeypatch.setattr(build, "DEPS", [*build.DEPS, str(fake)])
+    src, defs, hdrs = build.UNITS["cabi"]
+    monkeypatch.setitem(build.UNITS, "cabi", (src, defs, [*hdrs, str(fake)]))
     assert build.source_hash() != h and build.needs_build()
+    monkeypatch.setitem(build.UNITS, "cabi", (src, defs, hdrs))
+    assert not build.needs_build()
     # and so does a missing stamp
-    monkeypatch.setattr(build, "DEPS", build.DEPS[:-1])
     monkeypatch.setattr(build, "STAMP", str(tmp_path / "nope.stamp"))
     assert build.needs_build()
