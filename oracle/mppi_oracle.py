@@ -149,6 +149,12 @@ class Problem:
     terminal_state_cost: Optional[Callable] = None
     sample_null_action: bool = False
     noise_abs_cost: bool = False
+    # M > 1 rollouts of stochastic dynamics (mppi.py:54-58, 166-177)
+    rollout_samples: int = 1
+    rollout_var_cost: float = 0
+    rollout_var_discount: float = 0.95
+    # SpecificActionSampler.sample_trajectories as a plain function state -> (n,T,nu) (mppi.py:16-32, 393-399)
+    specific_actions: Optional[Callable] = None
     # derived
     dtype: torch.dtype = field(init=False)
     nu: int = field(init=False)
@@ -244,6 +250,49 @@ def rollout_costs(prob: Problem, x0, perturbed_action):
     return cost, None, None
 
 
+def rollout_costs_multi(prob: Problem, x0, perturbed_action):
+    """mppi.py:334-373 (M>1): the K action sequences are rolled out M times through (stochastic)
+    dynamics — rows are copy-major, row m*K+k is copy m of sample k (`state.repeat(M,1,1)` :351) —;
+    cost = mean over copies + rollout_var_cost * sum_t discount^t * var_m(c_t)  (unbiased variance,
+    torch.var's default).  Returns (cost (K,), states (M,K,T,nx), actions (M,K,T,nu))."""
+    K, T, nu = perturbed_action.shape
+    M = prob.rollout_samples
+    cost_total = torch.zeros(K, dtype=prob.dtype)
+    cost_samples = cost_total.repeat(M, 1)                                     # :340
+    cost_var = torch.zeros_like(cost_total)                                    # :341
+    if x0.shape == (K, prob.nx):
+        state = x0
+    else:
+        state = x0.view(1, -1).expand(K, -1)
+    state = state.repeat(M, 1, 1)                                              # :348
+    states = torch.empty(M, K, T, prob.nx, dtype=prob.dtype)
+    actions = torch.empty(M, K, T, nu, dtype=prob.dtype)
+    discount = prob.rollout_var_discount ** torch.arange(T, dtype=prob.dtype)  # :174-175
+    MK = M * K
+    state_flat = state.reshape(MK, prob.nx)
+    for t in range(T):
+        u = prob.u_scale * perturbed_action[:, t].expand(M, -1, -1)            # :355
+        u_flat = u.reshape(MK, nu)
+        state_flat = prob.dynamics(state_flat, u_flat)                         # :357
+        c = prob.running_cost(state_flat, u_flat)                              # :362
+        cost_samples = cost_samples + c.reshape(M, K)                          # :363
+        cost_var += c.reshape(M, K).var(dim=0) * discount[t]                   # :364
+        states[:, :, t] = state_flat.reshape(M, K, -1)[:, :, :prob.nx]
+        actions[:, :, t] = u
+    c = prob.terminal_state_cost(states, actions) if prob.terminal_state_cost is not None else 0   # :161, :369
+    cost_samples = cost_samples + c
+    cost_total = cost_total + cost_samples.mean(dim=0)                         # :371
+    cost_total = cost_total + cost_var * prob.rollout_var_cost                 # :372
+    return cost_total, states, actions
+
+
+def rollout(prob: Problem, x0, perturbed_action):
+    """mppi.py:292-295"""
+    if prob.rollout_samples == 1:
+        return rollout_costs(prob, x0, perturbed_action)
+    return rollout_costs_multi(prob, x0, perturbed_action)
+
+
 def softmin_weights(cost_total, lambda_):
     """mppi.py:254-259 + 12-13: beta=min c; w=exp(-(1/lambda)(c-beta)); eta=sum w; omega=w/eta."""
     beta = torch.min(cost_total)
@@ -253,10 +302,16 @@ def softmin_weights(cost_total, lambda_):
     return beta, w, eta, omega
 
 
-def _apply_null_action(prob, perturbed_action):
-    # mppi.py:387-392: sample 0 is overwritten with zeros BEFORE the clamp
+def _apply_null_action(prob, perturbed_action, x0=None):
+    """mppi.py:387-400 (`_sample_specific_actions`): sample 0 is overwritten with zeros, then the rows after it with
+    the SpecificActionSampler's trajectories — all BEFORE the clamp."""
+    i = 0
     if prob.sample_null_action:
-        perturbed_action[0] = 0
+        perturbed_action[i] = 0                                    # :390-392
+        i += 1
+    if prob.specific_actions is not None:
+        acts = prob.specific_actions(x0).reshape(-1, perturbed_action.shape[1], perturbed_action.shape[2])   # :394-396
+        perturbed_action[i:i + acts.shape[0]] = acts               # :397
     return perturbed_action
 
 
@@ -274,11 +329,11 @@ def mppi_command(prob: Problem, U, x0, z, shift=True):
     x0 = torch.as_tensor(x0).to(prob.dtype)
     eps_raw = prob.colour(z)                                   # mppi.py:378
     pa = U + eps_raw                                           # :380
-    pa = _apply_null_action(prob, pa)                          # :381
+    pa = _apply_null_action(prob, pa, x0)                      # :381
     pa = prob.clamp_u(pa)                                      # :383
     noise = pa - U                                             # :385
     ac = prob.action_cost(noise)                               # :409
-    roll, states, actions = rollout_costs(prob, x0, pa)        # :411
+    roll, states, actions = rollout(prob, x0, pa)              # :411
     pert = torch.sum(U * ac, dim=(1, 2))                       # :415
     cost_total = roll + pert                                   # :416
     beta, w, eta, omega = softmin_weights(cost_total, prob.lambda_)
@@ -397,7 +452,7 @@ def kmppi_command(prob: Problem, U, theta, x0, z, W, Wshift, shift=True):
 # --------------------------------------------------------------------------------------
 # MPPI_Batched
 # --------------------------------------------------------------------------------------
-def mppi_batched_command(prob: Problem, U, states0, z, shift=True):
+def mppi_batched_command(prob: Problem, U, states0, z, shift=True, u_per_command=1):
     """`MPPI_Batched.command` (mppi.py:822-873): N environments, noise z (K,T,nu) shared across
     environments, independent softmin per environment.  U: (N,T,nu), states0: (N,nx)."""
     U = U.clone()
@@ -423,4 +478,7 @@ def mppi_batched_command(prob: Problem, U, states0, z, shift=True):
     eta = w.sum(dim=1, keepdim=True)
     omega = w / eta
     U_new = U + torch.einsum("nk,nktd->ntd", omega, noise)
-    return dict(U=U_new, action=U_new[:, 0], cost_total=total, omega=omega)
+    action = U_new[:, :u_per_command]                                # :870-873
+    if u_per_command == 1:
+        action = action[:, 0]
+    return dict(U=U_new, action=action, cost_total=total, omega=omega)

@@ -190,7 +190,7 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     pl->upc_nu = p->u_per_command * p->nu;
     pl->pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
     pl->epoch = p->epoch;
-    pl->host_epoch = 0;
+    pl->host_epoch = p->host_epoch;      // monotonic across re-plans: a stale mailbox tag of an earlier plan can never match
     pl->p = *p;
     return MPPI_OK;
 }

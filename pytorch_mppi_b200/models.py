@@ -322,9 +322,14 @@ def resolve_fused_model(dynamics, running_cost, terminal_state_cost) -> Optional
     m = AnalyticModel.owner_of(dynamics)
     if m is None or AnalyticModel.owner_of(running_cost) is not m:
         return None
-    if getattr(dynamics, "__func__", None) is not type(m).dynamics:
+    # the class that REGISTERED the model (declares model_id): a user subclass that overrides dynamics / running_cost /
+    # terminal_cost in Python is no longer the compiled model and must take the stepped route
+    reg = next((c for c in type(m).__mro__ if "model_id" in c.__dict__ and c is not AnalyticModel), None)
+    if reg is None:
         return None
-    if getattr(running_cost, "__func__", None) is not type(m).running_cost:
+    if getattr(dynamics, "__func__", None) is not reg.__dict__.get("dynamics"):
+        return None
+    if getattr(running_cost, "__func__", None) is not reg.__dict__.get("running_cost"):
         return None
     if terminal_state_cost is None:
         # the kernel adds the model's terminal cost iff terminal_scale != 0; without the plugin the
@@ -332,6 +337,6 @@ def resolve_fused_model(dynamics, running_cost, terminal_state_cost) -> Optional
         return m if not m.has_terminal else None
     if AnalyticModel.owner_of(terminal_state_cost) is not m or not m.has_terminal:
         return None
-    if getattr(terminal_state_cost, "__func__", None) is not getattr(type(m), "terminal_cost", None):
+    if getattr(terminal_state_cost, "__func__", None) is not reg.__dict__.get("terminal_cost"):
         return None
     return m

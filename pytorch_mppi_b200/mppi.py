@@ -219,6 +219,7 @@ class MPPI:
         self._z_inject = None
         self._z_out = None
         self._host_box = None
+        self._host_epoch = 0            # launch-route command_host() calls so far: the mailbox tag, carried across re-plans
         self._plan = None
         self._last = None
         self._resident = False          # a resident grid is armed for command_host (start_resident)
@@ -261,8 +262,14 @@ class MPPI:
         return self._noise_sigma_inv
 
     @noise_sigma_inv.setter
-    def noise_sigma_inv(self, v):   # autotune writes it next to noise_sigma (autotune.py:160-162); derived here
-        pass
+    def noise_sigma_inv(self, v):
+        """The reference's tuner writes this next to `noise_sigma` (autotune.py:160-162).  The engine always derives the
+        inverse from `noise_sigma`, so a consistent value is accepted as a no-op and an inconsistent one is an error
+        (it would otherwise be silently ignored)."""
+        v = torch.as_tensor(v).to(self.d, self.dtype).reshape(self.nu, self.nu)
+        if not torch.allclose(v, self._noise_sigma_inv, rtol=1e-4, atol=1e-6):
+            raise ValueError("noise_sigma_inv is derived from noise_sigma; assign noise_sigma (the given inverse does not "
+                             "match the current covariance)")
 
     def _mk(name):   # noqa: N805  (tiny property factory)
         def get(self):
@@ -454,6 +461,7 @@ class MPPI:
         p.flags = self._base_flags | (_cabi.FLAG_EXPORT_PARTIAL if (self._world > 1 and self._exchange != "p2p") else 0)
         p.z_out = None if self._z_out is None else self._z_out.data_ptr()
         p.epoch = self._epoch
+        p.host_epoch = self._host_epoch      # the new plan continues the mailbox tags where the old one stopped
         plan = C.c_void_p()
         _cabi.check(self._lib.mppi_plan_create(C.byref(p), C.byref(plan)), "mppi_plan_create")
         self._plan = plan
@@ -667,12 +675,14 @@ class MPPI:
                 self._graph_mode = False
                 torch.cuda.synchronize(self.d)
                 return self._command_stepped(state, shift)
-        g, st_static, action_static = self._graphs[key]
+        g, st_static, action_static, cost_buf = self._graphs[key]
         st_static.copy_(st)
         g.replay()
         self._cmd_count += 1
         self._materialized_at["noise"] = self._cmd_count
         self._last = None
+        self._cost_buf = cost_buf                      # the buffer THIS graph writes (several keys = several graphs)
+        self._p.cost_total = cost_buf.data_ptr()
         self.cost_total = self._cost_buf
         out = action_static.clone()
         return out[0] if self.u_per_command == 1 else out
@@ -706,21 +716,29 @@ class MPPI:
         st_static = st.clone()
         snap = self._nominal_snapshot()
         off0 = self._offset_dev.clone()
-        cur = torch.cuda.current_stream(self.d)
-        side = torch.cuda.Stream(device=self.d)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):                       # warm-up: allocator, geometry cache, lazy module loads
-            for _ in range(2):
-                self._command_stepped(st_static, shift)
-        cur.wait_stream(side)
-        torch.cuda.synchronize(self.d)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            p, action = self._begin_command(st_static, shift)
-            action = self._stepped_body(p, action, st_static)
-        self._nominal_restore(snap)                          # the warm-up commands were real ones: undo them
-        self._offset_dev.copy_(off0)
-        self._graphs[key] = (g, st_static, action)
+        count0 = self._cmd_count
+        try:
+            cur = torch.cuda.current_stream(self.d)
+            side = torch.cuda.Stream(device=self.d)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                       # warm-up: allocator, geometry cache, lazy module loads
+                for _ in range(2):
+                    self._command_stepped(st_static, shift)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.d)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                p, action = self._begin_command(st_static, shift)
+                action = self._stepped_body(p, action, st_static)
+            cost_buf = self._cost_buf                           # this graph's own result buffer
+        finally:
+            # the warm-up (and a failed capture) ran real commands: undo them whatever happened, so that the caller's
+            # command() — replayed from the graph, or re-run eagerly after a capture failure — is the only one applied
+            torch.cuda.synchronize(self.d)
+            self._nominal_restore(snap)
+            self._offset_dev.copy_(off0)
+            self._cmd_count = count0
+        self._graphs[key] = (g, st_static, action, cost_buf)
 
     def get_params(self):
         return f"K={self.K} T={self.T} M={self.M} lambda={self.lambda_} noise_mu={self.noise_mu.cpu().numpy()} noise_sigma={self.noise_sigma.cpu().numpy()}".replace(
@@ -911,6 +929,7 @@ class MPPI:
         self._last = (flags, seed, off, zptr, None)
         self._cmd_count += 1
         out = torch.empty_like(self._host_template)
+        self._host_epoch += 1
         rc = self._lib.mppi_plan_command_host(self._plan, self._state_arr, flags, seed, off, zptr,
                                               self._scratch_action.data_ptr(), self._host_box.data_ptr(), out.data_ptr(), stream)
         if rc != 0:
@@ -1043,6 +1062,8 @@ class MPPI:
         actions = torch.empty(M, K, T, nu, device=self.d, dtype=self.dtype)
         MK = M * K
         state_flat = state.reshape(MK, self.nx)
+        # mppi.py:174-175: discount^t evaluated in the controller dtype (so fp32 controllers use the reference's factors)
+        disc = (self.rollout_var_discount ** torch.arange(T, dtype=self.dtype)).tolist()
         for t in range(T):
             u = self._u_scale * perturbed_actions[:, t].expand(M, -1, -1)
             u_flat = u.reshape(MK, nu)
@@ -1053,7 +1074,7 @@ class MPPI:
                 state_flat = s3.reshape(MK, -1)
             c = self._running_cost_fn(state_flat, u_flat, t).reshape(MK).to(self.dtype).contiguous()
             _cabi.check(lib.mppi_cost_accumulate(cost_samples.data_ptr(), c.data_ptr(), cost_var.data_ptr(), M, K,
-                                                 float(self.rollout_var_discount) ** t, dt, stream), "mppi_cost_accumulate")
+                                                 disc[t], dt, stream), "mppi_cost_accumulate")
             states[:, :, t] = state_flat.reshape(M, K, -1)[:, :, :self.nx]
             actions[:, :, t] = u
         if self.terminal_state_cost is not None:
@@ -1356,6 +1377,16 @@ class KMPPI(MPPI):
     def deparameterize_to_trajectory_batch(self, theta):
         assert theta.shape == (self.K, self.num_support_pts, self.nu)
         return torch.matmul(self._W, theta), None
+
+    def change_horizon(self, horizon):
+        """The reference inherits MPPI.change_horizon (mppi.py:277-284) and then fails on stale interpolation
+        matrices; here the control points are kept, the time grids and operators are rebuilt for the new horizon, and
+        the trajectory is re-derived from the control points (U = W theta, as mppi.py:682 leaves it)."""
+        self._leave_resident()
+        self._resize_horizon(int(horizon), torch.zeros(int(horizon), self.nu, device=self.d, dtype=self.dtype))
+        self.prepare_vmap_interpolation()
+        self.U = self._W @ self._theta
+        self._dirty = True
 
     def _variant_pack(self, p):
         p.S = self.num_support_pts

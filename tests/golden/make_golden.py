@@ -27,13 +27,15 @@ sys.path.insert(0, ROOT)
 
 from pytorch_mppi import mppi as ref  # noqa: E402  (the untouched reference)
 from oracle import mppi_oracle as orc  # noqa: E402
-from tests.golden.cases import CASES, draw_z, build_problem  # noqa: E402
+from tests.golden.cases import (BATCHED_CASES, CASES, build_problem, draw_z, mlp_state_arrays,  # noqa: E402
+                                sampler_actions)
 
 
-def ref_plugins(case):
+def ref_plugins(case, prob, model):
     """Plugins handed to the reference controller.  The pendulum is written with the same
     np.sin / np.clip-on-tensor calls as /root/reference/tests/pendulum.py:30-60 so the fixture
-    also pins that those equal the oracle's torch.sin / torch.clamp."""
+    also pins that those equal the oracle's torch.sin / torch.clamp.  Every other model hands the reference the
+    callables of the oracle's problem (the MLP network and the per-copy offset dynamics are torch callables)."""
     if case["model"]["kind"] == "pendulum":
         def dynamics(state, perturbed_action):
             th = state[:, 0].view(-1, 1)
@@ -52,15 +54,21 @@ def ref_plugins(case):
             return angle_normalize(state[:, 0]) ** 2 + 0.1 * state[:, 1] ** 2
 
         return dynamics, running_cost, None
-    prob, model = build_problem(case)
-    return model.dynamics, model.running_cost, (model.terminal_cost if model.has_terminal else None)
+    return prob.dynamics, prob.running_cost, prob.terminal_state_cost
 
 
-def make_ref_controller(case, prob, U_init):
-    dyn, cost, term = ref_plugins(case)
+def make_ref_controller(case, prob, model, U_init):
+    dyn, cost, term = ref_plugins(case, prob, model)
     kw = dict(num_samples=case["K"], horizon=case["T"], lambda_=case["lambda_"], device="cpu",
               u_scale=case.get("u_scale", 1), sample_null_action=case.get("sample_null_action", False),
-              noise_abs_cost=case.get("noise_abs_cost", False), terminal_state_cost=term)
+              noise_abs_cost=case.get("noise_abs_cost", False), terminal_state_cost=term,
+              rollout_samples=case.get("rollout_samples", 1), rollout_var_cost=case.get("rollout_var_cost", 0),
+              rollout_var_discount=case.get("rollout_var_discount", 0.95))
+    if case.get("sampler") is not None:
+        class Sampler(ref.SpecificActionSampler):                       # mppi.py:16-32
+            def sample_trajectories(self, state, info):
+                return sampler_actions(case, state)
+        kw["specific_action_sampler"] = Sampler()
     dt = prob.dtype
     if case.get("noise_mu") is not None:
         kw["noise_mu"] = torch.tensor(case["noise_mu"], dtype=dt)
@@ -101,7 +109,7 @@ def run_case(name, case):
     S = case["kernel"]["S"] if variant == "kmppi" else None
     g = np.random.Generator(np.random.Philox(key=case["seed"]))
     U0 = (torch.from_numpy(g.standard_normal((T, nu), dtype=np.float32)) * np.float32(case.get("U_init_scale", 1.0))).to(dt)
-    ctrl = make_ref_controller(case, prob, U0)
+    ctrl = make_ref_controller(case, prob, model, U0)
     zbox = {}
     ctrl._sample_noise = lambda shape: prob.colour(zbox["z"])   # injection point (mppi.py:201-206)
 
@@ -120,6 +128,8 @@ def run_case(name, case):
 
     x = torch.tensor(case["x0"], dtype=dt)
     out = {"U0": U0.numpy()}
+    if case["model"]["kind"] == "pendulum_mlp":
+        out.update(mlp_state_arrays(model.net))
     zsums = []
     for step in range(case["steps"]):
         zshape = (K, S, nu) if variant == "kmppi" else (K, T, nu)
@@ -144,6 +154,16 @@ def run_case(name, case):
         assert torch.equal(r["omega"], ctrl.omega), f"{name} step {step}: omega mismatch"
         assert torch.equal(r["action"], a_ref), f"{name} step {step}: action mismatch"
         assert torch.equal(r["noise"], ctrl.noise)
+        assert torch.equal(r["perturbed_action"], ctrl.perturbed_action)
+        if case.get("rollout_samples", 1) > 1:
+            assert torch.equal(r["states"], ctrl.states) and torch.equal(r["actions"], ctrl.actions)
+            # the case must exercise the variance term: the M copies of a sample really differ
+            assert float(ctrl.states.var(dim=0).max()) > 1e-4, f"{name}: rollout copies are identical"
+        if case.get("sampler") is not None:
+            i0 = 1 if case.get("sample_null_action") else 0
+            smp = ctrl.specific_action_sampler
+            assert (smp.start_idx, smp.end_idx) == (i0, i0 + case["sampler"]["n"])
+            out[f"pa_head_{step}"] = r["perturbed_action"][: i0 + case["sampler"]["n"] + 1].numpy()
         out[f"U_{step}"] = r["U"].numpy()
         out[f"action_{step}"] = r["action"].numpy()
         if K <= 2048 or step == 0:      # keep the big cases' fixtures small: full cost vector for step 0 only
@@ -163,13 +183,66 @@ def run_case(name, case):
     return out
 
 
+def run_batched_case(name, case):
+    """MPPI_Batched (mppi.py:691-873): the live class against oracle.mppi_batched_command on injected shared noise."""
+    prob, model = build_problem(dict(case, variant="mppi"))
+    dt = prob.dtype
+    N, K, T, nu = case["N"], case["K"], case["T"], prob.nu
+    upc = case.get("u_per_command", 1)
+    g = np.random.Generator(np.random.Philox(key=case["seed"]))
+    U0 = torch.from_numpy(g.standard_normal((N, T, nu), dtype=np.float32)).to(dt)
+    dyn, cost, _ = ref_plugins(dict(case, variant="mppi"), prob, model)
+    kw = dict(num_envs=N, num_samples=K, horizon=T, lambda_=case["lambda_"], device="cpu", u_scale=case.get("u_scale", 1),
+              u_per_command=upc, noise_abs_cost=case.get("noise_abs_cost", False))
+    for key in ("noise_mu", "u_init", "u_min", "u_max"):
+        if case.get(key) is not None:
+            kw[key] = torch.tensor(case[key], dtype=dt)
+    ctrl = ref.MPPI_Batched(dyn, cost, prob.nx, torch.tensor(case["noise_sigma"], dtype=dt), **kw)
+    ctrl.U = U0.clone()
+    zbox = {}
+    ctrl._sample_noise = lambda shape: prob.colour(zbox["z"])            # mppi.py:807-811 (shared (K,T,nu) draw)
+    U = U0.clone()
+    x = torch.tensor(case["x0"], dtype=dt)
+    out = {"U0": U0.numpy()}
+    zsums = []
+    for step in range(case["steps"]):
+        z = draw_z(g, (K, T, nu), dt, case.get("z_dtype"))
+        zsums.append(float(z.double().sum()))
+        zbox["z"] = z
+        a_ref = ctrl.command(x.clone())
+        r = orc.mppi_batched_command(prob, U, x, z, u_per_command=upc)
+        assert torch.equal(r["U"], ctrl.U), f"{name} step {step}: U mismatch {(r['U'] - ctrl.U).abs().max()}"
+        assert torch.equal(r["action"], a_ref), f"{name} step {step}: action mismatch"
+        U = r["U"]
+        out[f"U_{step}"] = r["U"].numpy()
+        out[f"action_{step}"] = r["action"].numpy()
+        out[f"cost_total_{step}"] = r["cost_total"].numpy()
+        out[f"omega_{step}"] = r["omega"].numpy()
+        out[f"x_{step}"] = x.numpy().copy()
+        a0 = r["action"] if upc == 1 else r["action"][:, 0]
+        x = prob.dynamics(x, prob.u_scale * a0)[:, : prob.nx]
+    out["z_sums"] = np.asarray(zsums)
+    out["case_json"] = np.asarray(json.dumps(case))
+    return out
+
+
 def main():
     torch.set_num_threads(1)   # fixed reduction order inside ATen sums
+    only = set(sys.argv[1:])
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         res = run_case(name, case)
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **res)
         print(f"{name}: oracle == reference over {case['steps']} step(s); wrote {os.path.getsize(path)} bytes")
+    for name, case in BATCHED_CASES.items():
+        if only and name not in only:
+            continue
+        res = run_batched_case(name, case)
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **res)
+        print(f"{name}: oracle == reference (MPPI_Batched) over {case['steps']} step(s); wrote {os.path.getsize(path)} bytes")
 
 
 if __name__ == "__main__":

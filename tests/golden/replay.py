@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from oracle import mppi_oracle as orc
-from tests.golden.cases import CASES, draw_z, build_problem
+from tests.golden.cases import BATCHED_CASES, CASES, draw_z, build_problem  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -35,9 +35,9 @@ class Stream:
 class OracleRunner:
     """Steps the oracle through a case; `.step(x, z)` returns the oracle's result dict."""
 
-    def __init__(self, case):
+    def __init__(self, case, gold=None):
         self.case = case
-        self.prob, self.model = build_problem(case)
+        self.prob, self.model = build_problem(case, gold)      # gold: the MLP cases read their weights from the fixture
         p, dt = self.prob, self.prob.dtype
         self.variant = case["variant"]
         self.stream = Stream(case, p)
@@ -73,3 +73,29 @@ class OracleRunner:
     def advance(self, x, action):
         p = self.prob
         return p.dynamics(x.view(1, -1), (p.u_scale * action).view(1, -1)).view(-1)[: p.nx]
+
+
+class BatchedOracleRunner:
+    """MPPI_Batched golden cases: shared (K,T,nu) draws, (N,T,nu) nominal, (N,nx) states."""
+
+    def __init__(self, case):
+        self.case = case
+        self.prob, self.model = build_problem(dict(case, variant="mppi"))
+        p = self.prob
+        self.gen = np.random.Generator(np.random.Philox(key=case["seed"]))
+        self.U0 = torch.from_numpy(self.gen.standard_normal((case["N"], case["T"], p.nu), dtype=np.float32)).to(p.dtype)
+        self.U = self.U0.clone()
+        self.upc = case.get("u_per_command", 1)
+
+    def next_z(self):
+        c = self.case
+        return draw_z(self.gen, (c["K"], c["T"], self.prob.nu), self.prob.dtype, c.get("z_dtype"))
+
+    def step(self, x, z):
+        r = orc.mppi_batched_command(self.prob, self.U, x, z, u_per_command=self.upc)
+        self.U = r["U"]
+        return r
+
+    def advance(self, x, action):
+        a0 = action if self.upc == 1 else action[:, 0]
+        return self.prob.dynamics(x, self.prob.u_scale * a0)[:, : self.prob.nx]

@@ -424,3 +424,87 @@ def test_quality_bounds(route):
     for T in (5, 15):
         d, acc = _loop(make(route=route, num_samples=500, horizon=T))
         assert d < 5.0 and acc < 300.0                                                                   # :884-896
+
+
+def test_command_host_after_replan_returns_the_new_action():
+    """a re-plan (any parameter setter) restarts the C plan; the pinned mailbox still holds the tags of the
+    previous plan.  The mailbox tag is carried across plans, so command_host() after a re-plan waits for ITS kernel
+    and returns the same action command() does."""
+    import pytorch_mppi_b200 as eng
+    pend = eng.Pendulum()
+
+    def make():
+        torch.manual_seed(0)
+        U0 = torch.randn(15, 1) * 2
+        return eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(4.0), num_samples=2048, horizon=15, U_init=U0,
+                        u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=5)
+    a, b = make(), make()
+    x = [3.0, 0.4]
+    for lam in (1.0, 0.5, 2.0, 0.7):                 # exactly ONE command_host per plan: the stale tag would be 1 again
+        a.lambda_ = lam
+        b.lambda_ = lam
+        ah = a.command_host(x)
+        bd = b.command(x)
+        assert torch.equal(ah, bd.cpu()), lam
+        assert torch.equal(a.U, b.U)
+    a.record_noise()                                  # another kind of re-plan
+    b.record_noise()
+    assert torch.equal(a.command_host(x), b.command(x).cpu())
+
+
+def test_kmppi_change_horizon_rebuilds_interpolation():
+    """KMPPI.change_horizon must rebuild W / Wshift / Tk / Hs for the new horizon (growing T used to read
+    the old (T_old x S) matrix out of bounds)."""
+    import pytorch_mppi_b200 as eng
+    from oracle import mppi_oracle as orc
+    dt = torch.float64
+    lin = eng.LinearPoint.unit_test_env()
+    K, S = 256, 4
+    ctrl = eng.KMPPI(lin.dynamics, lin.running_cost, 2, torch.eye(2, dtype=dt), num_samples=K, horizon=8, num_support_pts=S,
+                     kernel=eng.RBFKernel(sigma=1.5), device="cuda")
+    ctrl.command([0.0, 0.0])
+    for T in (14, 6):
+        theta0 = ctrl.theta.clone()
+        ctrl.change_horizon(T)
+        assert ctrl.T == T and ctrl.U.shape == (T, 2) and ctrl.Hs.shape == (1, T)
+        W, Wsh = orc.kernel_matrices(T, S, lambda a, b: orc.rbf_kernel(a, b, 1.5), dt)
+        assert torch.allclose(ctrl._W.cpu(), W, atol=1e-12) and torch.allclose(ctrl._Wshift.cpu(), Wsh, atol=1e-12)
+        assert torch.equal(ctrl.theta, theta0)
+        assert torch.allclose(ctrl.U.cpu(), W @ theta0.cpu(), atol=1e-12)
+        # and a command on the new horizon matches the oracle
+        olin = orc.LinearPointModel(B=lin.B, goal=lin.goal, dtype=dt)
+        prob = orc.Problem(olin.dynamics, olin.running_cost, 2, torch.eye(2, dtype=dt), K=K, T=T)
+        z = torch.randn(K, S, 2, dtype=dt)
+        ctrl.inject_noise(z)
+        U_before, th_before = ctrl.U.cpu().clone(), ctrl.theta.cpu().clone()
+        ctrl.command([0.5, -0.5])
+        r = orc.kmppi_command(prob, U_before, th_before, torch.tensor([0.5, -0.5], dtype=dt), z, W, Wsh)
+        assert float((ctrl.theta.cpu() - r["theta"]).abs().max()) < 1e-10
+        assert float((ctrl.U.cpu() - r["U"]).abs().max()) < 1e-10
+
+
+def test_compile_fallback_applies_exactly_one_command():
+    """a plugin that is not capture-safe makes compile() fall back to the eager stepped route; the warm-up
+    commands of the failed capture must be undone, so the nominal moves by exactly one command."""
+    import pytorch_mppi_b200 as eng
+    lin = eng.LinearPoint.unit_test_env()
+    dt = torch.float64
+
+    def bad_cost(s, a):
+        c = lin.running_cost(s, a)
+        float(c[0])                      # host sync: illegal during stream capture
+        return c
+
+    def make(cost):
+        torch.manual_seed(3)
+        U0 = torch.randn(7, 2, dtype=dt) * 0.1
+        return eng.MPPI(lambda s, a: lin.dynamics(s, a), cost, 2, torch.eye(2, dtype=dt), num_samples=128, horizon=7,
+                        U_init=U0, device="cuda", rng_seed=11)
+    ref_ctrl = make(lambda s, a: lin.running_cost(s, a))
+    bad = make(bad_cost)
+    bad.compile()
+    a0 = ref_ctrl.command([1.0, 1.0])
+    a1 = bad.command([1.0, 1.0])          # capture fails -> eager; one command applied
+    assert bad._graph_mode is False
+    assert torch.allclose(a0, a1, atol=1e-12) and torch.allclose(ref_ctrl.U, bad.U, atol=1e-12)
+    assert torch.allclose(ref_ctrl.command([0.9, 1.1]), bad.command([0.9, 1.1]), atol=1e-12)

@@ -13,24 +13,41 @@ import numpy as np
 import pytest
 import torch
 
-from tests.golden.cases import CASES
+from tests.golden.cases import BATCHED_CASES, CASES
 from tests.golden.replay import OracleRunner, load
 
 pytestmark = pytest.mark.gpu
 
 U_TOL = {"f64": 1e-9, "f32": 1e-5}
-# pendulum_small_f32: K=257, lambda=0.5 (ESS ~ 3): a 2e-7 relative (1-2 ulp) difference in a sample cost --
-# which sinf-vs-numpy-sin alone produces -- already moves U by 1e-5; 3e-5 is that case's noise floor.
-U_TOL_OVERRIDE = {"linear_mppi_f32": 2e-4, "nav2d_kmppi_c3_f32": 2e-4, "pendulum_small_f32": 3e-5}
+# Overrides of the fp32 north-star bound, each <= 2x the error measured on B200 (profiles/r02_parity_errors.json):
+#  pendulum_small_f32: K=257, lambda=0.5 (ESS ~ 3): a 2e-7 relative (1-2 ulp) difference in a sample cost -- which
+#    sinf-vs-numpy-sin alone produces -- already moves U by 1e-5 (measured 1.04e-5).
+#  mlp_c4_f32: the network's three contractions run as FMA chains in the kernel and as BLAS calls in the reference
+#    (different summation order through two tanh layers and 30 steps).
+U_TOL_OVERRIDE = {"pendulum_small_f32": 2.1e-5, "mlp_c4_f32": 5e-5}
+_MEASURED = {}
 
 
-def _run(name, route, check_oracle=True):
+def _record(key, err):
+    """Worst error per (case, route), dumped to gpurun_out/parity_errors.json for the tolerance table above."""
+    import json
+    import os
+    _MEASURED[key] = max(_MEASURED.get(key, 0.0), float(err))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", "parity_errors.json"), "w") as f:
+            json.dump(_MEASURED, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _run(name, route, check_oracle=True, model_kw=None, tol=None):
     from tests.golden.engine import make_engine
     torch.set_num_threads(1)
     case, gold = load(name)
-    run = OracleRunner(case)
-    tol = U_TOL_OVERRIDE.get(name, U_TOL[case["dtype"]])
-    ctrl = make_engine(case, run.stream.U0, route=route)
+    run = OracleRunner(case, gold)
+    tol = tol if tol is not None else U_TOL_OVERRIDE.get(name, U_TOL[case["dtype"]])
+    ctrl = make_engine(case, run.stream.U0, route=route, gold=gold, model_kw=model_kw)
     assert (ctrl._model is not None) == (route == "fused")
     x = torch.tensor(case["x0"], dtype=run.prob.dtype)
     worst = 0.0
@@ -43,6 +60,7 @@ def _run(name, route, check_oracle=True):
         U = ctrl.U.detach().cpu()
         err = float(np.abs(U.numpy() - gold[f"U_{step}"]).max())
         worst = max(worst, err)
+        _record(f"{name}/{route}" + (f"/{model_kw}" if model_kw else ""), err)
         assert err <= tol, f"{name}/{route} step {step}: |U - U_ref| = {err:.3e} > {tol}"
         aerr = float(np.abs(a.detach().cpu().numpy() - gold[f"action_{step}"]).max())
         assert aerr <= tol, f"{name}/{route} step {step}: action error {aerr:.3e}"
@@ -54,7 +72,7 @@ def _run(name, route, check_oracle=True):
             assert np.abs(th - gold[f"theta_{step}"]).max() <= tol
         if f"cost_total_{step}" in gold:
             c = ctrl.cost_total.detach().cpu().numpy()
-            rtol = 1e-10 if case["dtype"] == "f64" else 5e-6
+            rtol = 1e-10 if case["dtype"] == "f64" else (5e-6 if model_kw is None and case["model"]["kind"] != "pendulum_mlp" else 2e-3)
             np.testing.assert_allclose(c, gold[f"cost_total_{step}"], rtol=rtol, atol=rtol)
         if check_oracle and case["K"] <= 2048:
             r = run.step(xg, z)
@@ -64,7 +82,14 @@ def _run(name, route, check_oracle=True):
             assert abs(om.sum() - 1.0) < 1e-5                                    # test_mppi.py:269-274
             np.testing.assert_allclose(ctrl.noise.cpu().numpy(), r["noise"].numpy(), atol=otol, rtol=0)
             np.testing.assert_allclose(ctrl.perturbed_action.cpu().numpy(), r["perturbed_action"].numpy(), atol=otol, rtol=0)
-            if r["states"] is not None:
+            if f"pa_head_{step}" in gold:                     # null action + SpecificActionSampler rows (mppi.py:387-400)
+                n = gold[f"pa_head_{step}"].shape[0]
+                np.testing.assert_allclose(ctrl.perturbed_action[:n].cpu().numpy(), gold[f"pa_head_{step}"], atol=otol, rtol=0)
+                i0 = 1 if case.get("sample_null_action") else 0
+                smp = ctrl.specific_action_sampler
+                assert (smp.start_idx, smp.end_idx) == (i0, i0 + case["sampler"]["n"])
+            if r["states"] is not None and ctrl.states is not None:
+                assert ctrl.states.shape == r["states"].shape
                 np.testing.assert_allclose(ctrl.states.cpu().numpy(), r["states"].numpy(), atol=max(otol, 1e-5 if case["dtype"] == "f32" else 0), rtol=0)
         # keep the engine's nominal in lock-step with the reference trajectory
         ctrl.U = torch.from_numpy(gold[f"U_{step}"])
@@ -79,17 +104,60 @@ def _run(name, route, check_oracle=True):
     return worst
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+def _routes(name):
+    return CASES[name].get("routes", ["fused", "stepped"])
+
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if "fused" in _routes(n)))
 def test_fused_matches_reference_golden(name):
     _run(name, "fused")
 
 
-@pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n]["K"] <= 2048))
+@pytest.mark.parametrize("name", sorted(n for n in CASES if "stepped" in _routes(n) and (CASES[n]["K"] <= 2048 or CASES[n]["model"]["kind"] == "pendulum_mlp")))
 def test_stepped_route_matches_reference_golden(name):
+    """Arbitrary callables (Python T-loop around the sampling / accumulation / softmin kernels), including the cases
+    only this route serves: rollout_samples M>1 with dynamics that differ between the copies (non-zero variance cost,
+    mppi.py:334-373), SpecificActionSampler rows (mppi.py:387-400), and the config-4 MLP as a plain torch module."""
     _run(name, "stepped")
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("mode,fast,tol", [("bf16x3", False, 2e-4), ("bf16x3", True, 2e-3)])
+def test_tensor_core_mlp_matches_reference_golden(mode, fast, tol):
+    """BASELINE config 4 on the tcgen05 route against the LIVE-reference fixture (mlp_c4_f32): hi/lo-split bf16
+    operands keep the layer outputs at ~2^-16 relative, so the plan agrees with the fp32 reference to 2e-4
+    (exact tanh; MUFU.TANH's 1e-3 absolute error per activation shows at 2e-3)."""
+    _run("mlp_c4_f32", "fused", model_kw=dict(tensor_cores=mode, fast_tanh=fast), tol=tol)
+
+
+@pytest.mark.parametrize("name", sorted(BATCHED_CASES))
+@pytest.mark.parametrize("route", ["fused", "stepped"])
+def test_mppi_batched_matches_reference_golden(name, route):
+    """MPPI_Batched against fixtures produced by the live `ref.MPPI_Batched` (mppi.py:822-873)."""
+    from tests.golden.engine import make_batched_engine
+    from tests.golden.replay import BatchedOracleRunner
+    torch.set_num_threads(1)
+    case, gold = load(name)
+    run = BatchedOracleRunner(case)
+    tol = U_TOL[case["dtype"]]
+    ctrl = make_batched_engine(case, run.U0, route=route)
+    assert (ctrl._model is not None) == (route == "fused")
+    for step in range(case["steps"]):
+        z = run.next_z()
+        ctrl.inject_noise(z)
+        xg = torch.from_numpy(gold[f"x_{step}"]).to(run.prob.dtype)
+        a = ctrl.command(xg.cuda())
+        err = float(np.abs(ctrl.U.cpu().numpy() - gold[f"U_{step}"]).max())
+        _record(f"{name}/{route}", err)
+        assert err <= tol, f"{name}/{route} step {step}: |U - U_ref| = {err:.3e} > {tol}"
+        assert a.shape == gold[f"action_{step}"].shape
+        assert float(np.abs(a.cpu().numpy() - gold[f"action_{step}"]).max()) <= tol
+        rtol = 1e-10 if case["dtype"] == "f64" else 5e-6
+        np.testing.assert_allclose(ctrl.cost_total.cpu().numpy(), gold[f"cost_total_{step}"], rtol=rtol, atol=rtol)
+        np.testing.assert_allclose(ctrl.omega.cpu().numpy(), gold[f"omega_{step}"], atol=1e-9 if case["dtype"] == "f64" else 2e-5, rtol=0)
+        ctrl.U = torch.from_numpy(gold[f"U_{step}"])
+
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if "fused" in _routes(n) and CASES[n]["model"]["kind"] != "pendulum_mlp"))
 def test_split_cost_rollout_is_bit_identical_to_the_single_loop(name, monkeypatch):
     """MPPI_FLAG_SPLIT_COST (the default for single-GPU problems small enough to run with helper threads;
     MPPI_B200_SPLIT_COST=0 turns it off): the rollout thread runs the bare recurrence, the sample's

@@ -28,6 +28,31 @@ def test_registry_resolution():
     assert len(nav.param_blob()) <= 48 and len(pend.param_blob()) == 7
 
 
+def test_subclass_overriding_a_plugin_takes_the_stepped_route():
+    """A user subclass of a registered model that overrides dynamics / running_cost in Python is not the compiled
+    model any more: its bound methods must NOT resolve to the fused route (the override would be silently ignored)."""
+    class MyPendulum(eng.Pendulum):
+        def dynamics(self, state, action):
+            return super().dynamics(state, action) * 0.5
+
+    class MyCost(eng.Pendulum):
+        def running_cost(self, state, action):
+            return super().running_cost(state, action) + 1.0
+
+    class Plain(eng.Pendulum):          # no override: still the compiled model
+        pass
+
+    for cls, fused in ((MyPendulum, False), (MyCost, False), (Plain, True)):
+        m = cls()
+        assert (resolve_fused_model(m.dynamics, m.running_cost, None) is m) == fused, cls.__name__
+
+    class MyNav(eng.LinearPoint):
+        def terminal_cost(self, states, actions):
+            return 2 * super().terminal_cost(states, actions)
+    nav = MyNav(B=[[0.5, 0.0], [0.0, -0.5]], goal=[2.0, 2.0], terminal_scale=10.0)
+    assert resolve_fused_model(nav.dynamics, nav.running_cost, nav.terminal_cost) is None
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_torch_models_equal_oracle_models(dtype):
     g = torch.Generator().manual_seed(0)
