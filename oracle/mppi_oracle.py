@@ -128,6 +128,41 @@ class LinearPointModel:
         return self.terminal_scale != 0.0
 
 
+class MlpPendulumModel:
+    """Learned pendulum dynamics of BASELINE config 4, restating the plugins of
+    /root/reference/tests/pendulum_approximate.py:54-66, 100-110 around a given 3-32-32-2 tanh network:
+    x' = x + net([x, clamp(u, +-2)]), theta' wrapped to [-pi, pi); cost as the analytic pendulum."""
+    nx, nu = 2, 1
+    has_terminal = False
+    terminal_cost = None
+
+    def __init__(self, net):
+        self.net = net
+
+    @staticmethod
+    def angle_normalize(x):
+        return (((x + math.pi) % (2 * math.pi)) - math.pi)
+
+    def dynamics(self, state, perturbed_action):
+        u = torch.clamp(perturbed_action, -2.0, 2.0)
+        if state.dim() == 1 or u.dim() == 1:
+            state = state.view(1, -1)
+            u = u.view(1, -1)
+        if u.shape[1] > 1:
+            u = u[:, 0].view(-1, 1)
+        xu = torch.cat((state, u), dim=1)
+        with torch.no_grad():
+            state_residual = self.net(xu)
+        next_state = state + state_residual
+        next_state[:, 0] = self.angle_normalize(next_state[:, 0])
+        return next_state
+
+    def running_cost(self, state, action):
+        theta = state[:, 0]
+        theta_dt = state[:, 1]
+        return self.angle_normalize(theta) ** 2 + 0.1 * theta_dt ** 2
+
+
 # --------------------------------------------------------------------------------------
 # Problem description
 # --------------------------------------------------------------------------------------
