@@ -169,9 +169,13 @@ typedef struct MppiFusedParams {
     const double* model_params_ext;   /* HOST pointer: extra model parameters (e.g. MLP weights), read at call /
                                          plan-creation time; NULL if the model needs none                    */
     int32_t n_model_params_ext;
-    int32_t _pad1;
+    int32_t K_geom;              /* 0, or the sample count the launch geometry is planned for (>= K): every shard of a
+                                    multi-GPU controller passes the LARGEST shard so that all ranks launch the same
+                                    grid and publish the same number of records per command                */
     void* debug_clocks;          /* optional profiling aid: (grid_blocks, 16) uint64 %globaltimer stamps (ns) at
                                     phase boundaries of each CTA's first tile; NULL on the product path   */
+    void* xchg_status_host;      /* optional pinned HOST int64: the kernel stores MPPI_ERR_TIMEOUT there when a peer
+                                    exchange timed out (the caller checks it before the next command)      */
 } MppiFusedParams;
 
 typedef struct MppiLaunchInfo {
@@ -183,6 +187,10 @@ typedef struct MppiLaunchInfo {
     int32_t threads_per_sample;
     int32_t split_cost;          /* 1 if MPPI_FLAG_SPLIT_COST was honoured for these dimensions          */
     int32_t wide_regs;           /* 1 if MPPI_FLAG_WIDE_REGS was honoured for these dimensions           */
+    int32_t cluster_size;        /* thread-block-cluster size of the launch (1 = no cluster): the CTAs of a cluster
+                                    reduce their softmin partials through distributed shared memory        */
+    int32_t xchg_records;        /* sharded controllers: records each rank publishes per command (its cluster records
+                                    in direct mode, 1 = the rank's combined record); 0 = not sharded       */
 } MppiLaunchInfo;
 
 int mppi_b200_abi_version(void);

@@ -102,8 +102,9 @@ class MppiFusedParams(C.Structure):
         ("offset_inc", C.c_uint64),
         ("model_params_ext", C.c_void_p),
         ("n_model_params_ext", C.c_int32),
-        ("_pad1", C.c_int32),
+        ("K_geom", C.c_int32),
         ("debug_clocks", C.c_void_p),
+        ("xchg_status_host", C.c_void_p),
     ]
 
 
@@ -120,6 +121,8 @@ class MppiLaunchInfo(C.Structure):
         ("threads_per_sample", C.c_int32),
         ("split_cost", C.c_int32),
         ("wide_regs", C.c_int32),
+        ("cluster_size", C.c_int32),
+        ("xchg_records", C.c_int32),
     ]
 
 

@@ -125,7 +125,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 def build_user_model(header_text: str, verbose: bool = False) -> str:
     """JIT-build a variant of the library with a user model in the registry: only the two user-model units (fp32, fp64)
-    are compiled (the generated header + the fused-kernel templates); the stock units are reused from csrc/_obj/.
+    are compiled (the generated header + the fused-kernel templates) and linked with the C-ABI unit from csrc/_obj/ —
+    the variant serves that model (and the model-independent stepped-route kernels), not the stock registry.
     Cached by the hash of the header text and the kernel sources under csrc/_user/."""
     tag = hashlib.sha1((header_text + source_hash()).encode()).hexdigest()[:16]
     udir = os.path.join(CSRC, "_user")
@@ -136,7 +137,7 @@ def build_user_model(header_text: str, verbose: bool = False) -> str:
         return out
     with open(hdr, "w") as f:
         f.write(header_text)
-    base = _compile_all(UNITS, verbose)          # normally all cached
+    base = _compile_all({"cabi": UNITS["cabi"]}, verbose)          # normally cached
     units = {f"user_{tag}_{'f64' if f64 else 'f32'}": ("mppi_model_tu.cu", ["-DMPPI_TU_MODEL=100", f"-DMPPI_TU_F64={f64}",
                                                                               f'-DMPPI_USER_MODEL_HEADER="{hdr}"'], MODEL_HEADERS)
              for f64 in (0, 1)}

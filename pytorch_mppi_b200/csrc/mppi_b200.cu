@@ -11,16 +11,17 @@
 namespace mppi_host {
 thread_local char g_cuda_err[512] = "";
 
-// one getter per (model, dtype) translation unit; the user-model getters exist only in a variant library built by
-// pytorch_mppi_b200.build.build_user_model (weak: absent from the stock library)
-const ModelOps* model_ops_pendulum_f32();
-const ModelOps* model_ops_pendulum_f64();
-const ModelOps* model_ops_linear_point_f32();
-const ModelOps* model_ops_linear_point_f64();
-const ModelOps* model_ops_pendulum_mlp_f32();
-const ModelOps* model_ops_pendulum_mlp_f64();
-const ModelOps* model_ops_user_f32() __attribute__((weak));
-const ModelOps* model_ops_user_f64() __attribute__((weak));
+// one getter per (model, dtype) translation unit, all weak: the stock library links the six registry units, a user-model
+// variant library (pytorch_mppi_b200.build.build_user_model) links this unit and the two units of that model only
+#define MPPI_OPS_DECL(name) const ModelOps* name() __attribute__((weak))
+MPPI_OPS_DECL(model_ops_pendulum_f32);
+MPPI_OPS_DECL(model_ops_pendulum_f64);
+MPPI_OPS_DECL(model_ops_linear_point_f32);
+MPPI_OPS_DECL(model_ops_linear_point_f64);
+MPPI_OPS_DECL(model_ops_pendulum_mlp_f32);
+MPPI_OPS_DECL(model_ops_pendulum_mlp_f64);
+MPPI_OPS_DECL(model_ops_user_f32);
+MPPI_OPS_DECL(model_ops_user_f64);
 }  // namespace mppi_host
 
 namespace {
@@ -29,20 +30,21 @@ namespace {
 const ModelOps* find_ops(const MppiFusedParams* p, int* rc) {
     *rc = MPPI_ERR_UNSUPPORTED;
     const bool f32 = p->dtype == MPPI_F32;
+    typedef const ModelOps* (*Getter)();
+    Getter get = nullptr;
     switch (p->model) {
-        case MPPI_MODEL_PENDULUM: return f32 ? model_ops_pendulum_f32() : model_ops_pendulum_f64();
-        case MPPI_MODEL_LINEAR_POINT: return f32 ? model_ops_linear_point_f32() : model_ops_linear_point_f64();
+        case MPPI_MODEL_PENDULUM: get = f32 ? model_ops_pendulum_f32 : model_ops_pendulum_f64; break;
+        case MPPI_MODEL_LINEAR_POINT: get = f32 ? model_ops_linear_point_f32 : model_ops_linear_point_f64; break;
         case MPPI_MODEL_PENDULUM_MLP:
             if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) {
                 *rc = MPPI_ERR_BAD_ARG;
                 return nullptr;
             }
-            return f32 ? model_ops_pendulum_mlp_f32() : model_ops_pendulum_mlp_f64();
-        case MPPI_MODEL_USER:
-            if (f32) return model_ops_user_f32 != nullptr ? model_ops_user_f32() : nullptr;
-            return model_ops_user_f64 != nullptr ? model_ops_user_f64() : nullptr;
+            get = f32 ? model_ops_pendulum_mlp_f32 : model_ops_pendulum_mlp_f64;
+            break;
+        case MPPI_MODEL_USER: get = f32 ? model_ops_user_f32 : model_ops_user_f64; break;
     }
-    return nullptr;
+    return get != nullptr ? get() : nullptr;      // nullptr: this library was linked without that unit
 }
 
 template <typename real>
@@ -65,9 +67,10 @@ inline void plan_update(Plan* pl, const double* state, const void* state_dev, ui
 
 inline int plan_launch(Plan* pl, cudaStream_t stream) {
     void* argv[2] = {(void*)pl->kargs, (void*)pl->mparams};
-    cudaError_t e = launch_raw(pl->kernel, pl->g.nb, pl->g.BD, pl->g.smem, stream, argv, pl->pdl != 0, pl->p.n_env > 1 ? pl->p.n_env : 1);
+    cudaError_t e = launch_raw(pl->kernel, pl->g.nb, pl->g.BD, pl->g.smem, stream, argv, pl->pdl != 0, pl->p.n_env > 1 ? pl->p.n_env : 1,
+                               pl->g.cluster);
     if (e != cudaSuccess) {
-        snprintf(g_cuda_err, sizeof(g_cuda_err), "plan launch grid=%d block=%d smem=%d: %s (%s)", pl->g.nb, pl->g.BD, pl->g.smem,
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "plan launch grid=%d block=%d smem=%d cluster=%d: %s (%s)", pl->g.nb, pl->g.BD, pl->g.smem, pl->g.cluster,
                  cudaGetErrorName(e), cudaGetErrorString(e));
         return MPPI_ERR_CUDA;
     }
@@ -96,19 +99,23 @@ int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_p
     ra.idle_ns = d.idle_ns;
     ra.gen = gen;
     ra.shift_pred = shift_pred;
-    ra.n_words = 3 + pl->nx * (pl->is_double ? 2 : 1) + (pl->res_xchg ? 2 : 0);
+    ra.n_words = 3 + pl->nx * (pl->is_double ? 2 : 1);
     DevInfo di;
     int rc = get_dev_info(di);
     if (rc) return rc;
+    // the resident grid has its own shape: one CTA per tile (no cluster padding) and the per-CTA-partials tail's layout
+    const int nb = a.n_tiles;
+    const MppiFusedParams& pp = pl->p;
+    const int smem = make_layout<real>(pp.variant, pp.T, pp.nu, pp.S, a.R, pl->g.BD, pl->g.BS, nb, layout_extra(0, pl->nx, 0, 0)).total;
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, pl->res_kernel));
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
-    if (pl->g.smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
+    if (smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
     CK(cudaFuncSetAttribute(pl->res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
     CK(cudaMemsetAsync(d.board, 0, MPPI_RES_BOARD_WORDS * sizeof(unsigned long long), d.stream));
     void* argv[3] = {(void*)&a, (void*)pl->mparams, (void*)&ra};
     // cooperative: every CTA is resident or the launch fails — the CTAs wait for each other through the board
-    cudaError_t e = cudaLaunchCooperativeKernel(pl->res_kernel, dim3(pl->g.nb), dim3(pl->g.BD), argv, (size_t)pl->g.smem, d.stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(pl->res_kernel, dim3(nb), dim3(pl->g.BD), argv, (size_t)smem, d.stream);
     if (e != cudaSuccess) return cuda_fail(e, "resident launch");
     return MPPI_OK;
 }
@@ -374,15 +381,13 @@ int mppi_resident_start(void* plan, void* host_box, void* board_dev, void* actio
     d.idle_ns = idle_us * 1000ull;
     d.stream = (cudaStream_t)stream;
     const ResidentBackend be{pl, resident_be_launch, resident_be_drain, resident_be_health};
-    return res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be, pl->res_xchg);
+    return res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be, 0);
 }
 
 int mppi_resident_command(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset, void* action_host_out) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
     if (pl == nullptr) return MPPI_ERR_BAD_ARG;
-    // a sharded controller advances its exchange epoch once per command, on whichever route the command takes
-    const uint64_t epoch = pl->res_xchg ? ++pl->epoch : 0;
-    return res_command(pl->res, state, (flags & MPPI_FLAG_SHIFT) ? 1 : 0, seed, offset, action_host_out, epoch);
+    return res_command(pl->res, state, (flags & MPPI_FLAG_SHIFT) ? 1 : 0, seed, offset, action_host_out, 0);
 }
 
 int mppi_resident_sync(void* plan) {
@@ -422,7 +427,10 @@ int mppi_apply_partials(const MppiFusedParams* p, const void* partials, void* st
     return MPPI_ERR_BAD_ARG;
 }
 
-uint64_t mppi_xchg_bytes(void) { return (uint64_t)2 * MPPI_MAX_RANKS * MPPI_XCHG_MAX_WORDS * sizeof(unsigned long long); }
+// two epoch parities of MPPI_XCHG_PARITY_WORDS flagged 8-byte words: world x records x 2 (R+2) words per command (the
+// fused kernel's record layout), or the stepped route's [source rank][MPPI_XCHG_MAX_WORDS] layout — both fit
+uint64_t mppi_xchg_bytes(void) { return (uint64_t)2 * MPPI_XCHG_PARITY_WORDS * sizeof(unsigned long long); }
+static_assert(MPPI_MAX_RANKS * MPPI_XCHG_MAX_WORDS <= MPPI_XCHG_PARITY_WORDS, "mailbox parity too small for the rank-record layout");
 
 int mppi_xchg_create(void** mailbox, void* ipc_handle_out_64B) {
     if (mailbox == nullptr || ipc_handle_out_64B == nullptr) return MPPI_ERR_BAD_ARG;

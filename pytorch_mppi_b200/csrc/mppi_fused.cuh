@@ -62,11 +62,15 @@ template <typename real> struct KArgs {
     real* betaP;
     real* etaP;
     real* VP;
+    double* crec;                 // cluster records (n_clusters, R+2) doubles: (beta, eta, V[R]) — overlays betaP/etaP/VP
     // multi-GPU
     unsigned long long* peers[8];
     double* partial_out;
     unsigned long long epoch;
     int rank, world, export_partial;
+    int xchg_npub;                // records each rank publishes per command: its cluster records (direct mode) or 1
+    unsigned long long xchg_timeout_ns;
+    long long* xchg_status_host;  // optional pinned host word: set to MPPI_ERR_TIMEOUT when a peer exchange timed out
     // sizes
     int K, T, S, R, TN, upc, n_tiles;
     long long k_offset;
@@ -100,9 +104,15 @@ template <typename real> struct KArgs {
 // ---- shared-memory carve, computed identically on host and device -------------------------------
 struct SmemLayout {
     int off_uraw, off_araw, off_thraw, off_us, off_as, off_ths, off_w, off_wsh, off_vrun, off_ws, off_red,
-        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, off_xs, total;
+        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, off_xs, off_wrec, off_xstage, total;
     int LD;
 };
+
+// `extra` word of make_layout: bit 0 = rows2 tile; bits 8..15 = nx of the split-cost state buffer; bits 16..19 = cluster
+// size of the warp-record area (0 = the kernel does not use the warp-fold tail); bits 20.. = doubles of exchange staging
+__host__ __device__ inline int layout_extra(int rows2, int nx_split, int cluster, int xstage_doubles) {
+    return (rows2 & 1) | (nx_split << 8) | (cluster << 16) | (xstage_doubles << 20);
+}
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
 
@@ -113,7 +123,7 @@ __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a *
 template <typename real>
 __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int BS, int nb, int extra) {
     SmemLayout L;
-    const int need_rows2 = extra & 1, nx_split = extra >> 8;
+    const int need_rows2 = extra & 1, nx_split = (extra >> 8) & 0xff, cluster = (extra >> 16) & 0xf, xstage = extra >> 20;
     const int es = (int)sizeof(real);
     const int TN = T * nu, SN = S * nu, nw = BD / 32;
     int o = 16;  // [0,8): mbarrier
@@ -137,6 +147,10 @@ __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, in
     L.off_numd = o; o = align_up(o + (R + 2) * 8, 16);
     L.off_redd = o; o = align_up(o + 64 * 8, 16);
     L.off_xs = o; o = align_up(o + T * nx_split * BS * es, 16);
+    // warp-fold tail: (cluster x rollout warps) records of (R+2) doubles — slots [0, BS/32) are this CTA's own running
+    // records, the cluster leader also receives its peers' through distributed shared memory
+    L.off_wrec = o; o = align_up(o + cluster * (BS / 32) * (R + 2) * 8, 16);
+    L.off_xstage = o; o = align_up(o + xstage * 8, 16);
     L.total = o;
     return L;
 }
@@ -223,7 +237,7 @@ template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
 template <typename real> struct Smem {
     unsigned long long* bar;
     real *Uraw, *Araw, *thraw, *Us, *As, *ths, *Ws, *Wsh, *Vrun, *w_s, *red, *part, *rows, *rows2, *sS, *xs;
-    double *part2, *numd, *redd;
+    double *part2, *numd, *redd, *wrec, *xstage;
     int LD;
     __device__ Smem(unsigned char* smem, const SmemLayout& L) {
         bar = reinterpret_cast<unsigned long long*>(smem);
@@ -246,6 +260,8 @@ template <typename real> struct Smem {
         numd = reinterpret_cast<double*>(smem + L.off_numd);
         redd = reinterpret_cast<double*>(smem + L.off_redd);
         xs = reinterpret_cast<real*>(smem + L.off_xs);
+        wrec = reinterpret_cast<double*>(smem + L.off_wrec);
+        xstage = reinterpret_cast<double*>(smem + L.off_xstage);
         LD = L.LD;
     }
 };
@@ -836,6 +852,301 @@ __device__ bool publish_and_finish(const KArgs<real>& a, Smem<real>& sm, real be
     return true;
 }
 
+
+// =================================================================================================
+// Warp-fold tail (fused_command_kernel): the softmin reduction without CTA-wide barriers in the fold, a
+// thread-block-cluster stage through distributed shared memory, and a finisher that works on a handful of records.
+//
+//   per tile   each ROLLOUT WARP folds its 32 samples into its own running record (beta_w, eta_w, V_w[R]) — shuffles
+//              only, fp64 accumulation, record in shared memory (warp-private: no barrier)
+//   per CTA    the warp records go to the cluster LEADER's shared memory (st.shared::cluster), one cluster barrier
+//   leader     combines cluster_size x warps records into ONE cluster record and publishes it: to the L2 workspace
+//              (ticket among the leaders — 16 atomics instead of 128 at BASELINE config 2), or, on a sharded controller
+//              in direct mode, straight into every peer GPU's mailbox over NVLink
+//   finisher   (last leader) combines the n_clusters (x world) records and writes the update
+// Every combination is in fixed record order and fp64, so the result does not depend on scheduling and is bit-identical
+// on all ranks of a sharded controller.   Reference lines: mppi.py:254-259, 268-270 (and the SMPPI / KMPPI forms).
+// =================================================================================================
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ void st_dsmem_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+#define MPPI_XCHG_PARITY_WORDS 65536       // 8-byte words per epoch parity of a peer mailbox (mppi_xchg_bytes = 2 x this x 8)
+
+// this CTA's running warp records: (beta = +inf, eta = 0, V = 0); call before the first barrier of the kernel
+template <typename real>
+__device__ __forceinline__ void warp_records_init(const KArgs<real>& a, Smem<real>& sm) {
+    const int RW = a.R + 2, n = (blockDim.x / a.tps >> 5) * RW;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm.wrec[i] = (i % RW == 0) ? (double)INFINITY : 0.0;
+}
+
+// ---- per tile: fold this warp's 32 samples into its running record (rollout warps only; warp-synchronous) ----------
+template <typename real, int VARIANT>
+__device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool active, int nvalid) {
+    typedef Ops<real> O;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int R = a.R, LD = sm.LD, i0 = w * 32;
+    double* rec = sm.wrec + (size_t)w * (R + 2);
+    const real nfl = a.nm.neg_inv_lambda;
+    const real cmin = warp_min<real>(active ? c_tot : O::inf());
+    const real beta_run = (real)rec[0];                 // a value of type `real`, kept in a double slot
+    const real beta_new = cmin < beta_run ? cmin : beta_run;
+    if (beta_new == O::inf()) return;                   // warp-uniform: no sample of this warp has a cost yet
+    const real wgt = active ? O::exp_(nfl * (c_tot - beta_new)) : (real)0;                       // mppi.py:12-13, 256
+    const double resc = (beta_run == O::inf()) ? 0.0 : (double)O::exp_(nfl * (beta_run - beta_new));
+    const double eta_tile = warp_sum<double>((double)wgt);
+    const int nv = min(32, nvalid - i0);
+    for (int jb = 0; jb < R; jb += 32) {
+        const int j = jb + lane;
+        const bool jv = j < R;
+        const int jc = jv ? j : 0;
+        const real us = (VARIANT == V_KMPPI) ? (real)0 : sm.Us[jc];
+        const real a2 = VARIANT == V_SMPPI ? sm.As[jc] : (VARIANT == V_KMPPI ? sm.ths[jc] : (real)0);
+        const real* row = sm.rows + (size_t)jc * LD + i0;
+        double acc = 0.0;
+        for (int i = 0; i < nv; ++i) {
+            const real wi = __shfl_sync(0xffffffffu, wgt, i);
+            acc += (double)(wi * eps_of<real, VARIANT>(a.nm, row[i], us, a2));                  // mppi.py:268
+        }
+        if (jv) rec[2 + j] = rec[2 + j] * resc + acc;
+    }
+    if (lane == 0) {
+        rec[0] = (double)beta_new;
+        rec[1] = rec[1] * resc + eta_tile;
+    }
+    __syncwarp();
+}
+
+// ---- fixed-order fp64 combination of records (beta_q, eta_q, V_q[R]) -----------------------------------------------
+//   beta = min beta_q ; s_q = exp(nfl (beta_q - beta)) ; eta = sum s_q eta_q ; V[j] = sum s_q V_q[j]
+// Warp-synchronous.  ld(q, i) returns element i of record q.  The calling warp produces rows j = jb + lane for
+// jb = row0, row0 + rstep, ... < R through out(j, value); beta and eta are returned to every lane.
+template <class Load, class Out>
+__device__ __forceinline__ void combine_records(Load ld, Out out, int nrec, int R, double nfl, int row0, int rstep, double& beta,
+                                                double& eta) {
+    const int lane = threadIdx.x & 31;
+    double b = (double)INFINITY;
+    for (int q = lane; q < nrec; q += 32) b = fmin(b, ld(q, 0));
+    beta = warp_min<double>(b);
+    double el = 0.0;
+    for (int q = lane; q < nrec; q += 32) el += exp(nfl * (ld(q, 0) - beta)) * ld(q, 1);
+    eta = warp_sum<double>(el);
+    for (int jb = row0; jb < R; jb += rstep) {
+        const int j = jb + lane;
+        const bool jv = j < R;
+        const int jc = jv ? j : 0;
+        double acc = 0.0;
+        for (int qb = 0; qb < nrec; qb += 32) {
+            const int q = qb + lane;
+            const double s_mine = q < nrec ? exp(nfl * (ld(q, 0) - beta)) : 0.0;
+            const int n = min(32, nrec - qb);
+#pragma unroll 8
+            for (int u = 0; u < n; ++u) {
+                const double sq = __shfl_sync(0xffffffffu, s_mine, u);
+                acc += sq * ld(qb + u, 2 + jc);
+            }
+        }
+        if (jv) out(j, acc);
+    }
+}
+
+// ---- peer mailboxes: records of (R+2) doubles as LL words (payload32 | flag32), record r at word r * 2 (R+2) -------
+template <typename real>
+__device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int rec_index, const double* src) {
+    const int nwords = 2 * (a.R + 2);
+    const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
+    const size_t off = (size_t)(a.epoch & 1ull) * MPPI_XCHG_PARITY_WORDS + (size_t)rec_index * nwords;
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(src[i >> 1]);
+        const uint32_t half = (i & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
+        const unsigned long long word = ((unsigned long long)flag << 32) | half;
+        for (int g = 0; g < a.world; ++g) st_peer(a.peers[g] + off + i, word);
+    }
+}
+// all threads of the CTA; nrec records from this rank's own mailbox into sm.xstage (doubles).  Returns 0, or 1 on timeout.
+template <typename real>
+__device__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int nrec) {
+    const int nwords = nrec * 2 * (a.R + 2);
+    const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
+    const unsigned long long* mine = a.peers[a.rank] + (size_t)(a.epoch & 1ull) * MPPI_XCHG_PARITY_WORDS;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.xstage);
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    unsigned long long t0 = 0;
+    for (int e = threadIdx.x; e < nwords; e += blockDim.x) {
+        unsigned long long rec;
+        unsigned int spins = 0;
+        while (true) {
+            rec = ld_poll(mine + e);
+            if ((uint32_t)(rec >> 32) == flag) break;
+            if ((++spins & 1023u) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                if (now - t0 > a.xchg_timeout_ns || s_timeout) { s_timeout = 1; break; }
+            }
+        }
+        dst[e] = (uint32_t)rec;
+    }
+    __syncthreads();
+    return s_timeout;
+}
+
+// a peer never delivered: report it (device stats, pinned host word) and return a DEFINED action — the nominal the
+// command sampled around, not updated.  This rank's U then lags its peers by one update: the host raises on the next
+// command (mppi.py reads the status word), it does not continue silently.
+template <typename real, int VARIANT>
+__device__ void xchg_timed_out(const KArgs<real>& a, Smem<real>& sm, int nu) {
+    const real* nom = VARIANT == V_SMPPI ? sm.As : sm.Us;
+    for (int j = threadIdx.x; j < a.upc * nu; j += blockDim.x) {
+        a.action_out[j] = nom[j];
+        if (a.host_mailbox != nullptr) host_store<real>(a.host_mailbox, j, nom[j], a.host_epoch);
+    }
+    if (threadIdx.x == 0) {
+        a.stats[3] = -6.0;     // MPPI_ERR_TIMEOUT
+        if (a.xchg_status_host != nullptr) {
+            *reinterpret_cast<volatile long long*>(a.xchg_status_host) = -6;
+            __threadfence_system();
+        }
+        *a.ticket = 0u;
+    }
+}
+
+// ---- the tail: returns true in the CTA that finished the command --------------------------------------------------
+template <typename real, int VARIANT, int NU>
+__device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
+    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
+    const int R = a.R, RW = R + 2;
+    const int nrw = (BD / a.tps) >> 5;                       // rollout warps = records per CTA
+    const int cs = (int)cluster_nctarank();                  // cluster dims are (cs, 1, 1)
+    const int cr = blockIdx.x % cs, cid = blockIdx.x / cs, NC = gridDim.x / cs;
+    const double nfl = (double)a.nm.neg_inv_lambda;
+    const bool sharded = a.world > 1 && !a.export_partial;
+    const bool direct = sharded && a.xchg_npub > 1;          // cluster records go straight to the peers
+    __shared__ int s_is_last;
+
+    // (1) warp records -> the cluster leader's shared memory
+    if (cs > 1) {
+        if (cr != 0 && warp < nrw) {
+            const uint32_t dst = mapa_shared(smem_u32(sm.wrec), 0) + (uint32_t)(((cr * nrw + warp) * RW) * 8);
+            const double* rec = sm.wrec + (size_t)warp * RW;
+            for (int i = lane; i < RW; i += 32) st_dsmem_f64(dst + i * 8, rec[i]);
+        }
+        cluster_arrive_release();
+        if (cr != 0) return false;
+        cluster_wait_acquire();
+    } else {
+        __syncthreads();
+    }
+    stamp(a.dbg, 6);
+
+    // (2) leader: cs x nrw warp records -> one cluster record in sm.numd
+    {
+        const double* recs = sm.wrec;
+        double beta, eta;
+        auto ld = [&](int q, int i) { return recs[(size_t)q * RW + i]; };
+        auto out = [&](int j, double v) { sm.numd[2 + j] = v; };
+        if (warp == 0 || warp * 32 < R) {
+            combine_records(ld, out, cs * nrw, R, nfl, warp * 32, nw * 32, beta, eta);
+            if (tid == 0) {
+                sm.numd[0] = beta;
+                sm.numd[1] = eta;
+            }
+        }
+    }
+    __syncthreads();
+    // (3) publish the cluster record; ticket among the leaders of this GPU
+    if (direct) {
+        xchg_publish<real>(a, a.rank * NC + cid, sm.numd);
+    } else if (NC > 1) {
+        for (int i = tid; i < RW; i += BD) a.crec[(size_t)cid * RW + i] = sm.numd[i];
+    }
+    if (NC > 1) {
+        __syncthreads();        // every thread's stores precede thread 0's release (one MEMBAR per leader)
+        if (tid == 0) {
+            unsigned int t;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(t) : "l"(a.ticket), "r"(1u) : "memory");
+            s_is_last = (t == (unsigned int)NC - 1);
+        }
+        __syncthreads();
+        if (!s_is_last) return false;
+        if (tid == 0) *a.ticket = 0u;   // self-reset: the next launch needs no memset
+    }
+    stamp(a.dbg, 8);
+
+    // (4) finisher: the rank's records -> (beta, eta, numerators) in sm.numd
+    if (!direct && NC > 1) {
+        const double* recs = a.crec;
+        double beta, eta;
+        auto ld = [&](int q, int i) { return __ldcg(recs + (size_t)q * RW + i); };
+        auto out = [&](int j, double v) { sm.numd[2 + j] = v; };
+        if (warp == 0 || warp * 32 < R) {
+            combine_records(ld, out, NC, R, nfl, warp * 32, nw * 32, beta, eta);
+            if (tid == 0) {
+                sm.numd[0] = beta;
+                sm.numd[1] = eta;
+            }
+        }
+        __syncthreads();
+    }
+    stamp(a.dbg, 10);
+    if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
+        const int TN = a.TN;
+        for (int j = tid; j < RW; j += BD) a.partial_out[j] = sm.numd[j];
+        for (int j = tid; j < TN; j += BD) {
+            a.nominal_used[j] = sm.Us[j];
+            if (VARIANT == V_SMPPI) a.nominal_used[TN + j] = sm.As[j];
+        }
+        if (VARIANT == V_KMPPI)
+            for (int j = tid; j < R; j += BD) a.nominal_used[2 * TN + j] = sm.ths[j];
+        if (tid == 0) {
+            a.stats[0] = sm.numd[0];
+            a.stats[1] = sm.numd[1];
+            a.stats[3] = 0.0;
+        }
+        return true;
+    }
+    if (sharded) {
+        // rank-record mode: this rank's combined record is its one published record; direct mode: the cluster
+        // records of every rank are already on their way
+        if (!direct) xchg_publish<real>(a, a.rank, sm.numd);
+        const int nrec = a.world * (direct ? NC : 1);
+        if (xchg_collect<real>(a, sm, nrec)) {
+            xchg_timed_out<real, VARIANT>(a, sm, NU);
+            return true;
+        }
+        const double* recs = sm.xstage;
+        double beta, eta;
+        auto ld = [&](int q, int i) { return recs[(size_t)q * RW + i]; };
+        auto out = [&](int j, double v) { sm.numd[2 + j] = v; };
+        if (warp == 0 || warp * 32 < R) {
+            combine_records(ld, out, nrec, R, nfl, warp * 32, nw * 32, beta, eta);
+            if (tid == 0) {
+                sm.numd[0] = beta;
+                sm.numd[1] = eta;
+            }
+        }
+        __syncthreads();
+    }
+    stamp(a.dbg, 11);
+    finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);
+    if (tid == 0) a.stats[3] = 0.0;
+    return true;
+}
+
 // ---- per-environment view of the kernel arguments (batched launches) -------------------------------
 // The argument block lives in constant (parameter) space; a batched CTA needs its environment's
 // pointers, so it builds an adjusted copy in shared memory once and every stage reads that copy.
@@ -861,6 +1172,7 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
             out->betaP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.betaP) + off);
             out->etaP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.etaP) + off);
             out->VP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.VP) + off);
+            out->crec = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(in.crec) + off);
         }
         if (in.out_pa) out->out_pa = in.out_pa + e * K * TN;
         if (in.out_noise) out->out_noise = in.out_noise + e * K * TN;
@@ -874,11 +1186,7 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
 // ---- stage C', split-cost rollout as a function: recurrence on the rollout thread | running costs on all tps
 // threads of the sample | ordered sum.  Returns the sample's total cost on its rollout thread (+inf elsewhere) and
 // stores it to cost_total[k].  Contains two CTA barriers: every thread must call it.
-// This is the SAME code as the `if constexpr (SPLIT)` block of fused_command_kernel, kept as a second copy on purpose:
-// calling the function from that kernel changes ptxas' register allocation of the default kernel at BASELINE
-// config 2 (checked with cuobjdump), and that kernel's SASS is the one every GPU measurement of round 1 was taken
-// on.  The resident kernel (mppi_resident.cuh) uses this copy; tests/test_gpu_resident.py checks both against each
-// other bit for bit.
+// Shared by fused_command_kernel<..., SPLIT = true> and the resident kernel (mppi_resident.cuh).
 template <class Model, typename real, int VARIANT>
 __device__ __forceinline__ real split_cost_rollout(const KArgs<real>& a, const typename Model::template P<real>& mp, Smem<real>& sm,
                                                    int k, unsigned long long kg, bool in_range, bool active) {
@@ -976,10 +1284,13 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
     if (BATCHED) make_env_args<real, NX, NU>(a_in, reinterpret_cast<KArgs<real>*>(a_env_raw));
     const KArgs<real>& a = BATCHED ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, SPLIT ? (NX << 8) : 0);
+    const int xst = (a.world > 1 && !a.export_partial) ? a.world * a.xchg_npub * (a.R + 2) : 0;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1,
+                                           layout_extra(0, SPLIT ? NX : 0, (int)cluster_nctarank(), xst));
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
+    warp_records_init<real>(a, sm);      // published by the barrier in stage_issue
 
     stamp(a.dbg, 0);
     // Programmatic dependent launch: this grid may be resident while the previous kernel on the stream is
@@ -996,7 +1307,6 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
     stamp(a.dbg, 1);
     bool staged = false;
 
-    real beta_run = O::inf(), eta_run = (real)0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int k = tile * BS + (tid % BS);
         const bool in_range = k < a.K;
@@ -1019,67 +1329,7 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
         real c_tot = O::inf();
         if constexpr (SPLIT) {
             // C'. split rollout: recurrence (rollout thread) | running costs (all tps threads) | ordered sum
-            real* xcol = sm.xs + (tid % BS);
-            real x[NX];
-            real pert = (real)0, smooth = (real)0;
-            if (active) {
-                if (a.state_dev != nullptr) {
-                    const real* sp = a.state_dev + (a.state_per_sample ? (size_t)k * NX : 0);
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) x[i] = sp[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) x[i] = a.x0[i];
-                }
-                real vprev[NU];
-#pragma unroll
-                for (int n = 0; n < NU; ++n) vprev[n] = (real)0;
-MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
-                for (int t = 0; t < T; ++t) {
-                    real v[NU], u[NU], eps[NU];
-                    action_at<real, VARIANT, NU>(a, sm, kg, t, v);
-                    noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
-#pragma unroll
-                    for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
-                    Model::template step<real>(mp, x, u);                                     // mppi.py:314
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) xcol[(t * NX + i) * BS] = x[i];
-                    pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
-                    if (VARIANT == V_SMPPI) {
-                        if (t > 0) {
-#pragma unroll
-                            for (int n = 0; n < NU; ++n) {
-                                const real d = O::mul(nm.u_scale, O::sub(v[n], vprev[n]));    // mppi.py:559
-                                smooth = O::add(smooth, O::mul(d, d));
-                            }
-                        }
-#pragma unroll
-                        for (int n = 0; n < NU; ++n) vprev[n] = v[n];
-                    }
-                }
-            }
-            __syncthreads();
-            if (in_range) {
-MPPI_UNROLL_N(2)
-                for (int t = tid / BS; t < T; t += a.tps) {      // independent across t: two in flight per thread
-                    real v[NU], u[NU], xt[NX];
-                    action_at<real, VARIANT, NU>(a, sm, kg, t, v);
-#pragma unroll
-                    for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) xt[i] = xcol[(t * NX + i) * BS];
-                    xcol[(t * NX) * BS] = Model::template cost<real>(mp, xt, u);              // mppi.py:318
-                }
-            }
-            __syncthreads();
-            if (active) {
-                real roll = (real)0;
-                for (int t = 0; t < T; ++t) roll = O::add(roll, xcol[(t * NX) * BS]);         // mppi.py:319, t = 0..T-1
-                if (Model::template has_terminal<real>(mp)) roll = O::add(roll, Model::template terminal<real>(mp, x));
-                c_tot = O::add(roll, pert);                                                   // mppi.py:416
-                if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569
-                a.cost_total[k] = c_tot;
-            }
+            c_tot = split_cost_rollout<Model, real, VARIANT>(a, mp, sm, k, kg, in_range, active);
         } else if (active) {
 
             // C. rollout (mppi.py:297-332) + action cost (mppi.py:409,415) [+ smoothness :559-562]
@@ -1139,13 +1389,14 @@ MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
             if (VARIANT == V_SMPPI) c_tot = O::add(c_tot, O::mul(smooth, nm.w_smooth));   // mppi.py:562,569
             a.cost_total[k] = c_tot;
         }
-        real w_unused;
         if (tile == blockIdx.x) stamp(a.dbg, 4);
-        fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+        // D. every rollout warp folds its 32 samples into its own running record (no CTA barrier)
+        if (tid < BS) warp_fold<real, VARIANT>(a, sm, c_tot, active, nvalid);
         if (tile == blockIdx.x) stamp(a.dbg, 5);
+        if (tile + (int)gridDim.x < a.n_tiles) __syncthreads();      // the tile is refilled by the next pass
     }
     if (!staged) stage_finish<real, VARIANT, NU>(a, sm);
-    publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+    warp_tail<real, VARIANT, NU>(a, sm);
     stamp(a.dbg, 7);
 }
 

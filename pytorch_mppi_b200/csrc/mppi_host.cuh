@@ -25,6 +25,8 @@ extern thread_local char g_cuda_err[512];
 
 struct Geometry {
     int BD, BS, tps, nb, smem, occ, regs;   // BD = BS * tps threads per CTA, BS samples per tile
+    int cluster;                            // thread-block-cluster size of the launch (1: none); nb is a multiple of it
+    int npub;                               // sharded controllers: records published per rank and command (0: not sharded)
 };
 
 // Resident mode: the host side of the protocol (struct Resident, res_*) is csrc/mppi_resident_host.h; this file supplies its
@@ -41,7 +43,7 @@ struct Plan {
     MppiFusedParams p;
     const void* kernel;
     const void* res_kernel;            // resident_command_kernel<Model, real, V, sharded>, or nullptr when this plan cannot run resident
-    int res_xchg;                      // the plan is one shard of a multi-GPU controller: records carry the exchange epoch
+    int res_xchg;                      // always 0 (resident mode serves single-GPU controllers)
     Resident res;
     ResidentDevice resdev;
     Geometry g;
@@ -139,8 +141,20 @@ template <typename real> void fill_noise_model(const MppiFusedParams* p, NoiseMo
     nm.abs_cost = (p->flags & MPPI_FLAG_ABS_COST) ? 1 : 0;
 }
 
+// ticket + per-CTA partials (beta_b, eta_b, V_b[R]) of type `real` (stepped-route / resident / tensor-core tails), or
+// ticket + per-cluster records of (R + 2) doubles (fused kernel's warp-fold tail): the larger of the two
 inline uint64_t ws_bytes(int nb, int R, int es) {
-    return 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
+    const uint64_t per_cta = 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
+    const uint64_t per_cluster = 16 + (uint64_t)nb * (uint64_t)(R + 2) * 8;
+    return per_cta > per_cluster ? per_cta : per_cluster;
+}
+
+inline unsigned long long xchg_timeout_ns() {
+    // how long a shard waits for its peers' records before giving up (rank skew: a GC pause, a JIT build, a lazy module
+    // load on another rank); MPPI_B200_XCHG_TIMEOUT_S overrides the 20 s default
+    const char* e = getenv("MPPI_B200_XCHG_TIMEOUT_S");
+    double sec = (e != nullptr && atof(e) > 0) ? atof(e) : 20.0;
+    return (unsigned long long)(sec * 1e9);
 }
 
 template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a, int BS, int nb, int tps = 1) {
@@ -185,7 +199,11 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
         a.betaP = (real*)(w + 16);
         a.etaP = (real*)(w + 16 + align_up(nb * es, 16));
         a.VP = (real*)(w + 16 + 2 * align_up(nb * es, 16));
+        a.crec = (double*)(w + 16);
     }
+    a.xchg_npub = 1;
+    a.xchg_timeout_ns = xchg_timeout_ns();
+    a.xchg_status_host = (long long*)p->xchg_status_host;
     a.rank = p->rank;
     a.world = p->world <= 0 ? 1 : p->world;
     a.epoch = p->epoch;
@@ -209,19 +227,37 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
     return MPPI_OK;
 }
 
-inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cudaStream_t stream, void** argv, bool pdl, int ny = 1) {
-    if (!pdl) return cudaLaunchKernel(kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
-    cudaLaunchConfig_t cfg;
+// launch configuration with the optional attributes: programmatic dependent launch, thread-block clusters (cluster, 1, 1)
+inline void launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int nb, int BD, int smem, cudaStream_t stream, bool pdl,
+                          int ny, int cluster) {
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(nb, ny);
     cfg.blockDim = dim3(BD);
     cfg.dynamicSmemBytes = (size_t)smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    int n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = (unsigned)cluster;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = n;
+}
+
+inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cudaStream_t stream, void** argv, bool pdl, int ny = 1,
+                              int cluster = 1) {
+    if (!pdl && cluster <= 1) return cudaLaunchKernel(kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[2];
+    launch_config(cfg, at, nb, BD, smem, stream, pdl, ny, cluster);
     return cudaLaunchKernelExC(&cfg, kernel, argv);
 }
 
@@ -373,6 +409,8 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
     g.smem = L.total;
     g.occ = occ;
     g.regs = fa.numRegs;
+    g.cluster = 1;
+    g.npub = 0;
     (void)es;
     keys[next_slot] = key;
     vals[next_slot] = g;

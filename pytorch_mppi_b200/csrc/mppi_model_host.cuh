@@ -38,69 +38,131 @@ bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, K
     return false;
 }
 
-// MPPI_FLAG_SPLIT_COST: problems small enough to run with helper threads (threads_per_sample > 1) may take the
-// split-cost rollout (fused_command_kernel<..., SPLIT = true>) if its per-step state buffer fits in shared memory;
-// the geometry stays the one chosen for the plain kernel.
-template <class Model, typename real, int V, typename KernelT>
-void select_split_cost_rollout(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& split) {
-    split = 0;
-    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
-        if (!eligible || !(p->flags & MPPI_FLAG_SPLIT_COST) || g.tps <= 1) return;
-        KernelT k2 = fused_command_kernel<Model, real, V, false, true>;
-        MppiFusedParams p2 = *p;
-        p2.block_threads = g.BS;
-        p2.threads_per_sample = g.tps;
-        p2.grid_blocks = g.nb;
-        Geometry g2;
-        if (plan_geometry(k2, &p2, (int)sizeof(real), Model::NX << 8, false, g2, layout_fn<real>) != MPPI_OK) return;
-        if (g2.BS != g.BS || g2.tps != g.tps) return;
-        kernel = k2;
-        g = g2;
-        split = 1;
+// ---- kernel + launch geometry of one fused command -------------------------------------------------------------------
+// What is decided here, once per plan (or per mppi_fused_command call):
+//   kernel     fused_command_kernel<Model, real, V, batched, split>  (or the tcgen05 kernel, select_tensor_core_route)
+//   geometry   tile size / helper threads / grid (plan_geometry), planned for K_geom samples on sharded controllers so
+//              that every rank launches the same grid
+//   split      MPPI_FLAG_SPLIT_COST honoured: problems small enough to run with helper threads (threads_per_sample > 1)
+//              take the split-cost rollout if its per-step state buffer fits in shared memory
+//   cluster    thread-block-cluster size of the warp-fold tail: 8 / 4 / 2 when the whole grid is one wave of at most
+//              one CTA per SM and all its clusters are co-resident (cudaOccupancyMaxActiveClusters), else 1
+//   npub       sharded controllers: the records a rank publishes to its peers per command — its cluster records when
+//              their staging (world x clusters x (R+2) doubles) is small (direct mode), else its one combined record
+struct FusedChoice {
+    const void* kernel;
+    Geometry g;
+    int split, wide, tc;
+};
+
+template <class Model, typename real, int V>
+int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& c) {
+    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+    const bool batched = p->n_env > 1;
+    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
+    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
+    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
+    if (tc_route) p = &p_tc;
+    const int R = rows_of(p), es = (int)sizeof(real);
+    const int world = p->world <= 0 ? 1 : p->world;
+    bool any_peer = false;
+    for (int g = 0; g < MPPI_MAX_RANKS; ++g) any_peer = any_peer || p->peer_slots[g] != nullptr;
+    const bool sharded = world > 1 && any_peer && !(p->flags & MPPI_FLAG_EXPORT_PARTIAL);
+    MppiFusedParams pg = *p;
+    if (p->K_geom > p->K) pg.K = p->K_geom;
+    Geometry g;
+    int rc;
+    if (tc_route) {
+        rc = plan_geometry(kernel, &pg, es, 0, false, g, layout_fn<real>);
+        g_tc_kernel = 0;
+        if (rc) return rc;
+        c = FusedChoice{(const void*)kernel, g, 0, 0, 1};
+        return MPPI_OK;
     }
+    const int xst1 = sharded ? world * (R + 2) : 0;          // staging of the rank-record exchange
+    rc = plan_geometry(kernel, &pg, es, layout_extra(0, 0, 1, xst1), true, g, layout_fn<real>);
+    if (rc) return rc;
+    int split = 0;
+    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
+        if (!batched && (p->flags & MPPI_FLAG_SPLIT_COST) && g.tps > 1) {
+            auto k2 = fused_command_kernel<Model, real, V, false, true>;
+            MppiFusedParams p2 = pg;
+            p2.block_threads = g.BS;
+            p2.threads_per_sample = g.tps;
+            p2.grid_blocks = g.nb;
+            Geometry g2;
+            if (plan_geometry(k2, &p2, es, layout_extra(0, Model::NX, 1, xst1), true, g2, layout_fn<real>) == MPPI_OK &&
+                g2.BS == g.BS && g2.tps == g.tps) {
+                kernel = k2;
+                g = g2;
+                split = 1;
+            }
+        }
+    }
+    // ---- cluster size and exchange mode ------------------------------------------------------------------------------
+    DevInfo di;
+    rc = get_dev_info(di);
+    if (rc) return rc;
+    int want = 8;
+    if (const char* e = getenv("MPPI_B200_CLUSTER")) want = atoi(e);
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, (const void*)kernel));
+    const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
+    const int envs = batched ? p->n_env : 1;
+    g.cluster = 1;
+    g.npub = sharded ? 1 : 0;
+    for (int cs = 8; cs >= 1; cs >>= 1) {
+        if (cs > want && cs > 1) continue;
+        const int nbp = (g.nb + cs - 1) / cs * cs;
+        if (cs > 1 && (nbp > di.sm_count || g.nb < 2)) continue;          // one wave, at most one CTA per SM
+        const int NC = nbp / cs;
+        // direct mode: every rank's cluster records are staged by the finisher (world x NC x (R+2) doubles)
+        int npub = sharded ? 1 : 0;
+        if (sharded && NC > 1 && (long long)world * NC * (R + 2) * 8 <= 49152 && (long long)world * NC * 2 * (R + 2) <= MPPI_XCHG_PARITY_WORDS)
+            npub = NC;
+        if (const char* e = getenv("MPPI_B200_XCHG_DIRECT"))
+            if (atoi(e) == 0 && sharded) npub = 1;
+        const int xst = sharded ? world * npub * (R + 2) : 0;
+        const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, 1, layout_extra(0, split ? Model::NX : 0, cs, xst));
+        if (L.total > dyn_limit) continue;
+        if (cs > 1) {
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute at[2];
+            launch_config(cfg, at, nbp, g.BD, L.total, nullptr, (p->flags & MPPI_FLAG_PDL) != 0, envs, cs);
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kernel, &cfg) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
+            if (max_clusters < NC * envs) continue;                       // a cluster left for a second wave doubles the time
+        }
+        g.cluster = cs;
+        g.nb = nbp;
+        g.smem = L.total;
+        g.npub = npub;
+        break;
+    }
+    c = FusedChoice{(const void*)kernel, g, split, 0, 0};
+    return MPPI_OK;
 }
 
-// MPPI_FLAG_WIDE_REGS: a launch that puts at most one CTA on an SM can afford the instantiation compiled without the
-// 64-register cap (fused_command_kernel<..., SPLIT = false, MINB = 1>: no spills in the last-CTA tail).
-template <class Model, typename real, int V, typename KernelT>
-void select_wide_register_kernel(const MppiFusedParams* p, bool eligible, KernelT& kernel, Geometry& g, int& wide) {
-    wide = 0;
-    if (!eligible || !(p->flags & MPPI_FLAG_WIDE_REGS)) return;
-    DevInfo di;
-    if (get_dev_info(di) != MPPI_OK || g.nb > di.sm_count) return;
-    KernelT k2 = fused_command_kernel<Model, real, V, false, false, 1>;
-    MppiFusedParams p2 = *p;
-    p2.block_threads = g.BS;
-    p2.threads_per_sample = g.tps;
-    p2.grid_blocks = g.nb;
-    Geometry g2;
-    if (plan_geometry(k2, &p2, (int)sizeof(real), 0, false, g2, layout_fn<real>) != MPPI_OK) return;
-    if (g2.BS != g.BS || g2.tps != g.tps || g2.nb != g.nb) return;
-    kernel = k2;
-    g = g2;
-    wide = 1;
+template <typename real> void finish_kargs(const MppiFusedParams* p, const FusedChoice& c, KArgs<real>& a) {
+    fill_kargs<real>(p, a, c.g.BS, c.g.nb, c.g.tps);
+    a.xchg_npub = c.g.npub > 0 ? c.g.npub : 1;
 }
 
 template <class Model, typename real, int V>
 int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
     const bool batched = p->n_env > 1;
-    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
     if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
-    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
     MppiFusedParams p_tc;
-    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
-    if (tc_route) p = &p_tc;
-    Geometry g;
-    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, g, layout_fn<real>);
-    g_tc_kernel = 0;
+    FusedChoice c;
+    int rc = choose_fused<Model, real, V>(p, p_tc, c);
     if (rc) return rc;
-    int split = 0, wide = 0;
-    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, g, split);
-    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, g, wide);
+    const Geometry& g = c.g;
     const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
     KArgs<real> a;
-    fill_kargs<real>(p, a, g.BS, g.nb, g.tps);
+    finish_kargs<real>(p, c, a);
     if (info != nullptr) {
         DevInfo di;
         get_dev_info(di);
@@ -114,8 +176,10 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
         // report the worst case so one allocation serves any later geometry for these dimensions
         info->workspace_bytes = ws_bytes(di.sm_count * 16, rows_of(p), (int)sizeof(real));
         info->tma_staging = a.tma_ok;
-        info->split_cost = split;
-        info->wide_regs = wide;
+        info->split_cost = c.split;
+        info->wide_regs = c.wide;
+        info->cluster_size = g.cluster;
+        info->xchg_records = g.npub;
         return MPPI_OK;
     }
     if (p->U == nullptr || p->cost_total == nullptr || p->action_out == nullptr || p->nominal_used == nullptr ||
@@ -130,7 +194,7 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
     void* argv2[2] = {(void*)&a, (void*)&mp};
-    cudaError_t e = launch_raw((const void*)kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env);
+    cudaError_t e = launch_raw(c.kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env, g.cluster);
     if (e != cudaSuccess) return cuda_fail(e, "fused launch");
     return MPPI_OK;
 }
@@ -147,42 +211,33 @@ int run_fused_variant(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* 
 
 
 template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
     const bool batched = p->n_env > 1;
-    if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
-    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
     MppiFusedParams p_tc;
-    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
-    if (tc_route) p = &p_tc;
-    int rc = plan_geometry(kernel, p, (int)sizeof(real), 0, false, pl->g, layout_fn<real>);
-    g_tc_kernel = 0;
+    FusedChoice c;
+    int rc = choose_fused<Model, real, V>(p, p_tc, c);
     if (rc) return rc;
-    int split = 0, wide = 0;
-    select_split_cost_rollout<Model, real, V>(p, !tc_route && !batched, kernel, pl->g, split);
-    select_wide_register_kernel<Model, real, V>(p, !tc_route && !batched && !split, kernel, pl->g, wide);
+    pl->g = c.g;
     if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
         return MPPI_ERR_BAD_ARG;
     if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
     static_assert(sizeof(typename Model::template P<real>) <= sizeof(pl->mparams), "model parameter block too large");
     KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
-    fill_kargs<real>(p, *a, pl->g.BS, pl->g.nb, pl->g.tps);
+    finish_kargs<real>(p, c, *a);
     if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
     Model::template load<real>(*mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    pl->kernel = (const void*)kernel;
+    pl->kernel = c.kernel;
     pl->res_kernel = nullptr;
     pl->res_xchg = 0;
     if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {
-        // resident mode runs the split-cost rollout with one tile per CTA: exactly the plans that took it; a sharded
-        // controller (in-kernel NVLink exchange) gets the instantiation whose records carry the exchange epoch
-        if (split && !batched && !a->export_partial && pl->g.nb == a->n_tiles)
-            pl->res_kernel = a->world > 1 ? (const void*)resident_command_kernel<Model, real, V, true>
-                                          : (const void*)resident_command_kernel<Model, real, V, false>;
-        pl->res_xchg = a->world > 1 ? 1 : 0;
+        // resident mode runs the split-cost rollout with one tile per CTA: exactly the single-GPU plans that took it
+        // (the resident grid is a cooperative launch without clusters; it carries its own tail, mppi_resident.cuh)
+        if (c.split && !batched && !a->export_partial && a->world == 1 && a->n_tiles <= pl->g.nb)
+            pl->res_kernel = (const void*)resident_command_kernel<Model, real, V>;
         // the one instantiation with %globaltimer stamps (a profiling aid, scripts/resident_timeline.py)
         if constexpr (std::is_same<Model, PendulumModel>::value && std::is_same<real, float>::value && V == V_MPPI) {
-            if (pl->res_kernel != nullptr && !pl->res_xchg && p->debug_clocks != nullptr)
-                pl->res_kernel = (const void*)resident_command_kernel<Model, real, V, false, true>;
+            if (pl->res_kernel != nullptr && p->debug_clocks != nullptr)
+                pl->res_kernel = (const void*)resident_command_kernel<Model, real, V, true>;
         }
     }
     pl->is_double = sizeof(real) == 8;

@@ -27,10 +27,8 @@
 // other spin loop carries the same clock check with a margin.  Launched cooperatively, so all CTAs are resident or
 // the launch fails.  One tile per CTA (the small-problem geometry the split-cost rollout serves).
 //
-// XCHG = true is the instantiation for controllers sharded over the GPUs of one box (in-kernel NVLink exchange,
-// exchange_partials in the shared tail): every rank's host posts its own record, which then also carries the exchange
-// epoch (two more words after the state).  XCHG = false compiles to the single-GPU kernel validated in round 1
-// (byte-identical SASS, checked with cuobjdump); the sharded instantiation is opt-in until it has run on two GPUs.
+// Single-GPU controllers only (a sharded controller's ranks would each need their own host record in lock-step; the
+// launch route with its in-kernel NVLink exchange serves them).
 //
 // Reference lines replaced: the same as fused_command_kernel (mppi.py:232-275, 297-417 and the SMPPI / KMPPI forms).
 #pragma once
@@ -39,7 +37,7 @@
 
 namespace mppi {
 
-#define MPPI_RES_MAX_WORDS 32             // command record: 3 + nx (f32) or 3 + 2 nx (f64) words (+ 2: exchange epoch, XCHG)
+#define MPPI_RES_MAX_WORDS 32             // command record: 3 + nx (f32) or 3 + 2 nx (f64) words
 #define MPPI_RES_BOARD_DONE 64            // board[64] = seq of the last finished command
 #define MPPI_RES_BOARD_WORDS 128
 #define MPPI_RES_CMD_SHIFT 1u
@@ -103,7 +101,7 @@ __device__ __forceinline__ void resident_prepare(const KArgs<real>& a, Smem<real
 //   14 previous update visible | 0 prepared, polling | 13 (CTA 0) record seen in host memory | 1 record seen by this CTA |
 //   2 decoded | 3 rolled out | 4 folded | 6 ticket taken | 8, 10, 11 finisher: partials acquired, eta, numerators |
 //   12 finisher: action stored, fence done, done word written.   scripts/resident_timeline.py reads them.
-template <class Model, typename real, int VARIANT, bool XCHG = false, bool STAMPS = false>
+template <class Model, typename real, int VARIANT, bool STAMPS = false>
 __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                                   const __grid_constant__ typename Model::template P<real> mp,
                                                                   const __grid_constant__ ResidentArgs ra) {
@@ -132,7 +130,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             if (!STAMPS) a.dbg = nullptr;
             a.offset_dev = nullptr;
             a.state_dev = nullptr;
-            if (!XCHG) a.world = 1;
+            a.world = 1;
             a.export_partial = 0;
             a.offset = ra.offset_pred;
             a.shift = ra.shift_pred;
@@ -218,7 +216,6 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             a.host_epoch = seq + 1;
             uint32_t* x0w = reinterpret_cast<uint32_t*>(a.x0);
             for (int i = 0; i < NX * WPV; ++i) x0w[i] = s_cmd[3 + i];
-            if (XCHG) a.epoch = (unsigned long long)s_cmd[3 + NX * WPV] | ((unsigned long long)s_cmd[4 + NX * WPV] << 32);
         }
         __syncthreads();
         if (offset != offset_pred || shift != shift_pred) resident_prepare<real, VARIANT, NU>(a, sm, in_range, kg, nvalid);

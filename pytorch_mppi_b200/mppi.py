@@ -182,14 +182,7 @@ class MPPI:
         self._pdl = os.environ.get("MPPI_B200_PDL", "1") != "0"
         # split-cost rollout for problems that run with helper threads: measured 17.1 -> 14.8 us per command back to
         # back at K=16384, T=30 (bit-identical results); MPPI_B200_SPLIT_COST=0 selects the single-loop kernel
-        # (=2 also selects it on multi-GPU controllers, which otherwise stay on the single-loop kernel: that combination
-        # has not been run on two GPUs yet)
-        _mode = os.environ.get("MPPI_B200_SPLIT_COST", "1")
-        self._split_cost = _mode != "0"
-        self._split_cost_multi_gpu = _mode == "2"
-        # opt-in (not yet the default: to be measured at mid-size K and on sharded controllers): the single-loop kernel
-        # compiled without the 64-register cap for launches of at most one CTA per SM
-        self._wide_regs = os.environ.get("MPPI_B200_WIDE_REGS", "0") != "0"
+        self._split_cost = os.environ.get("MPPI_B200_SPLIT_COST", "1") != "0"
         self._threads_per_sample = int(threads_per_sample)
 
         # multi-GPU: K is the GLOBAL sample count, sharded over the group
@@ -362,6 +355,9 @@ class MPPI:
         p.threads_per_sample = self._threads_per_sample
         p.grid_blocks = 0
         p.k_offset = self._k_offset
+        # sharded controllers plan their launch for the LARGEST shard: every rank then launches the same grid and
+        # publishes the same number of records per command (the shards differ by at most one sample)
+        p.K_geom = -(-self.K // self._world) if self._world > 1 else 0
         p.lambda_ = float(self._lambda)
         p.u_scale = float(self._u_scale)
         mu = _vec(self._noise_mu, nu, "noise_mu")
@@ -399,9 +395,7 @@ class MPPI:
                             | (_cabi.FLAG_DIAG_SIGMA if self._diagonal_sigma else 0)
                             | _cabi.FLAG_NOMINAL_PADDED
                             | (_cabi.FLAG_PDL if (self._pdl and self._model is not None) else 0)
-                            | (_cabi.FLAG_WIDE_REGS if (self._wide_regs and self._model is not None) else 0)
-                            | (_cabi.FLAG_SPLIT_COST if (self._split_cost and self._model is not None
-                                                          and (self._world == 1 or self._split_cost_multi_gpu)) else 0))
+                            | (_cabi.FLAG_SPLIT_COST if (self._split_cost and self._model is not None) else 0))
         p.U = self._Ubuf.data_ptr()
         p.A = None
         p.theta = None
@@ -434,6 +428,11 @@ class MPPI:
         p.offset_inc = (self._noise_rows() + per - 1) // per
         p.host_mailbox = None
         p.host_epoch = 0
+        p.xchg_status_host = None
+        if self._world > 1 and self._exchange == "p2p":
+            if getattr(self, "_xchg_status", None) is None:
+                self._xchg_status = torch.zeros(1, dtype=torch.int64).pin_memory()     # written by the kernel on a peer timeout
+            p.xchg_status_host = self._xchg_status.data_ptr()
         self._variant_pack(p)
         # workspace sized for the worst-case geometry of these dimensions
         if self._model is not None:
@@ -576,8 +575,7 @@ class MPPI:
         setters) makes the grid leave first and the next `command_host()` brings it back.  Write through the
         setters, not through views obtained earlier.
         Requires a registered analytic model on the split-cost rollout (a problem of at most one tile per SM, e.g.
-        BASELINE config 2) and host states.  Sharded controllers (process_group=..., exchange="p2p") need the split-cost
-        rollout on the shards (MPPI_B200_SPLIT_COST=2) — both opt-in until they have run on two GPUs."""
+        BASELINE config 2), host states and a single-GPU controller."""
         if self._dirty:
             self._pack()
         if self._model is None or self._plan is None:
@@ -674,6 +672,13 @@ class MPPI:
                 logger.warning("compile(): CUDA-graph capture failed (%s); continuing without graphs", e)
                 self._graph_mode = False
                 torch.cuda.synchronize(self.d)
+                try:
+                    # a capture that died in the plugin leaves torch's default CUDA generator flagged as "capturing"
+                    # (its next use would raise): give it a fresh state object with the same seed / offset
+                    gen = torch.cuda.default_generators[self.d.index]
+                    gen.graphsafe_set_state(gen.clone_state())
+                except Exception:      # noqa: BLE001 — best effort; older torch has no graph-safe generator states
+                    pass
                 return self._command_stepped(state, shift)
         g, st_static, action_static, cost_buf = self._graphs[key]
         st_static.copy_(st)
@@ -815,6 +820,19 @@ class MPPI:
         self.state = state
         return 0, None
 
+    def _check_exchange_status(self):
+        """A peer exchange that timed out inside an earlier command left this rank's nominal one update behind its
+        peers (the kernel returned the un-updated nominal as the action and flagged a pinned status word): refuse to
+        continue silently."""
+        st = getattr(self, "_xchg_status", None)
+        if st is not None and int(st[0]) != 0:
+            code = int(st[0])
+            st[0] = 0
+            raise _cabi.MppiLibraryError(
+                f"a peer exchange of an earlier command() timed out on rank {self._rank} (status {code}): this rank's nominal "
+                "sequence is now out of step with its peers; reset() / re-synchronise U across ranks before continuing "
+                "(MPPI_B200_XCHG_TIMEOUT_S sets the wait, default 20 s)")
+
     def _noise_source(self):
         """(z_ptr, seed, offset) for this command."""
         if self._z_inject is not None:
@@ -828,6 +846,8 @@ class MPPI:
         return None, seed, off
 
     def _command_fused(self, state, shift):
+        if self._world > 1:
+            self._check_exchange_status()
         sflags, sdev = self._host_state(state)
         flags = self._base_flags | sflags | (_cabi.FLAG_SHIFT if shift else 0)
         zptr, seed, off = self._noise_source()
@@ -923,6 +943,8 @@ class MPPI:
                     self.start_resident(self._resident_wanted)
                 return self._command_resident(shift_nominal_trajectory)
             self._leave_resident()         # injected noise / device-resident counter: a launch-route command
+        if self._world > 1:
+            self._check_exchange_status()
         flags = self._base_flags | (_cabi.FLAG_SHIFT if shift_nominal_trajectory else 0)
         zptr, seed, off = self._noise_source()
         stream = torch._C._cuda_getCurrentRawStream(self.d.index)
@@ -1464,7 +1486,8 @@ class MPPI_Batched(MPPI):
         es = _ES[self.dtype]
         rows = self.T * self.nu
         nb_max = min((self.K + 31) // 32 + 1, 148 * 16)
-        stride = 16 + 2 * ((nb_max * es + 15) // 16 * 16) + ((nb_max * rows * es + 15) // 16 * 16) + 64
+        stride = max(16 + 2 * ((nb_max * es + 15) // 16 * 16) + ((nb_max * rows * es + 15) // 16 * 16),
+                     16 + nb_max * (rows + 2) * 8) + 64          # per-CTA partials / per-cluster records (ws_bytes)
         self._env_ws_stride = (stride + 255) // 256 * 256
         need = self._env_ws_stride * self.N
         if self._workspace is None or self._workspace.numel() < need:

@@ -485,26 +485,43 @@ def test_kmppi_change_horizon_rebuilds_interpolation():
 
 def test_compile_fallback_applies_exactly_one_command():
     """a plugin that is not capture-safe makes compile() fall back to the eager stepped route; the warm-up
-    commands of the failed capture must be undone, so the nominal moves by exactly one command."""
-    import pytorch_mppi_b200 as eng
-    lin = eng.LinearPoint.unit_test_env()
-    dt = torch.float64
-
-    def bad_cost(s, a):
-        c = lin.running_cost(s, a)
-        float(c[0])                      # host sync: illegal during stream capture
-        return c
-
-    def make(cost):
-        torch.manual_seed(3)
-        U0 = torch.randn(7, 2, dtype=dt) * 0.1
-        return eng.MPPI(lambda s, a: lin.dynamics(s, a), cost, 2, torch.eye(2, dtype=dt), num_samples=128, horizon=7,
-                        U_init=U0, device="cuda", rng_seed=11)
-    ref_ctrl = make(lambda s, a: lin.running_cost(s, a))
-    bad = make(bad_cost)
-    bad.compile()
-    a0 = ref_ctrl.command([1.0, 1.0])
-    a1 = bad.command([1.0, 1.0])          # capture fails -> eager; one command applied
-    assert bad._graph_mode is False
-    assert torch.allclose(a0, a1, atol=1e-12) and torch.allclose(ref_ctrl.U, bad.U, atol=1e-12)
-    assert torch.allclose(ref_ctrl.command([0.9, 1.1]), bad.command([0.9, 1.1]), atol=1e-12)
+    commands of the failed capture must be undone, so the nominal moves by exactly one command.  Runs in its own process:
+    a CUDA-graph capture that dies inside a plugin can leave process-wide torch state (the default generator) unusable,
+    and the rest of this suite must not depend on the repair."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import pytorch_mppi_b200 as eng
+lin = eng.LinearPoint.unit_test_env()
+dt = torch.float64
+def bad_cost(s, a):
+    c = lin.running_cost(s, a)
+    float(c[0])                      # host sync: illegal during stream capture
+    return c
+def make(cost):
+    torch.manual_seed(3)
+    U0 = torch.randn(7, 2, dtype=dt) * 0.1
+    return eng.MPPI(lambda s, a: lin.dynamics(s, a), cost, 2, torch.eye(2, dtype=dt), num_samples=128, horizon=7,
+                    U_init=U0, device="cuda", rng_seed=11)
+ref_ctrl = make(lambda s, a: lin.running_cost(s, a))
+bad = make(bad_cost)
+bad.compile()
+a0 = ref_ctrl.command([1.0, 1.0])
+a1 = bad.command([1.0, 1.0])          # capture fails -> eager; one command applied
+assert bad._graph_mode is False
+assert torch.allclose(a0, a1, atol=1e-12) and torch.allclose(ref_ctrl.U, bad.U, atol=1e-12), (a0, a1)
+assert torch.allclose(ref_ctrl.command([0.9, 1.1]), bad.command([0.9, 1.1]), atol=1e-12)
+print("FALLBACK_OK")
+try:
+    torch.randn(4, device="cuda")
+    print("GENERATOR_OK")
+except RuntimeError as e:
+    print("GENERATOR_BROKEN", e)
+''' % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "FALLBACK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "GENERATOR_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,7 +1,8 @@
 """Multi-GPU (K sharded over ranks): needs >= 2 CUDA devices (gpurun --gpus 2).
 Each rank rolls out its slice; the (beta, eta, V) records are exchanged (a) inside the kernel over
-NVLink peer mailboxes, (b) with an NCCL all-gather + mppi_apply_partials; both must reproduce the
-unsharded update, identically on every rank."""
+NVLink peer mailboxes — the cluster records of every rank straight to every peer (direct mode) or one
+combined record per rank —, (b) with an NCCL all-gather + mppi_apply_partials; all must reproduce the
+unsharded update, identically on every rank.  The log of a 2-GPU run is kept under profiles/."""
 import os
 
 import pytest
@@ -10,10 +11,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out, split_mode="1"):
+def _worker(rank, world, port, out, mode):
     import torch.distributed as dist
+    split_mode, direct, cluster = mode
+    os.environ["MPPI_B200_SPLIT_COST"] = split_mode      # "1": split-cost rollout (also on the shards), "0": single loop
+    os.environ["MPPI_B200_XCHG_DIRECT"] = direct         # "1": cluster records straight to the peers, "0": one rank record
+    os.environ["MPPI_B200_CLUSTER"] = cluster            # thread-block-cluster size limit of the warp-fold tail
+    os.environ["MPPI_B200_XCHG_TIMEOUT_S"] = "3"
     import pytorch_mppi_b200 as eng
-    os.environ["MPPI_B200_SPLIT_COST"] = split_mode     # "2": the sharded controllers take the split-cost rollout too
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -76,44 +81,65 @@ def _worker(rank, world, port, out, split_mode="1"):
             one.command([3.0, 0.5])
             many.command([3.0, 0.5])
         results["philox"] = (float((one.U - many.U).abs().max()), 0.0, True)
-        # Resident mode on sharded controllers (opt-in until it has run on two GPUs; needs the split-cost rollout on the
-        # shards, split_mode "2"): every rank's host loop posts its own record, the finishers exchange over NVLink inside
-        # the resident grid; actions and U must equal the launch route's, on every rank.
-        if split_mode == "2" and os.environ.get("MPPI_TEST_RESIDENT_MULTI_GPU", "0") == "1":
-            def shard():
-                torch.manual_seed(5)
-                return eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=8192, horizon=30, device=dev,
-                                u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), U_init=torch.zeros(30, 1), rng_seed=99,
-                                process_group=dist.group.WORLD)
-            a, b = shard(), shard()
-            x = [3.0, 0.5]
+        results["philox_geometry"] = (0.0, 0.0, many.launch_info.split_cost == (1 if split_mode == "1" else 0)
+                                      and many.launch_info.xchg_records >= 1
+                                      and (many.launch_info.xchg_records > 1) == (direct == "1")
+                                      and many.launch_info.cluster_size <= int(cluster))
+        # BASELINE config 2 per rank (K = 16384 x world) and a config-5-sized shard (multi-tile grid, rank-record mode)
+        for K_, T_, name in ((16384 * world, 30, "c2_weak"), (131072 * world, 50, "c5_shard")):
+            U0p = torch.randn(T_, 1, generator=g) * 2
+            kwp = dict(num_samples=K_, horizon=T_, device=dev, u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), rng_seed=7)
+            one = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), U_init=U0p.clone(), **kwp)
+            many = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), U_init=U0p.clone(), process_group=dist.group.WORLD, **kwp)
             worst = 0.0
-            b.start_resident(idle_us=200000)
-            try:
-                for _ in range(10):
-                    ua, ub = a.command_host(x), b.command_host(x)
-                    worst = max(worst, float((ua - ub).abs().max()))
-                Ua, Ub = a.U.clone(), b.U.clone()
-            finally:
-                b.stop_resident()
-            lst = [torch.zeros_like(Ub) for _ in range(world)]
-            dist.all_gather(lst, Ub.contiguous())
-            results["resident"] = (float((Ua - Ub).abs().max()), worst, all(torch.equal(lst[0], t) for t in lst))
+            for _ in range(3):
+                a1 = one.command([3.0, 0.5])
+                a2 = many.command([3.0, 0.5])
+                worst = max(worst, float((a1 - a2).abs().max()))
+            lst = [torch.zeros_like(many.U) for _ in range(world)]
+            dist.all_gather(lst, many.U.detach().clone().contiguous())
+            results[name] = (float((one.U - many.U).abs().max()), worst, all(torch.equal(lst[0], t) for t in lst))
+            results[name + f"/records={many.launch_info.xchg_records}/cluster={many.launch_info.cluster_size}"] = (0.0, 0.0, True)
+        # a peer that never delivers: the waiting rank gives up after the timeout, returns the un-updated nominal as
+        # the action, and its NEXT command raises (the timeout used to be silent)
+        if mode == MODES[0]:
+            os.environ["MPPI_B200_XCHG_TIMEOUT_S"] = "0.3"
+            lone = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=4096, horizon=20, device=dev,
+                            u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), U_init=torch.ones(20, 1), rng_seed=1,
+                            process_group=dist.group.WORLD)
+            lone.command([3.0, 0.5])                      # both ranks: fine
+            torch.cuda.synchronize()
+            dist.barrier()
+            ok = True
+            if rank == 0:
+                U_before = lone.U.clone()
+                a = lone.command([3.0, 0.5], shift_nominal_trajectory=False)     # rank 1 stays away
+                torch.cuda.synchronize()
+                ok = bool(torch.equal(lone.U, U_before)) and bool(torch.equal(a.reshape(-1), U_before[0].reshape(-1)))
+                try:
+                    lone.command([3.0, 0.5])
+                    ok = False
+                except eng.mppi._cabi.MppiLibraryError:
+                    pass
+            dist.barrier()
+            results["timeout_is_reported"] = (0.0, 0.0, ok)
         out[rank] = results
     finally:
         dist.destroy_process_group()
 
 
+# (split-cost rollout, direct exchange of cluster records, cluster size limit): the default first
+MODES = [("1", "1", "8"), ("0", "0", "1"), ("1", "1", "1"), ("1", "0", "8")]
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("split_mode", ["1", "2"])
-def test_two_gpu_sharding_matches_single_gpu(split_mode):
-    if split_mode == "2" and os.environ.get("MPPI_TEST_SPLIT_MULTI_GPU", "0") != "1":
-        pytest.skip("split-cost rollout on sharded controllers: first run it with MPPI_TEST_SPLIT_MULTI_GPU=1 (round 2)")
+@pytest.mark.parametrize("mode", MODES, ids=lambda m: f"split{m[0]}-direct{m[1]}-cluster{m[2]}")
+def test_two_gpu_sharding_matches_single_gpu(mode):
     import torch.multiprocessing as mp
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29700 + (os.getpid() % 1000) + (50 if split_mode == "2" else 0)
-    mp.spawn(_worker, args=(2, port, out, split_mode), nprocs=2, join=True)
+    port = 29700 + (os.getpid() % 1000) + 37 * MODES.index(mode)
+    mp.spawn(_worker, args=(2, port, out, mode), nprocs=2, join=True)
     assert len(out) == 2
     for rank in range(2):
         for key, (err, aerr, same) in out[rank].items():

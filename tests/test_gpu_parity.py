@@ -201,29 +201,6 @@ def test_split_cost_rollout_is_bit_identical_to_the_single_loop(name, monkeypatc
     assert float(np.abs(again.U.cpu().numpy() - gold["U_0"]).max()) <= tol
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MPPI_TEST_WIDE_REGS", "0") != "1",
-                    reason="opt-in until first run on a GPU (round 2): MPPI_TEST_WIDE_REGS=1")
-@pytest.mark.parametrize("K", [2048, 32768, 70000])
-def test_wide_register_instantiation_is_bit_identical(K, monkeypatch):
-    """MPPI_FLAG_WIDE_REGS (MPPI_B200_WIDE_REGS=1): the single-loop kernel compiled without the 64-register cap, taken by
-    launches of at most one CTA per SM.  Same source -> same bits."""
-    import pytorch_mppi_b200 as eng
-    pend = eng.Pendulum()
-    torch.manual_seed(0)
-    U0 = torch.randn(30, 1) * 3.0
-
-    def make(wide):
-        monkeypatch.setenv("MPPI_B200_SPLIT_COST", "0")
-        monkeypatch.setenv("MPPI_B200_WIDE_REGS", "1" if wide else "0")
-        return eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=K, horizon=30, U_init=U0,
-                        u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), device="cuda", rng_seed=5)
-    a, b = make(False), make(True)
-    for _ in range(3):
-        ua, ub = a.command([3.0, 0.5]), b.command([3.0, 0.5])
-        assert torch.equal(a.U, b.U) and torch.equal(a.cost_total, b.cost_total) and torch.equal(ua, ub)
-    assert a.launch_info.wide_regs == 0 and b.launch_info.wide_regs == 1 and b.launch_info.regs_per_thread > 64
-
-
 def test_closed_loop_free_running_c2():
     """10 closed-loop commands WITHOUT resynchronising U: error vs the fp32 reference stays at the
     fp32 noise floor (SURVEY.md §8d parity check)."""
