@@ -103,19 +103,33 @@ int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_p
     DevInfo di;
     int rc = get_dev_info(di);
     if (rc) return rc;
-    // the resident grid has its own shape: one CTA per tile (no cluster padding) and the per-CTA-partials tail's layout
-    const int nb = a.n_tiles;
+    // the launch route's grid (one tile per CTA, padded to the cluster size) and cluster size: same reduction tree, same
+    // bits.  If the driver refuses cooperative + cluster together, the grid is launched without clusters (its results
+    // then agree with the launch route to fp64 rounding of the reduction order instead of bit for bit).
     const MppiFusedParams& pp = pl->p;
-    const int smem = make_layout<real>(pp.variant, pp.T, pp.nu, pp.S, a.R, pl->g.BD, pl->g.BS, nb, layout_extra(0, pl->nx, 0, 0)).total;
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, pl->res_kernel));
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
-    if (smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
     CK(cudaFuncSetAttribute(pl->res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_limit));
     CK(cudaMemsetAsync(d.board, 0, MPPI_RES_BOARD_WORDS * sizeof(unsigned long long), d.stream));
     void* argv[3] = {(void*)&a, (void*)pl->mparams, (void*)&ra};
-    // cooperative: every CTA is resident or the launch fails — the CTAs wait for each other through the board
-    cudaError_t e = cudaLaunchCooperativeKernel(pl->res_kernel, dim3(nb), dim3(pl->g.BD), argv, (size_t)smem, d.stream);
+    cudaError_t e = cudaErrorInvalidConfiguration;
+    for (int cs = pl->g.cluster; cs >= 1; cs = (cs > 1 ? 1 : 0)) {
+        const int nb = cs > 1 ? pl->g.nb : a.n_tiles;
+        const int smem = make_layout<real>(pp.variant, pp.T, pp.nu, pp.S, a.R, pl->g.BD, pl->g.BS, 1,
+                                           layout_extra(pp.variant != MPPI_VARIANT_MPPI, pl->nx, cs, 0)).total;
+        if (smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
+        // cooperative: every CTA is resident or the launch fails — the CTAs wait for each other through the board
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute at[3];
+        launch_config(cfg, at, nb, pl->g.BD, smem, d.stream, false, 1, cs);
+        at[cfg.numAttrs].id = cudaLaunchAttributeCooperative;
+        at[cfg.numAttrs].val.cooperative = 1;
+        ++cfg.numAttrs;
+        e = cudaLaunchKernelExC(&cfg, pl->res_kernel, argv);
+        if (e == cudaSuccess) break;
+        cudaGetLastError();
+    }
     if (e != cudaSuccess) return cuda_fail(e, "resident launch");
     return MPPI_OK;
 }

@@ -392,7 +392,10 @@ __device__ __forceinline__ bool override_value(const KArgs<real>& a, unsigned lo
 }
 
 // ---- stage B: colour + nominal + clamp, in place in this thread's column --------------------------
-template <typename real, int VARIANT, int NU>
+// TILE2 (fused / resident kernels): a second tile `rows2` of T*nu rows per sample keeps what the serial rollout thread
+// would otherwise recompute per step — SMPPI: the effective noise eps = (v - A)/dt - U (one IEEE division per element,
+// needed by the action cost and by the softmin fold); KMPPI: the interpolated, clamped trajectory (interp_column).
+template <typename real, int VARIANT, int NU, bool TILE2 = false>
 __device__ __forceinline__ void transform_column(const KArgs<real>& a, Smem<real>& sm, unsigned long long kg) {
     typedef Ops<real> O;
     const NoiseModel<real>& nm = a.nm;
@@ -422,6 +425,8 @@ __device__ __forceinline__ void transform_column(const KArgs<real>& a, Smem<real
                     p = O::add(sm.As[t * NU + n], O::mul(p, nm.delta_t));                 // mppi.py:548
                     override_value<real>(a, kg, t * NU + n, p);                           // mppi.py:549
                     p = clamp<real>(p, nm.a_min[n], nm.a_max[n]);                         // mppi.py:550
+                    if (TILE2)                                                            // mppi.py:552
+                        sm.rows2[(t * NU + n) * LD + s_] = O::sub(O::div(O::sub(p, sm.As[t * NU + n]), nm.delta_t), sm.Us[t * NU + n]);
                 } else {
                     override_value<real>(a, kg, t * NU + n, p);                           // mppi.py:381
                     p = clamp<real>(p, nm.u_min[n], nm.u_max[n]);                         // mppi.py:383
@@ -432,13 +437,36 @@ __device__ __forceinline__ void transform_column(const KArgs<real>& a, Smem<real
     }
 }
 
+// KMPPI, TILE2: interpolate this sample's control points onto the horizon ONCE, with all its tps threads
+// (mppi.py:665-668: W @ theta_k, specific actions, clamp), after the barrier that completes the control-point tile
+template <typename real, int NU>
+__device__ __forceinline__ void interp_column(const KArgs<real>& a, Smem<real>& sm, unsigned long long kg) {
+    typedef Ops<real> O;
+    const int LD = sm.LD, S = a.S;
+    const int BS = blockDim.x / a.tps, s_ = threadIdx.x % BS, g_ = threadIdx.x / BS;
+    const real* col = sm.rows + s_;
+    for (int t = g_; t < a.T; t += a.tps) {
+#pragma unroll
+        for (int n = 0; n < NU; ++n) {
+            real acc = O::mul(sm.Ws[t * S], col[n * LD]);
+            for (int s = 1; s < S; ++s) acc = O::add(acc, O::mul(sm.Ws[t * S + s], col[(s * NU + n) * LD]));
+            override_value<real>(a, kg, t * NU + n, acc);
+            sm.rows2[(t * NU + n) * LD + s_] = clamp<real>(acc, a.nm.u_min[n], a.nm.u_max[n]);
+        }
+    }
+}
+
 // perturbed action at step t for this thread (KMPPI interpolates the control points: mppi.py:665-668)
-template <typename real, int VARIANT, int NU>
+template <typename real, int VARIANT, int NU, bool TILE2 = false>
 __device__ __forceinline__ void action_at(const KArgs<real>& a, const Smem<real>& sm, unsigned long long kg, int t, real* v) {
     typedef Ops<real> O;
     const int LD = sm.LD;
     const real* col = sm.rows + (threadIdx.x % (blockDim.x / a.tps));
-    if (VARIANT == V_KMPPI) {
+    if (VARIANT == V_KMPPI && TILE2) {
+        const real* col2 = sm.rows2 + (threadIdx.x % (blockDim.x / a.tps));
+#pragma unroll
+        for (int n = 0; n < NU; ++n) v[n] = col2[(t * NU + n) * LD];
+    } else if (VARIANT == V_KMPPI) {
         const int S = a.S;
 #pragma unroll
         for (int n = 0; n < NU; ++n) {
@@ -454,12 +482,14 @@ __device__ __forceinline__ void action_at(const KArgs<real>& a, const Smem<real>
 }
 
 // effective noise entering the action cost at step t (mppi.py:385 / :552 / :670)
-template <typename real, int VARIANT, int NU>
+template <typename real, int VARIANT, int NU, bool TILE2 = false>
 __device__ __forceinline__ void noise_at(const KArgs<real>& a, const Smem<real>& sm, int t, const real* v, real* eps) {
     typedef Ops<real> O;
 #pragma unroll
     for (int n = 0; n < NU; ++n) {
-        if (VARIANT == V_SMPPI)
+        if (VARIANT == V_SMPPI && TILE2)
+            eps[n] = sm.rows2[(t * NU + n) * sm.LD + (threadIdx.x % (blockDim.x / a.tps))];
+        else if (VARIANT == V_SMPPI)
             eps[n] = O::sub(O::div(O::sub(v[n], sm.As[t * NU + n]), a.nm.delta_t), sm.Us[t * NU + n]);
         else
             eps[n] = O::sub(v[n], sm.Us[t * NU + n]);
@@ -914,11 +944,13 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
         const int jc = jv ? j : 0;
         const real us = (VARIANT == V_KMPPI) ? (real)0 : sm.Us[jc];
         const real a2 = VARIANT == V_SMPPI ? sm.As[jc] : (VARIANT == V_KMPPI ? sm.ths[jc] : (real)0);
-        const real* row = sm.rows + (size_t)jc * LD + i0;
+        // SMPPI: the tile of effective noise (rows2, written once by transform_column) — no division here
+        const real* row = (VARIANT == V_SMPPI ? sm.rows2 : sm.rows) + (size_t)jc * LD + i0;
         double acc = 0.0;
         for (int i = 0; i < nv; ++i) {
             const real wi = __shfl_sync(0xffffffffu, wgt, i);
-            acc += (double)(wi * eps_of<real, VARIANT>(a.nm, row[i], us, a2));                  // mppi.py:268
+            const real e = VARIANT == V_SMPPI ? row[i] : eps_of<real, VARIANT>(a.nm, row[i], us, a2);
+            acc += (double)(wi * e);                                                            // mppi.py:268
         }
         if (jv) rec[2 + j] = rec[2 + j] * resc + acc;
     }
@@ -930,36 +962,56 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
 }
 
 // ---- fixed-order fp64 combination of records (beta_q, eta_q, V_q[R]) -----------------------------------------------
-//   beta = min beta_q ; s_q = exp(nfl (beta_q - beta)) ; eta = sum s_q eta_q ; V[j] = sum s_q V_q[j]
-// Warp-synchronous.  ld(q, i) returns element i of record q.  The calling warp produces rows j = jb + lane for
-// jb = row0, row0 + rstep, ... < R through out(j, value); beta and eta are returned to every lane.
-template <class Load, class Out>
-__device__ __forceinline__ void combine_records(Load ld, Out out, int nrec, int R, double nfl, int row0, int rstep, double& beta,
-                                                double& eta) {
-    const int lane = threadIdx.x & 31;
+//   beta = min beta_q ; s_q = exp(nfl (beta_q - beta)) ; eta = sum s_q eta_q ; V[j] = sum s_q V_q[j]   -> sm.numd[0 .. R+2)
+// CTA-wide (every thread calls it; two barriers).  ld(q, i) returns element i of record q.  Warp w takes the records
+// q = w, w + nw, ... (PF of them in flight: one shared-memory / L2 round trip per batch), accumulates s_q V_q[j] for all
+// rows in its own slice of sm.part2, and the slices are added in warp order — the result does not depend on timing.
+template <typename real, class Load>
+__device__ void combine_records(Load ld, int nrec, Smem<real>& sm, int R, double nfl) {
+    typedef Ops<real> O;
+    constexpr int PF = 8;
+    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
     double b = (double)INFINITY;
     for (int q = lane; q < nrec; q += 32) b = fmin(b, ld(q, 0));
-    beta = warp_min<double>(b);
-    double el = 0.0;
-    for (int q = lane; q < nrec; q += 32) el += exp(nfl * (ld(q, 0) - beta)) * ld(q, 1);
-    eta = warp_sum<double>(el);
-    for (int jb = row0; jb < R; jb += rstep) {
-        const int j = jb + lane;
-        const bool jv = j < R;
-        const int jc = jv ? j : 0;
-        double acc = 0.0;
-        for (int qb = 0; qb < nrec; qb += 32) {
-            const int q = qb + lane;
-            const double s_mine = q < nrec ? exp(nfl * (ld(q, 0) - beta)) : 0.0;
-            const int n = min(32, nrec - qb);
-#pragma unroll 8
-            for (int u = 0; u < n; ++u) {
-                const double sq = __shfl_sync(0xffffffffu, s_mine, u);
-                acc += sq * ld(qb + u, 2 + jc);
-            }
+    const double beta = warp_min<double>(b);             // every warp computes it (no barrier)
+    double* mine = sm.part2 + (size_t)warp * R;
+    for (int j = lane; j < R; j += 32) mine[j] = 0.0;
+    double eta_p = 0.0;
+    for (int q0 = warp; q0 < nrec; q0 += PF * nw) {
+        double s[PF];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int q = q0 + u * nw;
+            // the rescale factor in the controller's precision (exact for equal betas; beta_q - beta is exact in fp64)
+            s[u] = q < nrec ? (double)O::exp_((real)(nfl * (ld(q, 0) - beta))) : 0.0;
+            if (q < nrec) eta_p += s[u] * ld(q, 1);
         }
-        if (jv) out(j, acc);
+        for (int jb = 0; jb < R; jb += 32) {
+            const int j = jb + lane;
+            const int jc = j < R ? j : 0;
+            double v[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) v[u] = (q0 + u * nw < nrec) ? ld(q0 + u * nw, 2 + jc) : 0.0;
+            double acc = 0.0;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) acc += s[u] * v[u];
+            if (j < R) mine[j] += acc;
+        }
     }
+    if (lane == 0) sm.redd[warp] = eta_p;
+    __syncthreads();
+    for (int j = tid; j < R; j += BD) {
+        double t = sm.part2[j];
+        for (int w = 1; w < nw; ++w) t += sm.part2[(size_t)w * R + j];
+        sm.numd[2 + j] = t;
+    }
+    if (tid == 0) {
+        double e = sm.redd[0];
+        for (int w = 1; w < nw; ++w) e += sm.redd[w];
+        sm.numd[0] = beta;
+        sm.numd[1] = e;
+    }
+    __syncthreads();
 }
 
 // ---- peer mailboxes: records of (R+2) doubles as LL words (payload32 | flag32), record r at word r * 2 (R+2) -------
@@ -1026,9 +1078,11 @@ __device__ void xchg_timed_out(const KArgs<real>& a, Smem<real>& sm, int nu) {
 }
 
 // ---- the tail: returns true in the CTA that finished the command --------------------------------------------------
-template <typename real, int VARIANT, int NU>
+// PERSISTENT (resident kernel): the grid outlives the command, so the non-leader CTAs of a cluster complete the barrier
+// phase (arrive + wait) instead of exiting after their arrive.
+template <typename real, int VARIANT, int NU, bool PERSISTENT = false>
 __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
-    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
+    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int R = a.R, RW = R + 2;
     const int nrw = (BD / a.tps) >> 5;                       // rollout warps = records per CTA
     const int cs = (int)cluster_nctarank();                  // cluster dims are (cs, 1, 1)
@@ -1046,7 +1100,10 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
             for (int i = lane; i < RW; i += 32) st_dsmem_f64(dst + i * 8, rec[i]);
         }
         cluster_arrive_release();
-        if (cr != 0) return false;
+        if (cr != 0) {
+            if (PERSISTENT) cluster_wait_acquire();
+            return false;
+        }
         cluster_wait_acquire();
     } else {
         __syncthreads();
@@ -1056,18 +1113,8 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
     // (2) leader: cs x nrw warp records -> one cluster record in sm.numd
     {
         const double* recs = sm.wrec;
-        double beta, eta;
-        auto ld = [&](int q, int i) { return recs[(size_t)q * RW + i]; };
-        auto out = [&](int j, double v) { sm.numd[2 + j] = v; };
-        if (warp == 0 || warp * 32 < R) {
-            combine_records(ld, out, cs * nrw, R, nfl, warp * 32, nw * 32, beta, eta);
-            if (tid == 0) {
-                sm.numd[0] = beta;
-                sm.numd[1] = eta;
-            }
-        }
+        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, cs * nrw, sm, R, nfl);
     }
-    __syncthreads();
     // (3) publish the cluster record; ticket among the leaders of this GPU
     if (direct) {
         xchg_publish<real>(a, a.rank * NC + cid, sm.numd);
@@ -1090,17 +1137,7 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
     // (4) finisher: the rank's records -> (beta, eta, numerators) in sm.numd
     if (!direct && NC > 1) {
         const double* recs = a.crec;
-        double beta, eta;
-        auto ld = [&](int q, int i) { return __ldcg(recs + (size_t)q * RW + i); };
-        auto out = [&](int j, double v) { sm.numd[2 + j] = v; };
-        if (warp == 0 || warp * 32 < R) {
-            combine_records(ld, out, NC, R, nfl, warp * 32, nw * 32, beta, eta);
-            if (tid == 0) {
-                sm.numd[0] = beta;
-                sm.numd[1] = eta;
-            }
-        }
-        __syncthreads();
+        combine_records<real>([&](int q, int i) { return __ldcg(recs + (size_t)q * RW + i); }, NC, sm, R, nfl);
     }
     stamp(a.dbg, 10);
     if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
@@ -1129,17 +1166,7 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
             return true;
         }
         const double* recs = sm.xstage;
-        double beta, eta;
-        auto ld = [&](int q, int i) { return recs[(size_t)q * RW + i]; };
-        auto out = [&](int j, double v) { sm.numd[2 + j] = v; };
-        if (warp == 0 || warp * 32 < R) {
-            combine_records(ld, out, nrec, R, nfl, warp * 32, nw * 32, beta, eta);
-            if (tid == 0) {
-                sm.numd[0] = beta;
-                sm.numd[1] = eta;
-            }
-        }
-        __syncthreads();
+        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, nrec, sm, R, nfl);
     }
     stamp(a.dbg, 11);
     finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);
@@ -1213,8 +1240,8 @@ __device__ __forceinline__ real split_cost_rollout(const KArgs<real>& a, const t
 MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
         for (int t = 0; t < T; ++t) {
             real v[NU], u[NU], eps[NU];
-            action_at<real, VARIANT, NU>(a, sm, kg, t, v);
-            noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+            action_at<real, VARIANT, NU, true>(a, sm, kg, t, v);
+            noise_at<real, VARIANT, NU, true>(a, sm, t, v, eps);
 #pragma unroll
             for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
             Model::template step<real>(mp, x, u);                                     // mppi.py:314
@@ -1239,7 +1266,7 @@ MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
 MPPI_UNROLL_N(2)
         for (int t = tid / BS; t < T; t += a.tps) {      // independent across t: two in flight per thread
             real v[NU], u[NU], xt[NX];
-            action_at<real, VARIANT, NU>(a, sm, kg, t, v);
+            action_at<real, VARIANT, NU, true>(a, sm, kg, t, v);
 #pragma unroll
             for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);
 #pragma unroll
@@ -1286,7 +1313,7 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
     const int BS = BD / a.tps;
     const int xst = (a.world > 1 && !a.export_partial) ? a.world * a.xchg_npub * (a.R + 2) : 0;
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1,
-                                           layout_extra(0, SPLIT ? NX : 0, (int)cluster_nctarank(), xst));
+                                           layout_extra(VARIANT != V_MPPI, SPLIT ? NX : 0, (int)cluster_nctarank(), xst));
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
@@ -1322,8 +1349,12 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
             __syncthreads();
         }
         if (tile == blockIdx.x) stamp(a.dbg, 2);
-        if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
+        if (in_range) transform_column<real, VARIANT, NU, true>(a, sm, kg);
         if (a.tps > 1) __syncthreads();
+        if (VARIANT == V_KMPPI) {      // the control points of the sample are complete: interpolate them onto the horizon
+            if (in_range) interp_column<real, NU>(a, sm, kg);
+            if (a.tps > 1) __syncthreads();
+        }
         if (tile == blockIdx.x) stamp(a.dbg, 3);
 
         real c_tot = O::inf();
@@ -1353,8 +1384,8 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
 MPPI_UNROLL_N(MPPI_ROLLOUT_UNROLL)
             for (int t = 0; t < T; ++t) {
                 real v[NU], u[NU], eps[NU], xs[NX];
-                action_at<real, VARIANT, NU>(a, sm, kg, t, v);
-                noise_at<real, VARIANT, NU>(a, sm, t, v, eps);
+                action_at<real, VARIANT, NU, true>(a, sm, kg, t, v);
+                noise_at<real, VARIANT, NU, true>(a, sm, t, v, eps);
 #pragma unroll
                 for (int n = 0; n < NU; ++n) u[n] = O::mul(nm.u_scale, v[n]);            // mppi.py:313
 #pragma unroll

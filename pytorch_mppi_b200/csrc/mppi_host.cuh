@@ -256,7 +256,7 @@ inline cudaError_t launch_raw(const void* kernel, int nb, int BD, int smem, cuda
                               int cluster = 1) {
     if (!pdl && cluster <= 1) return cudaLaunchKernel(kernel, dim3(nb, ny), dim3(BD), argv, (size_t)smem, stream);
     cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[3];
     launch_config(cfg, at, nb, BD, smem, stream, pdl, ny, cluster);
     return cudaLaunchKernelExC(&cfg, kernel, argv);
 }
@@ -325,7 +325,7 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
         // latency hiding needs ~24 resident warps per SM when the problem is large enough to supply them
         const long long per_sm = ((long long)p->K + di.sm_count - 1) / di.sm_count;
         const long long want_threads = per_sm < 768 ? per_sm : 768;
-        for (int bs = 128; bs <= 512; bs += 32) {
+        for (int bs = 64; bs <= 512; bs += (bs < 128 ? 64 : 32)) {     // 64-sample tiles let K < 128 x SMs reach every SM
             SmemLayout Lc = layout(p->variant, p->T, p->nu, p->S, R, bs, bs, single_partial_grid ? 1 : di.sm_count * 4, need_rows2);
             if (Lc.total > dyn0) continue;
             int occ_c = 0;
@@ -358,10 +358,10 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
         // helper threads only pay off while an SM hosts a single small CTA
         tps = 1;
         const int envs = p->n_env > 1 ? p->n_env : 1;
-        if ((long long)n_tiles * envs <= di.sm_count) tps = 512 / BS >= 4 ? 4 : (512 / BS >= 2 ? 2 : 1);
+        if ((long long)n_tiles * envs <= di.sm_count) tps = 512 / BS >= 8 ? 8 : (512 / BS >= 4 ? 4 : (512 / BS >= 2 ? 2 : 1));
     }
     while (tps > 1 && BS * tps > 512) tps >>= 1;
-    if (tps != 1 && tps != 2 && tps != 4) return MPPI_ERR_BAD_ARG;
+    if (tps != 1 && tps != 2 && tps != 4 && tps != 8) return MPPI_ERR_BAD_ARG;
     const int BD = BS * tps;
     const int cap = di.sm_count * 16;
     cudaFuncAttributes fa;

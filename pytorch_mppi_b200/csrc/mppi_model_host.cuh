@@ -80,7 +80,8 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
         return MPPI_OK;
     }
     const int xst1 = sharded ? world * (R + 2) : 0;          // staging of the rank-record exchange
-    rc = plan_geometry(kernel, &pg, es, layout_extra(0, 0, 1, xst1), true, g, layout_fn<real>);
+    const int tile2 = V != V_MPPI;                          // SMPPI: effective-noise tile, KMPPI: interpolated-trajectory tile
+    rc = plan_geometry(kernel, &pg, es, layout_extra(tile2, 0, 1, xst1), true, g, layout_fn<real>);
     if (rc) return rc;
     int split = 0;
     if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
@@ -91,7 +92,7 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
             p2.threads_per_sample = g.tps;
             p2.grid_blocks = g.nb;
             Geometry g2;
-            if (plan_geometry(k2, &p2, es, layout_extra(0, Model::NX, 1, xst1), true, g2, layout_fn<real>) == MPPI_OK &&
+            if (plan_geometry(k2, &p2, es, layout_extra(tile2, Model::NX, 1, xst1), true, g2, layout_fn<real>) == MPPI_OK &&
                 g2.BS == g.BS && g2.tps == g.tps) {
                 kernel = k2;
                 g = g2;
@@ -114,7 +115,8 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
     for (int cs = 8; cs >= 1; cs >>= 1) {
         if (cs > want && cs > 1) continue;
         const int nbp = (g.nb + cs - 1) / cs * cs;
-        if (cs > 1 && (nbp > di.sm_count || g.nb < 2)) continue;          // one wave, at most one CTA per SM
+        if (cs > 2 && nbp > di.sm_count) continue;                        // 8 / 4: one wave of at most one CTA per SM (pairs pack anywhere)
+        if (cs > 1 && (g.nb < 2 || nbp > di.sm_count * g.occ)) continue;
         const int NC = nbp / cs;
         // direct mode: every rank's cluster records are staged by the finisher (world x NC x (R+2) doubles)
         int npub = sharded ? 1 : 0;
@@ -123,11 +125,11 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
         if (const char* e = getenv("MPPI_B200_XCHG_DIRECT"))
             if (atoi(e) == 0 && sharded) npub = 1;
         const int xst = sharded ? world * npub * (R + 2) : 0;
-        const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, 1, layout_extra(0, split ? Model::NX : 0, cs, xst));
+        const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, 1, layout_extra(tile2, split ? Model::NX : 0, cs, xst));
         if (L.total > dyn_limit) continue;
         if (cs > 1) {
             cudaLaunchConfig_t cfg;
-            cudaLaunchAttribute at[2];
+            cudaLaunchAttribute at[3];
             launch_config(cfg, at, nbp, g.BD, L.total, nullptr, (p->flags & MPPI_FLAG_PDL) != 0, envs, cs);
             int max_clusters = 0;
             if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kernel, &cfg) != cudaSuccess) {
@@ -232,7 +234,7 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {
         // resident mode runs the split-cost rollout with one tile per CTA: exactly the single-GPU plans that took it
         // (the resident grid is a cooperative launch without clusters; it carries its own tail, mppi_resident.cuh)
-        if (c.split && !batched && !a->export_partial && a->world == 1 && a->n_tiles <= pl->g.nb)
+        if (c.split && !batched && !a->export_partial && a->world == 1 && a->n_tiles <= pl->g.nb && pl->g.nb <= a->n_tiles + pl->g.cluster - 1)
             pl->res_kernel = (const void*)resident_command_kernel<Model, real, V>;
         // the one instantiation with %globaltimer stamps (a profiling aid, scripts/resident_timeline.py)
         if constexpr (std::is_same<Model, PendulumModel>::value && std::is_same<real, float>::value && V == V_MPPI) {

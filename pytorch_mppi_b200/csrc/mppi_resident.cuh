@@ -19,7 +19,7 @@
 // contradicts the prediction (other counter, other shift flag) just redoes that preparation — same results.
 //
 // Arithmetic: the stages are the functions of mppi_fused.cuh (fill_normals, stage_finish, transform_column,
-// split_cost_rollout, fold_tile, publish_and_finish), so a resident command is bit-identical to a launched one
+// split_cost_rollout, warp_fold, warp_tail — launched with the same cluster size), so a resident command is bit-identical to a launched one
 // with the same (state, seed, counter, flags) — tests/test_gpu_resident.py.
 //
 // Safety: the kernel cannot outlive its usefulness.  CTA 0 exits after `idle_ns` without a record (it tells the
@@ -85,11 +85,16 @@ __device__ void stage_resident(const KArgs<real>& a, Smem<real>& sm) {
 // everything of a command that does not need the start state: normals, shifted nominal, perturbed-action tile
 template <typename real, int VARIANT, int NU>
 __device__ __forceinline__ void resident_prepare(const KArgs<real>& a, Smem<real>& sm, bool in_range, unsigned long long kg, int nvalid) {
+    warp_records_init<real>(a, sm);                  // this command's softmin records (published by the barriers below)
     fill_normals<real>(a, sm, blockIdx.x, in_range, kg, nvalid);
     stage_resident<real, VARIANT>(a, sm);
     stage_finish<real, VARIANT, NU>(a, sm);          // tma_ok == 0: barrier, shifted copy, barrier
-    if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
+    if (in_range) transform_column<real, VARIANT, NU, true>(a, sm, kg);
     __syncthreads();
+    if (VARIANT == V_KMPPI) {
+        if (in_range) interp_column<real, NU>(a, sm, kg);
+        __syncthreads();
+    }
 }
 
 // __launch_bounds__(640, 1): CTAs have at most 512 threads; promising 640 makes ptxas stop at 96 registers
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
         __syncthreads();
     }
     const int BS = BD / a.tps;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, gridDim.x, NX << 8);
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1, layout_extra(VARIANT != V_MPPI, NX, (int)cluster_nctarank(), 0));
     Smem<real> sm(smem, L);
 
     // one tile per CTA
@@ -224,10 +229,9 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
         // (5) rollout, fold, tail — the launched kernel's stages
         const real c_tot = split_cost_rollout<Model, real, VARIANT>(a, mp, sm, k, kg, in_range, active);
         if constexpr (STAMPS) stamp(a.dbg, 3);
-        real beta_run = O::inf(), eta_run = (real)0, w_unused;
-        fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+        if (tid < BS) warp_fold<real, VARIANT>(a, sm, c_tot, active, nvalid);
         if constexpr (STAMPS) stamp(a.dbg, 4);
-        const bool finisher = publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+        const bool finisher = warp_tail<real, VARIANT, NU, true>(a, sm);
         if (finisher) {
             __syncthreads();           // every store of the update precedes thread 0's fence
             if (tid == 0) {

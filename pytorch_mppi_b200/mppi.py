@@ -1255,7 +1255,12 @@ class SMPPI(MPPI):
     @property
     def action_sequence(self):
         self._resident_sync()
-        return self._Abuf[: self.T * self.nu].view(self.T, self.nu)
+        # one view object per buffer: `ctrl.get_action_sequence() is ctrl.action_sequence` holds as in the reference
+        # (test_mppi.py:452-456), and the kernels update it in place
+        v = getattr(self, "_A_view", None)
+        if v is None or v.data_ptr() != self._Abuf.data_ptr() or v.shape != (self.T, self.nu):
+            v = self._A_view = self._Abuf[: self.T * self.nu].view(self.T, self.nu)
+        return v
 
     @action_sequence.setter
     def action_sequence(self, value):

