@@ -264,6 +264,9 @@ int mppi_apply_partials(const MppiFusedParams* p, const void* partials, void* st
 
 /* Peer mailboxes for the in-kernel NVLink exchange.  The library owns these small buffers
  * (cudaMalloc + cudaIpc), because IPC handles must cover a whole allocation. */
+/* Highest command epoch this plan has used (the tag of its reduction records, shared by the launch and resident routes);
+ * pass it as MppiFusedParams.epoch when re-creating the plan so that stale records can never match. */
+uint64_t mppi_plan_epoch(void* plan);
 int mppi_xchg_create(void** mailbox, void* ipc_handle_out_64B);       /* local mailbox + its IPC handle */
 int mppi_xchg_open(const void* ipc_handle_64B, void** peer_mailbox);  /* map a peer's mailbox           */
 int mppi_xchg_close(void* peer_mailbox);

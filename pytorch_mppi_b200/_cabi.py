@@ -146,6 +146,7 @@ SYMBOLS = [
     ("mppi_resident_sync", C.c_int, [C.c_void_p]),
     ("mppi_resident_stop", C.c_int, [C.c_void_p]),
     ("mppi_resident_launches", C.c_uint64, [C.c_void_p]),
+    ("mppi_plan_epoch", C.c_uint64, [C.c_void_p]),
     ("mppi_apply_partials", C.c_int, [_P, C.c_void_p, C.c_void_p]),
     ("mppi_xchg_create", C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
     ("mppi_xchg_open", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -60,12 +60,16 @@ inline void plan_update(Plan* pl, const double* state, const void* state_dev, ui
     a->offset = offset;
     a->z = (const real*)z;
     a->action_out = (real*)action_out;
-    if (a->world > 1 || a->export_partial) a->epoch = ++pl->epoch;
+    // one epoch per command on whichever route it takes: the tag of its reduction records (and, sharded, of the exchange)
+    if (pl->res.armed && pl->res_epoch_off + pl->res.seq > pl->epoch) pl->epoch = pl->res_epoch_off + pl->res.seq;
+    a->epoch = ++pl->epoch;
     a->host_mailbox = (unsigned long long*)host_mailbox;
     if (host_mailbox != nullptr) a->host_epoch = ++pl->host_epoch;
 }
 
 inline int plan_launch(Plan* pl, cudaStream_t stream) {
+    int rc = refuse_capture(stream, pl->g);
+    if (rc) return rc;
     void* argv[2] = {(void*)pl->kargs, (void*)pl->mparams};
     cudaError_t e = launch_raw(pl->kernel, pl->g.nb, pl->g.BD, pl->g.smem, stream, argv, pl->pdl != 0, pl->p.n_env > 1 ? pl->p.n_env : 1,
                                pl->g.cluster);
@@ -97,6 +101,7 @@ int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_p
     ra.seq_start = seq_start;
     ra.offset_pred = offset_pred;
     ra.idle_ns = d.idle_ns;
+    ra.epoch_off = pl->res_epoch_off;
     ra.gen = gen;
     ra.shift_pred = shift_pred;
     ra.n_words = 3 + pl->nx * (pl->is_double ? 2 : 1);
@@ -395,7 +400,10 @@ int mppi_resident_start(void* plan, void* host_box, void* board_dev, void* actio
     d.idle_ns = idle_us * 1000ull;
     d.stream = (cudaStream_t)stream;
     const ResidentBackend be{pl, resident_be_launch, resident_be_drain, resident_be_health};
-    return res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be, 0);
+    const int rc_arm = res_arm(pl->res, host_box, pl->nx, pl->upc_nu, pl->is_double, be, 0);
+    // resident commands continue the plan's epochs: command seq carries epoch res_epoch_off + seq
+    pl->res_epoch_off = pl->epoch - pl->res.seq;
+    return rc_arm;
 }
 
 int mppi_resident_command(void* plan, const double* state, uint32_t flags, uint64_t seed, uint64_t offset, void* action_host_out) {
@@ -412,6 +420,13 @@ int mppi_resident_sync(void* plan) {
 int mppi_resident_stop(void* plan) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
     return pl == nullptr ? (int)MPPI_ERR_BAD_ARG : res_stop(pl->res);
+}
+
+uint64_t mppi_plan_epoch(void* plan) {
+    Plan* pl = reinterpret_cast<Plan*>(plan);
+    if (pl == nullptr) return 0;
+    const unsigned long long res = pl->res.armed ? pl->res_epoch_off + pl->res.seq : 0;
+    return res > pl->epoch ? res : pl->epoch;
 }
 
 uint64_t mppi_resident_launches(void* plan) {

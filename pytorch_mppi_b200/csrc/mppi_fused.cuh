@@ -68,7 +68,8 @@ template <typename real> struct KArgs {
     double* partial_out;
     unsigned long long epoch;
     int rank, world, export_partial;
-    int xchg_npub;                // records each rank publishes per command: its cluster records (direct mode) or 1
+    int xchg_npub;                // records each rank publishes per command: its cluster records (LL mode) or 1
+    unsigned int xchg_parity_words;   // 8-byte words between the two epoch parities of a record mailbox
     unsigned long long xchg_timeout_ns;
     long long* xchg_status_host;  // optional pinned host word: set to MPPI_ERR_TIMEOUT when a peer exchange timed out
     // sizes
@@ -915,6 +916,13 @@ __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.c
 
 #define MPPI_XCHG_PARITY_WORDS 65536       // 8-byte words per epoch parity of a peer mailbox (mppi_xchg_bytes = 2 x this x 8)
 
+// doubles of the finisher's staging area: every record it polls (LL mode: xw x npub cluster records; sharded rank-record
+// mode: one per rank); a single GPU in ticket mode stages nothing
+__host__ __device__ inline int fused_xstage_doubles(bool sharded, int world, int npub, int R) {
+    const int xw = sharded ? world : 1;
+    return (npub > 1 || sharded) ? xw * npub * (R + 2) : 0;
+}
+
 // this CTA's running warp records: (beta = +inf, eta = 0, V = 0); call before the first barrier of the kernel
 template <typename real>
 __device__ __forceinline__ void warp_records_init(const KArgs<real>& a, Smem<real>& sm) {
@@ -971,30 +979,57 @@ __device__ void combine_records(Load ld, int nrec, Smem<real>& sm, int R, double
     typedef Ops<real> O;
     constexpr int PF = 8;
     const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
-    double b = (double)INFINITY;
-    for (int q = lane; q < nrec; q += 32) b = fmin(b, ld(q, 0));
+    // every load that does not depend on beta is issued BEFORE beta is reduced: the lane-parallel beta loads and the
+    // first batch of this warp's records (beta_q, eta_q, row block 0) — one memory round trip for the common case
+    constexpr int NB = 4;                                  // beta loads per lane issued up front (covers 128 records)
+    double bl[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) bl[i] = (lane + 32 * i < nrec) ? ld(lane + 32 * i, 0) : (double)INFINITY;
+    double bq[PF], eq[PF], v0[PF];
+    const int jc0 = lane < R ? lane : 0;
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const int q = warp + u * nw;
+        const bool ok = q < nrec;
+        bq[u] = ok ? ld(q, 0) : (double)INFINITY;
+        eq[u] = ok ? ld(q, 1) : 0.0;
+        v0[u] = ok ? ld(q, 2 + jc0) : 0.0;
+    }
+    double b = bl[0];
+#pragma unroll
+    for (int i = 1; i < NB; ++i) b = fmin(b, bl[i]);
+    for (int q = lane + 32 * NB; q < nrec; q += 32) b = fmin(b, ld(q, 0));
     const double beta = warp_min<double>(b);             // every warp computes it (no barrier)
     double* mine = sm.part2 + (size_t)warp * R;
     for (int j = lane; j < R; j += 32) mine[j] = 0.0;
     double eta_p = 0.0;
     for (int q0 = warp; q0 < nrec; q0 += PF * nw) {
+        const bool first = q0 == warp;
         double s[PF];
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
             const int q = q0 + u * nw;
+            const bool ok = q < nrec;
+            const double bqu = first ? bq[u] : (ok ? ld(q, 0) : (double)INFINITY);
+            const double equ = first ? eq[u] : (ok ? ld(q, 1) : 0.0);
             // the rescale factor in the controller's precision (exact for equal betas; beta_q - beta is exact in fp64)
-            s[u] = q < nrec ? (double)O::exp_((real)(nfl * (ld(q, 0) - beta))) : 0.0;
-            if (q < nrec) eta_p += s[u] * ld(q, 1);
+            s[u] = ok ? (double)O::exp_((real)(nfl * (bqu - beta))) : 0.0;
+            eta_p += s[u] * equ;
         }
         for (int jb = 0; jb < R; jb += 32) {
             const int j = jb + lane;
             const int jc = j < R ? j : 0;
-            double v[PF];
-#pragma unroll
-            for (int u = 0; u < PF; ++u) v[u] = (q0 + u * nw < nrec) ? ld(q0 + u * nw, 2 + jc) : 0.0;
             double acc = 0.0;
+            if (first && jb == 0) {
 #pragma unroll
-            for (int u = 0; u < PF; ++u) acc += s[u] * v[u];
+                for (int u = 0; u < PF; ++u) acc += s[u] * v0[u];
+            } else {
+                double v[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) v[u] = (q0 + u * nw < nrec) ? ld(q0 + u * nw, 2 + jc) : 0.0;
+#pragma unroll
+                for (int u = 0; u < PF; ++u) acc += s[u] * v[u];
+            }
             if (j < R) mine[j] += acc;
         }
     }
@@ -1014,44 +1049,62 @@ __device__ void combine_records(Load ld, int nrec, Smem<real>& sm, int R, double
     __syncthreads();
 }
 
-// ---- peer mailboxes: records of (R+2) doubles as LL words (payload32 | flag32), record r at word r * 2 (R+2) -------
+// ---- record mailboxes: records of (R+2) doubles as LL words (payload32 | flag32), record r at word r * 2 (R+2) ------
+// a.peers[g], g < xw, are the mailboxes the record goes to: every rank's (sharded controller, over NVLink) or just this
+// GPU's own (single GPU: a region of the workspace) — self-validating words need no fence and no ticket, the finisher
+// sees a record one store-to-poll latency after it was written.
 template <typename real>
-__device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int rec_index, const double* src) {
+__device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int xw, int rec_index, const double* src) {
     const int nwords = 2 * (a.R + 2);
     const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
-    const size_t off = (size_t)(a.epoch & 1ull) * MPPI_XCHG_PARITY_WORDS + (size_t)rec_index * nwords;
+    const size_t off = (size_t)(a.epoch & 1ull) * a.xchg_parity_words + (size_t)rec_index * nwords;
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(src[i >> 1]);
         const uint32_t half = (i & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
         const unsigned long long word = ((unsigned long long)flag << 32) | half;
-        for (int g = 0; g < a.world; ++g) st_peer(a.peers[g] + off + i, word);
+        for (int g = 0; g < xw; ++g) st_peer(a.peers[g] + off + i, word);
     }
 }
-// all threads of the CTA; nrec records from this rank's own mailbox into sm.xstage (doubles).  Returns 0, or 1 on timeout.
+// all threads of the CTA; nrec records from this rank's own mailbox into sm.xstage (doubles), PB polls in flight per
+// thread.  Returns 0, or 1 on timeout.
 template <typename real>
-__device__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int nrec) {
-    const int nwords = nrec * 2 * (a.R + 2);
+__device__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int own, int nrec) {
+    constexpr int PB = 8;
+    const int nwords = nrec * 2 * (a.R + 2), BD = blockDim.x;
     const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
-    const unsigned long long* mine = a.peers[a.rank] + (size_t)(a.epoch & 1ull) * MPPI_XCHG_PARITY_WORDS;
+    const unsigned long long* mine = a.peers[own] + (size_t)(a.epoch & 1ull) * a.xchg_parity_words;
     uint32_t* dst = reinterpret_cast<uint32_t*>(sm.xstage);
     __shared__ int s_timeout;
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
     unsigned long long t0 = 0;
-    for (int e = threadIdx.x; e < nwords; e += blockDim.x) {
-        unsigned long long rec;
+    for (int base = threadIdx.x; base < nwords; base += BD * PB) {
+        unsigned int pending = 0;
+#pragma unroll
+        for (int u = 0; u < PB; ++u)
+            if (base + u * BD < nwords) pending |= 1u << u;
         unsigned int spins = 0;
-        while (true) {
-            rec = ld_poll(mine + e);
-            if ((uint32_t)(rec >> 32) == flag) break;
-            if ((++spins & 1023u) == 0) {
+        while (pending) {
+            unsigned long long w[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u)
+                if (pending & (1u << u)) w[u] = ld_poll(mine + base + u * BD);
+#pragma unroll
+            for (int u = 0; u < PB; ++u)
+                if ((pending & (1u << u)) && (uint32_t)(w[u] >> 32) == flag) {
+                    dst[base + u * BD] = (uint32_t)w[u];
+                    pending &= ~(1u << u);
+                }
+            if (pending && (++spins & 255u) == 0) {
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (t0 == 0) t0 = now;
-                if (now - t0 > a.xchg_timeout_ns || s_timeout) { s_timeout = 1; break; }
+                if (now - t0 > a.xchg_timeout_ns || s_timeout) {
+                    s_timeout = 1;
+                    break;
+                }
             }
         }
-        dst[e] = (uint32_t)rec;
     }
     __syncthreads();
     return s_timeout;
@@ -1089,7 +1142,12 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
     const int cr = blockIdx.x % cs, cid = blockIdx.x / cs, NC = gridDim.x / cs;
     const double nfl = (double)a.nm.neg_inv_lambda;
     const bool sharded = a.world > 1 && !a.export_partial;
-    const bool direct = sharded && a.xchg_npub > 1;          // cluster records go straight to the peers
+    const int xw = sharded ? a.world : 1;                    // ranks whose records the finisher combines
+    const int xr = sharded ? a.rank : 0;                     // this rank's slot among them
+    // LL mode: the cluster records go out as flagged words (to this GPU's mailbox, and every peer's on a sharded
+    // controller); the leader of cluster 0 polls for all xw x NC of them — no fence, no ticket.  Otherwise (grids whose
+    // records do not fit the finisher's staging area): records to the L2 workspace, ticket among the leaders.
+    const bool ll = NC > 1 && a.xchg_npub == NC;
     __shared__ int s_is_last;
 
     // (1) warp records -> the cluster leader's shared memory
@@ -1115,13 +1173,12 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
         const double* recs = sm.wrec;
         combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, cs * nrw, sm, R, nfl);
     }
-    // (3) publish the cluster record; ticket among the leaders of this GPU
-    if (direct) {
-        xchg_publish<real>(a, a.rank * NC + cid, sm.numd);
+    // (3) publish the cluster record
+    if (ll) {
+        xchg_publish<real>(a, xw, xr * NC + cid, sm.numd);
+        if (cid != 0) return false;                          // the leader of cluster 0 finishes the command
     } else if (NC > 1) {
         for (int i = tid; i < RW; i += BD) a.crec[(size_t)cid * RW + i] = sm.numd[i];
-    }
-    if (NC > 1) {
         __syncthreads();        // every thread's stores precede thread 0's release (one MEMBAR per leader)
         if (tid == 0) {
             unsigned int t;
@@ -1134,8 +1191,15 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
     }
     stamp(a.dbg, 8);
 
-    // (4) finisher: the rank's records -> (beta, eta, numerators) in sm.numd
-    if (!direct && NC > 1) {
+    // (4) finisher: all records -> (beta, eta, numerators) in sm.numd
+    if (ll) {
+        if (xchg_collect<real>(a, sm, xr, xw * NC)) {
+            xchg_timed_out<real, VARIANT>(a, sm, NU);
+            return true;
+        }
+        const double* recs = sm.xstage;
+        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, xw * NC, sm, R, nfl);
+    } else if (NC > 1) {
         const double* recs = a.crec;
         combine_records<real>([&](int q, int i) { return __ldcg(recs + (size_t)q * RW + i); }, NC, sm, R, nfl);
     }
@@ -1156,17 +1220,15 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
         }
         return true;
     }
-    if (sharded) {
-        // rank-record mode: this rank's combined record is its one published record; direct mode: the cluster
-        // records of every rank are already on their way
-        if (!direct) xchg_publish<real>(a, a.rank, sm.numd);
-        const int nrec = a.world * (direct ? NC : 1);
-        if (xchg_collect<real>(a, sm, nrec)) {
+    if (sharded && !ll) {
+        // rank-record mode: this rank's combined record is its one published record
+        xchg_publish<real>(a, xw, xr, sm.numd);
+        if (xchg_collect<real>(a, sm, xr, xw)) {
             xchg_timed_out<real, VARIANT>(a, sm, NU);
             return true;
         }
         const double* recs = sm.xstage;
-        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, nrec, sm, R, nfl);
+        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, xw, sm, R, nfl);
     }
     stamp(a.dbg, 11);
     finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);
@@ -1200,6 +1262,8 @@ __device__ void make_env_args(const KArgs<real>& in, KArgs<real>* out) {
             out->etaP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.etaP) + off);
             out->VP = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(in.VP) + off);
             out->crec = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(in.crec) + off);
+            if (in.world == 1 || in.export_partial)      // this GPU's own record mailbox lives in the environment's workspace
+                out->peers[0] = reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(in.peers[0]) + off);
         }
         if (in.out_pa) out->out_pa = in.out_pa + e * K * TN;
         if (in.out_noise) out->out_noise = in.out_noise + e * K * TN;
@@ -1311,7 +1375,7 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
     if (BATCHED) make_env_args<real, NX, NU>(a_in, reinterpret_cast<KArgs<real>*>(a_env_raw));
     const KArgs<real>& a = BATCHED ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
-    const int xst = (a.world > 1 && !a.export_partial) ? a.world * a.xchg_npub * (a.R + 2) : 0;
+    const int xst = fused_xstage_doubles(a.world > 1 && !a.export_partial, a.world, a.xchg_npub, a.R);
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1,
                                            layout_extra(VARIANT != V_MPPI, SPLIT ? NX : 0, (int)cluster_nctarank(), xst));
     Smem<real> sm(smem, L);

@@ -49,6 +49,7 @@ struct Plan {
     Geometry g;
     int is_double, nx, upc_nu, pdl;
     unsigned long long epoch, host_epoch;
+    unsigned long long res_epoch_off;  // resident mode: record-mailbox epoch of command seq = res_epoch_off + seq
     alignas(16) unsigned char kargs[sizeof(KArgs<double>)];
     alignas(16) unsigned char mparams[12288];
 };
@@ -143,11 +144,15 @@ template <typename real> void fill_noise_model(const MppiFusedParams* p, NoiseMo
 
 // ticket + per-CTA partials (beta_b, eta_b, V_b[R]) of type `real` (stepped-route / resident / tensor-core tails), or
 // ticket + per-cluster records of (R + 2) doubles (fused kernel's warp-fold tail): the larger of the two
-inline uint64_t ws_bytes(int nb, int R, int es) {
+// ... followed by this GPU's own record mailbox (single-GPU LL mode): two epoch parities of MPPI_LL_LOCAL_WORDS flagged words
+#define MPPI_LL_STAGE_BYTES 49152                          // finisher staging budget: LL mode needs xw x clusters x (R+2) x 8 <= this
+#define MPPI_LL_LOCAL_WORDS (2 * MPPI_LL_STAGE_BYTES / 8)  // words per parity of the local mailbox (2 words per double)
+inline uint64_t ws_partials_bytes(int nb, int R, int es) {
     const uint64_t per_cta = 16 + 2 * (uint64_t)align_up(nb * es, 16) + (uint64_t)align_up(nb * R * es, 16);
     const uint64_t per_cluster = 16 + (uint64_t)nb * (uint64_t)(R + 2) * 8;
-    return per_cta > per_cluster ? per_cta : per_cluster;
+    return ((per_cta > per_cluster ? per_cta : per_cluster) + 255) / 256 * 256;
 }
+inline uint64_t ws_bytes(int nb, int R, int es) { return ws_partials_bytes(nb, R, es) + 2ull * MPPI_LL_LOCAL_WORDS * 8; }
 
 inline unsigned long long xchg_timeout_ns() {
     // how long a shard waits for its peers' records before giving up (rank skew: a GC pause, a JIT build, a lazy module
@@ -202,6 +207,7 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
         a.crec = (double*)(w + 16);
     }
     a.xchg_npub = 1;
+    a.xchg_parity_words = MPPI_XCHG_PARITY_WORDS;
     a.xchg_timeout_ns = xchg_timeout_ns();
     a.xchg_status_host = (long long*)p->xchg_status_host;
     a.rank = p->rank;
@@ -224,6 +230,11 @@ template <typename real> int fill_kargs(const MppiFusedParams* p, KArgs<real>& a
         any_peer = any_peer || p->peer_slots[g] != nullptr;
     }
     if (!any_peer || a.export_partial) a.world = a.export_partial ? a.world : 1;
+    if (p->workspace != nullptr && (a.world == 1 || a.export_partial)) {
+        // not sharded in-kernel: the record mailbox is this GPU's own, behind the partials in the workspace
+        a.peers[0] = (unsigned long long*)((unsigned char*)p->workspace + ws_partials_bytes(nb, a.R, es));
+        a.xchg_parity_words = MPPI_LL_LOCAL_WORDS;
+    }
     return MPPI_OK;
 }
 
@@ -273,6 +284,16 @@ int launch_kernel(void (*kernel)(Args...), int nb, int BD, int smem, cudaStream_
     return MPPI_OK;
 }
 
+// LL mode identifies a command's records by its epoch tag: a launch captured into a CUDA graph would replay one tag.
+inline int refuse_capture(cudaStream_t stream, const Geometry& g) {
+    if (g.npub <= 1) return MPPI_OK;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+        return UNSUPPORTED("the fused command cannot be captured into a CUDA graph (its reduction records carry a per-command tag); "
+                           "launch it directly — it is one kernel — or set MPPI_B200_XCHG_DIRECT=0");
+    return MPPI_OK;
+}
+
 struct GeomKey {
     const void* kernel;
     int dev, variant, K, T, nu, S, bt, tp, gb, r2, single, ne;
@@ -285,6 +306,7 @@ struct GeomKey {
 // Launch geometry for (kernel, dimensions).  The occupancy / attribute queries cost microseconds, so
 // the last few results are cached per thread: a steady-state command() pays only the lookup.
 static thread_local int g_tc_kernel = 0;   // set around plan_geometry() for the tcgen05 kernels (see below)
+static thread_local int g_tc_cols = 64;    // TMEM columns one CTA of that kernel allocates
 template <typename KernelT>
 int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_rows2, bool single_partial_grid, Geometry& g,
                   SmemLayout (*layout)(int, int, int, int, int, int, int, int, int)) {
@@ -383,13 +405,13 @@ int plan_geometry(KernelT kernel, const MppiFusedParams* p, int es, int need_row
         if (g_tc_kernel) {
             // The occupancy API answers 1 CTA/SM for kernels that allocate tensor memory; measured on B200 the
             // 128-thread tcgen05 CTAs do co-reside (K=131072, T=30: 585 us at 1 CTA/SM, 379 at 2, 311 at 3), so
-            // size the grid from the real limits: shared memory, registers, and 64 of 512 TMEM columns per CTA.
+            // size the grid from the real limits: shared memory, registers, and the CTA's share of the 512 TMEM columns.
             int smem_sm = 0;
             CK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
             const int by_smem = smem_sm / ((int)fa.sharedSizeBytes + L.total + 1024);
             const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * BD);
             int o = by_smem < by_regs ? by_smem : by_regs;
-            if (o > 512 / 64) o = 512 / 64;
+            if (o > 512 / g_tc_cols) o = 512 / g_tc_cols;
             const char* e = getenv("MPPI_TC_OCC");
             if (e != nullptr && atoi(e) > 0) o = atoi(e);
             if (o > occ) occ = o;

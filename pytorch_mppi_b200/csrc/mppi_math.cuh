@@ -494,9 +494,13 @@ struct PendulumMLPModel {
             asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
             return y;
         }
-        // 1 - 2 / (1 + e^{2x}) on the SFU: saturates correctly (e^{2x} -> inf gives 1, -> 0 gives -1)
-        const float t = __expf(2.0f * x);                       // MUFU.EX2
-        return fmaf(-2.0f, __fdividef(1.0f, 1.0f + t), 1.0f);   // MUFU.RCP
+        // 1 - 2 / (1 + e^{2x}): saturates correctly (e^{2x} -> inf gives 1, -> 0 gives -1).  ex2.approx.ftz + rcp.approx.ftz
+        // directly (one FMUL folds the 2 log2(e); no denormal pre-scaling, no x + x): FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA —
+        // five instructions, two of them on the XU pipe, abs error < 5e-7
+        float t, r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.8853900817779268f));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+        return fmaf(-2.0f, r, 1.0f);
 #else
         return tanhf(x);
 #endif

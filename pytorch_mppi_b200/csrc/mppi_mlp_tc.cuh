@@ -1,13 +1,21 @@
 // mppi_mlp_tc.cuh — tensor-core variant of the fused command kernel for the learned pendulum model
 // (BASELINE config 4: 3-32-32-2 tanh residual MLP, /root/reference/tests/pendulum_approximate.py:47-67).
 //
-// The network's three layers are genuine dense contractions, so per rollout step a CTA of 128 threads
-// (= 128 samples = the 128 TMEM lanes of one M=128 UMMA tile) runs them on the 5th-gen tensor cores:
+// The network's three layers are genuine dense contractions, so per rollout step a CTA of 128 samples (= the 128 TMEM
+// lanes of one M=128 UMMA tile) runs them on the 5th-gen tensor cores:
 //   registers -> bf16 operand tile in shared memory (canonical K-major, no swizzle)
-//   tcgen05.mma.cta_group::1.kind::f16  (one elected thread)  -> fp32 accumulator in TMEM
-//   tcgen05.commit -> mbarrier -> every thread tcgen05.ld's ITS OWN row (lane = sample) -> bias, tanh
+//   tcgen05.mma.cta_group::1.kind::f16  (one elected thread)  -> fp32 accumulators in TMEM
+//   tcgen05.commit -> mbarrier -> tcgen05.ld of the thread's own row (lane = sample) -> tanh -> next operand row
 // three times per step.  Everything else (sampling, clamp, cost, softmin fold, last-CTA update) is the
 // code of mppi_fused.cuh.
+//
+// Round 2: a step is a serial chain of three MMA round trips (7,090 clocks per step measured at BASELINE config 4, the
+// tensor pipe itself 7 % busy), so the kernel shortens the chain instead of widening the MMAs:
+//   * TWO threads per sample (256-thread CTAs): warps w and w+4 own the same 32 TMEM lanes and split the 32 hidden
+//     units — 16 tanh + 16 packs each instead of 32 (`tcgen05.ld.32x32b.x16` on their half of the columns);
+//   * NACC = 4: the 7 K-steps of a hi/lo-split layer accumulate into FOUR independent TMEM accumulators (chains of at
+//     most two dependent MMAs instead of seven), summed in registers after the load;
+//   * tanh = FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA (mppi_math.cuh).
 //
 // Precision: operands are bf16.  In the default (SPLIT) mode activations and weights are split into hi + lo
 // bf16 parts and each layer is issued as  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  ("3 x bf16": the a_hi chunks are
@@ -30,7 +38,12 @@ namespace tc {
 constexpr int H = 32;             // hidden width
 constexpr int KX3 = 64;           // SPLIT: activations of layers 2 and 3 are stored as [a_hi(32) | a_lo(32)]
 constexpr int CH = 128;           // bytes of one 8-row x 16-byte core matrix
-constexpr int TMEM_COLS = 64;     // D1: cols [0,32), D2: [32,64), D3: [0,16) (D1 is dead by then)
+// TMEM columns per CTA.  NACC = 1: D1 [0,32), D2 [32,64), D3 [0,16) (D1 is dead by then) = 64.
+// NACC = 4 (hi/lo split: 4 accumulators, plain bf16: 2): D1 [0,32), D2 [32, 32+32a), D3 after it, 16 columns each.
+__host__ __device__ constexpr int n_acc(int split, int nacc) { return nacc <= 1 ? 1 : (split ? 4 : 2); }
+__host__ __device__ constexpr int tmem_cols(int split, int nacc) {
+    return nacc <= 1 ? 64 : (split ? 256 : 128);
+}
 
 // shared-memory operand tiles (bytes); canonical K-major/no-swizzle: core (row group g, k-chunk c) at
 // g*SBO + c*LBO, rows 16 B apart inside a core, LBO = 128 B (adjacent chunks), SBO = chunks*128 B
@@ -94,6 +107,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld2_nowait(uint32_t taddr, float& v0, float& v1) {
+    uint32_t r0, r1;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+    v0 = __uint_as_float(r0);
+    v1 = __uint_as_float(r1);
+}
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& v0, float& v1) {
     uint32_t r0, r1;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
@@ -141,11 +173,31 @@ template <int SPLIT, int CHUNKS> __device__ __forceinline__ void write_a_row(uns
     }
 }
 
+// 16 of a thread-pair's 32 activations -> its two chunks of the operand row (half = 0: hidden units 0..15, 1: 16..31)
+template <int SPLIT, int CHUNKS> __device__ __forceinline__ void write_a_half(unsigned char* A, int row, int half, const float* h) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hi[i] = cvt2(h[2 * i], h[2 * i + 1]);
+        if (SPLIT) {
+            const float r0 = h[2 * i] - __uint_as_float(hi[i] << 16);
+            const float r1 = h[2 * i + 1] - __uint_as_float(hi[i] & 0xFFFF0000u);
+            lo[i] = cvt2(r0, r1);
+        }
+    }
+    unsigned char* base = A + (row >> 3) * (CHUNKS * CH) + (row & 7) * 16;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        *reinterpret_cast<uint4*>(base + (2 * half + c) * CH) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        if (SPLIT) *reinterpret_cast<uint4*>(base + (4 + 2 * half + c) * CH) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    }
+}
+
 }  // namespace tc
 
 // =================================================================================================
-template <int VARIANT, int SPLIT, int FAST>
-__global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_constant__ KArgs<float> a,
+template <int VARIANT, int SPLIT, int FAST, int NACC>
+__global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_constant__ KArgs<float> a,
                                                              const __grid_constant__ PendulumMLPModel::P<float> mp) {
     typedef float real;
     typedef Ops<real> O;
@@ -156,6 +208,11 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     constexpr int KB = SPLIT ? tc::KX3 : H;
     constexpr int KX = KB + 16;
     constexpr int CHUNKS = KX / 8, NSTEP = KX / 16;
+    // accumulators: NA independent TMEM column blocks per layer; K-step s of the main tile goes to block s / 2, the two
+    // K-steps of the w_lo tile (SPLIT) to blocks (NSTEP + s) / 2 — chains of at most two dependent MMAs
+    constexpr int NA = tc::n_acc(SPLIT, NACC);
+    constexpr int TMEM_COLS = tc::tmem_cols(SPLIT, NACC);
+    constexpr int C2 = 32, C3 = NACC <= 1 ? 0 : 32 + 32 * NA;       // NACC = 1: D3 reuses D1's columns (dead by then)
     extern __shared__ __align__(16) unsigned char smem[];
     // one operand tile for all three layers: columns [0,KB) hold the hidden activations (layer 2's, then layer
     // 3's); the last K-step [KB,KB+16) holds layer 1's row [x0h x0h x0l x1h x1h x1l uh uh | ul 1 1 0...], whose
@@ -168,8 +225,9 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     __shared__ __align__(128) unsigned char sB3lo[SPLIT ? 16 * H * 2 : 128];
     __shared__ __align__(8) unsigned long long s_mma_bar;
     __shared__ uint32_t s_tmem_base;
-    const int tid = threadIdx.x, BD = blockDim.x;      // BD == 128
+    const int tid = threadIdx.x, BD = blockDim.x;      // BD == 256: thread = (sample row tid % 128, half tid / 128)
     const int warp = tid >> 5;
+    const int row = tid & 127, half = tid >> 7;
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BD / a.tps, gridDim.x, 0);
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
@@ -178,7 +236,7 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     // ---- one-time setup: TMEM, MMA barrier, bf16 weight tiles (hi/lo split, K-extended) -----------------
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
-                     "r"((uint32_t)tc::TMEM_COLS)
+                     "r"((uint32_t)TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -252,7 +310,7 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     __syncthreads();
     tc::fence_after();
     const uint32_t tmem = s_tmem_base;
-    const uint32_t my_lane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes; thread = lane = sample row
+    const uint32_t my_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // warps w and w+4 own TMEM lanes 32 (w % 4) ..: lane = sample row
     uint32_t mma_phase = 0;
     const uint64_t dB1 = tc::smem_desc(sB1, 2 * tc::CH);
     const uint64_t dA2 = tc::smem_desc(sA2, CHUNKS * tc::CH), dB2 = tc::smem_desc(sB2, CHUNKS * tc::CH),
@@ -266,11 +324,10 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     bool staged = false;
     real beta_run = O::inf(), eta_run = (real)0;
 
-    // Tile = BS samples.  BS = 128: every thread rolls one sample.  BS = 64 (threads_per_sample = 2, chosen by the
-    // host when 128-sample tiles would leave SMs idle): warps 0-1 roll, warps 2-3 only help with the draws and
-    // the colour/clamp pass and then keep the CTA barriers company; rows 64..127 of the MMA are padding.
+    // Tile = 128 samples; the two threads of a sample share its draws and its colour/clamp pass (a.tps == 2), thread 0
+    // of the pair (half 0, warps 0-3) carries the state, the cost and the layer-1 operand row.
     const int BS = BD / a.tps;
-    const bool roller = tid < BS;                      // warp-uniform (BS is a multiple of 32)
+    const bool roller = half == 0;                     // warp-uniform
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int k = tile * BS + (tid % BS);
         const bool in_range = k < a.K;
@@ -281,11 +338,11 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
         if (!staged) {
             stage_finish<real, VARIANT, NU>(a, sm);
             staged = true;
-        } else if (a.tps > 1) {
+        } else {
             __syncthreads();
         }
         if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
-        if (a.tps > 1) __syncthreads();
+        __syncthreads();
 
         // ---- rollout: the MMAs are CTA-wide, so every thread keeps the step's three barriers ----------------
         real x[NX] = {(real)0, (real)0};
@@ -316,9 +373,9 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
                 tc::split_bf16(x[1], h1, l1);
                 tc::split_bf16(uc, h2, l2);
                 const __nv_bfloat16 z = __float2bfloat16_rn(0.0f), one = __float2bfloat16_rn(1.0f);
-                unsigned char* row = sA2 + (tid >> 3) * (CHUNKS * tc::CH) + (KB / 8) * tc::CH + (tid & 7) * 16;
-                *reinterpret_cast<uint4*>(row) = make_uint4(tc::pack2(h0, h0), tc::pack2(l0, h1), tc::pack2(h1, l1), tc::pack2(h2, h2));
-                *reinterpret_cast<uint4*>(row + tc::CH) = make_uint4(tc::pack2(l2, one), tc::pack2(one, z), 0u, 0u);
+                unsigned char* rp = sA2 + (row >> 3) * (CHUNKS * tc::CH) + (KB / 8) * tc::CH + (row & 7) * 16;
+                *reinterpret_cast<uint4*>(rp) = make_uint4(tc::pack2(h0, h0), tc::pack2(l0, h1), tc::pack2(h1, l1), tc::pack2(h2, h2));
+                *reinterpret_cast<uint4*>(rp + tc::CH) = make_uint4(tc::pack2(l2, one), tc::pack2(one, z), 0u, 0u);
                 tc::fence_async_smem();
                 tc::fence_before();
             }
@@ -328,14 +385,15 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
                 tc::mma_f16(tmem + 0, dA1, dB1, I32, 0u);
                 tc::mma_commit(&s_mma_bar);
             }
-            float h[H];
-            if (roller) {
+            float hv[16];
+            {   // layer 1 -> tanh -> this thread's half of the layer-2 operand row
                 tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
                 tc::fence_after();
-                tc::tmem_ld32(my_lane + 0, h);
+                tc::tmem_ld16_nowait(my_lane + 16 * half, hv);
+                tc::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
-                tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);
+                for (int i = 0; i < 16; ++i) hv[i] = Model::tanh_(hv[i], FAST);
+                tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);
                 tc::fence_async_smem();
                 tc::fence_before();
             }
@@ -344,20 +402,31 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
             if (tid == 0) {
                 tc::fence_after();
 #pragma unroll
-                for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + 32, dA2 + s * KSTEP, dB2 + s * KSTEP, I32, s > 0 ? 1u : 0u);
+                for (int s = 0; s < NSTEP; ++s)
+                    tc::mma_f16(tmem + C2 + 32 * (NA > 1 ? s / 2 : 0), dA2 + s * KSTEP, dB2 + s * KSTEP, I32, (NA > 1 ? (s & 1) : (s > 0)) ? 1u : 0u);
                 if (SPLIT) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) tc::mma_f16(tmem + 32, dA2 + s * KSTEP, dB2lo + s * KSTEP, I32, 1u);
+                    for (int s = 0; s < 2; ++s)
+                        tc::mma_f16(tmem + C2 + 32 * (NA > 1 ? (NSTEP + s) / 2 : 0), dA2 + s * KSTEP, dB2lo + s * KSTEP, I32,
+                                    (NA > 1 ? ((NSTEP + s) & 1) : 1) ? 1u : 0u);
                 }
                 tc::mma_commit(&s_mma_bar);
             }
-            if (roller) {
+            {   // layer 2 -> sum of the accumulators -> tanh -> half row of the layer-3 operand
                 tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
                 tc::fence_after();
-                tc::tmem_ld32(my_lane + 32, h);
+                float acc[NA][16];
 #pragma unroll
-                for (int i = 0; i < H; ++i) h[i] = Model::tanh_(h[i], FAST);
-                tc::write_a_row<SPLIT, CHUNKS>(sA2, tid, h);             // MMA 2 has completed (barrier): its operand tile is free
+                for (int q = 0; q < NA; ++q) tc::tmem_ld16_nowait(my_lane + C2 + 32 * q + 16 * half, acc[q]);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float sum = acc[0][i];
+                    if (NA == 2) sum = acc[0][i] + acc[1][i];
+                    if (NA == 4) sum = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
+                    hv[i] = Model::tanh_(sum, FAST);
+                }
+                tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);     // MMA 2 has completed (barrier): its operand tile is free
                 tc::fence_async_smem();
                 tc::fence_before();
             }
@@ -366,24 +435,32 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
             if (tid == 0) {
                 tc::fence_after();
 #pragma unroll
-                for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + 0, dA2 + s * KSTEP, dB3 + s * KSTEP, I16, s > 0 ? 1u : 0u);
+                for (int s = 0; s < NSTEP; ++s)
+                    tc::mma_f16(tmem + C3 + 16 * (NA > 1 ? s / 2 : 0), dA2 + s * KSTEP, dB3 + s * KSTEP, I16, (NA > 1 ? (s & 1) : (s > 0)) ? 1u : 0u);
                 if (SPLIT) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) tc::mma_f16(tmem + 0, dA2 + s * KSTEP, dB3lo + s * KSTEP, I16, 1u);
+                    for (int s = 0; s < 2; ++s)
+                        tc::mma_f16(tmem + C3 + 16 * (NA > 1 ? (NSTEP + s) / 2 : 0), dA2 + s * KSTEP, dB3lo + s * KSTEP, I16,
+                                    (NA > 1 ? ((NSTEP + s) & 1) : 1) ? 1u : 0u);
                 }
                 tc::mma_commit(&s_mma_bar);
             }
+            tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+            tc::fence_after();
             if (roller) {
-                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
-                tc::fence_after();
-                float o0, o1;
-                tc::tmem_ld2(my_lane + 0, o0, o1);
-                const real th = O::add(x[0], o0);
+                float o0[NA], o1[NA];
+#pragma unroll
+                for (int q = 0; q < NA; ++q) tc::tmem_ld2_nowait(my_lane + C3 + 16 * q, o0[q], o1[q]);
+                tc::tmem_wait_ld();
+                float s0 = o0[0], s1 = o1[0];
+                if (NA == 2) { s0 = o0[0] + o0[1]; s1 = o1[0] + o1[1]; }
+                if (NA == 4) { s0 = (o0[0] + o0[1]) + (o0[2] + o0[3]); s1 = (o1[0] + o1[1]) + (o1[2] + o1[3]); }
+                const real th = O::add(x[0], s0);
                 x[0] = O::sub(remainder<real>(O::add(th, mp.pi), mp.two_pi), mp.pi);    // pendulum_approximate.py:65
-                x[1] = O::add(x[1], o1);
-                // the next step's layer-1 MMA overwrites D3's columns: order this read before the barrier that releases it
-                tc::fence_before();
+                x[1] = O::add(x[1], s1);
             }
+            // the next step's MMAs overwrite these accumulators: order the reads before the barrier that releases them
+            tc::fence_before();
             mma_phase ^= 1u;
             if (active) {
                 roll = O::add(roll, Model::template cost<real>(mp, x, &u));               // mppi.py:318-319
@@ -410,7 +487,7 @@ __global__ void __launch_bounds__(128) mlp_tc_command_kernel(const __grid_consta
     tc::fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)tc::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TMEM_COLS) : "memory");
     }
     publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
 }

@@ -6,28 +6,30 @@
 namespace {
 
 // ---- fused command ----------------------------------------------------------------------------
-// PENDULUM_MLP in fp32 with model_params[3] != 0: the tcgen05/TMEM kernel (mppi_mlp_tc.cuh).  One CTA = 128
-// threads = 128 samples = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
+// PENDULUM_MLP in fp32 with model_params[3] != 0: the tcgen05/TMEM kernel (mppi_mlp_tc.cuh).  One CTA = 256 threads = 128
+// samples (two threads per sample) = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
 template <class Model, typename real, int V, typename KernelT>
 bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, KernelT& kernel) {
     if constexpr (std::is_same<Model, PendulumMLPModel>::value && std::is_same<real, float>::value) {
         const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
         if ((mode == 1 || mode == 2) && p->n_env <= 1) {
             p_tc = *p;
-            // 128-thread CTAs, tiles of 128 samples (every thread rolls one).  The kernel also supports tiles of 64
-            // samples + 64 helper threads (MPPI_TC_TILE=64; twice the CTAs to spread over the SMs), but a CTA's step
-            // time is set by the three MMA round trips, not by its tanh work: measured K=32768, T=30: 132 us with
-            // half tiles against 113 us with full ones, so full tiles are the default at every K.
-            int bs = 128;
-            const char* e_bs = getenv("MPPI_TC_TILE");
-            if (e_bs != nullptr && (atoi(e_bs) == 64 || atoi(e_bs) == 128)) bs = atoi(e_bs);
-            p_tc.block_threads = bs;
-            p_tc.threads_per_sample = 128 / bs;
+            p_tc.block_threads = 128;                   // samples per tile
+            p_tc.threads_per_sample = 2;
             p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
             const bool fast = p->model_params[2] != 0.0;
-            kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
-                               : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
+            // MPPI_TC_NACC=1: one TMEM accumulator per layer (a chain of 7 dependent MMAs in hi/lo-split mode) instead
+            // of independent accumulators summed in registers — kept for A/B timing
+            const char* e_na = getenv("MPPI_TC_NACC");
+            const bool one = e_na != nullptr && atoi(e_na) == 1;
+            if (one)
+                kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1, 1> : mlp_tc_command_kernel<V, 1, 0, 1>)
+                                   : (fast ? mlp_tc_command_kernel<V, 0, 1, 1> : mlp_tc_command_kernel<V, 0, 0, 1>);
+            else
+                kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1, 4> : mlp_tc_command_kernel<V, 1, 0, 4>)
+                                   : (fast ? mlp_tc_command_kernel<V, 0, 1, 4> : mlp_tc_command_kernel<V, 0, 0, 4>);
             g_tc_kernel = 1;
+            g_tc_cols = tc::tmem_cols(mode == 1, one ? 1 : 4);
             // co-residency is bounded by shared memory: ask for the largest carve-out
             cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             return true;
@@ -111,20 +113,20 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
     const int envs = batched ? p->n_env : 1;
     g.cluster = 1;
-    g.npub = sharded ? 1 : 0;
+    g.npub = 1;
     for (int cs = 8; cs >= 1; cs >>= 1) {
         if (cs > want && cs > 1) continue;
         const int nbp = (g.nb + cs - 1) / cs * cs;
         if (cs > 2 && nbp > di.sm_count) continue;                        // 8 / 4: one wave of at most one CTA per SM (pairs pack anywhere)
         if (cs > 1 && (g.nb < 2 || nbp > di.sm_count * g.occ)) continue;
         const int NC = nbp / cs;
-        // direct mode: every rank's cluster records are staged by the finisher (world x NC x (R+2) doubles)
-        int npub = sharded ? 1 : 0;
-        if (sharded && NC > 1 && (long long)world * NC * (R + 2) * 8 <= 49152 && (long long)world * NC * 2 * (R + 2) <= MPPI_XCHG_PARITY_WORDS)
-            npub = NC;
+        // LL mode: the finisher (leader of cluster 0) stages every rank's cluster records: xw x NC x (R+2) doubles
+        const int xw = sharded ? world : 1;
+        int npub = 1;
+        if (NC > 1 && (long long)xw * NC * (R + 2) * 8 <= MPPI_LL_STAGE_BYTES) npub = NC;
         if (const char* e = getenv("MPPI_B200_XCHG_DIRECT"))
-            if (atoi(e) == 0 && sharded) npub = 1;
-        const int xst = sharded ? world * npub * (R + 2) : 0;
+            if (atoi(e) == 0) npub = 1;
+        const int xst = fused_xstage_doubles(sharded, world, npub, R);
         const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, 1, layout_extra(tile2, split ? Model::NX : 0, cs, xst));
         if (L.total > dyn_limit) continue;
         if (cs > 1) {
@@ -195,6 +197,11 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
     typename Model::template P<real> mp;
     Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    if ((rc = refuse_capture(stream, g)) != MPPI_OK) return rc;
+    if (a.world == 1 || a.export_partial) {       // plan-less single-GPU launches draw their record tags from one process-wide counter
+        static unsigned long long s_epoch = 0;
+        a.epoch = __atomic_add_fetch(&s_epoch, 1ull, __ATOMIC_RELAXED);
+    }
     void* argv2[2] = {(void*)&a, (void*)&mp};
     cudaError_t e = launch_raw(c.kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env, g.cluster);
     if (e != cudaSuccess) return cuda_fail(e, "fused launch");
@@ -247,6 +254,7 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     pl->upc_nu = p->u_per_command * p->nu;
     pl->pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
     pl->epoch = p->epoch;
+    pl->res_epoch_off = 0;
     pl->host_epoch = p->host_epoch;      // monotonic across re-plans: a stale mailbox tag of an earlier plan can never match
     pl->p = *p;
     return MPPI_OK;

@@ -50,6 +50,7 @@ struct ResidentArgs {
     unsigned long long seq_start;         // commands up to here are done; the kernel waits for seq_start + 1
     unsigned long long offset_pred;       // Philox counter the next command is expected to carry
     unsigned long long idle_ns;           // leave after this long without a record
+    unsigned long long epoch_off;         // record-mailbox epoch of command seq = epoch_off + seq (continues the plan's epochs)
     unsigned int gen;                     // launch generation, echoed in the exit word
     int shift_pred;                       // shift flag the next command is expected to carry
     int n_words;                          // words per record
@@ -143,7 +144,8 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
         __syncthreads();
     }
     const int BS = BD / a.tps;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1, layout_extra(VARIANT != V_MPPI, NX, (int)cluster_nctarank(), 0));
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1,
+                                           layout_extra(VARIANT != V_MPPI, NX, (int)cluster_nctarank(), fused_xstage_doubles(false, 1, a.xchg_npub, a.R)));
     Smem<real> sm(smem, L);
 
     // one tile per CTA
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
             a.offset = offset;
             a.shift = shift;
             a.host_epoch = seq + 1;
+            a.epoch = ra.epoch_off + seq + 1;
             uint32_t* x0w = reinterpret_cast<uint32_t*>(a.x0);
             for (int i = 0; i < NX * WPV; ++i) x0w[i] = s_cmd[3 + i];
         }

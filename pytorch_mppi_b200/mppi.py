@@ -442,7 +442,7 @@ class MPPI:
             self.launch_info = info
             need = int(info.workspace_bytes)
         else:
-            need = 16 + 148 * 16 * (2 + self._noise_rows()) * 8 + 64
+            need = 16 + 148 * 16 * (2 + self._noise_rows()) * 8 + 256 + 2 * 12288 * 8
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.zeros(need, device=self.d, dtype=torch.uint8)
         p.workspace = self._workspace.data_ptr()
@@ -477,6 +477,8 @@ class MPPI:
         if plan is not None:
             if getattr(self, "_resident", False):        # mppi_plan_destroy sends the resident grid away
                 self._resident, self._resident_wanted = False, self._resident_idle_us
+            # the next plan continues this one's command epochs (the tags of the reduction / exchange records)
+            self._epoch = max(self._epoch, int(self._lib.mppi_plan_epoch(plan)))
             self._lib.mppi_plan_destroy(plan)
             self._plan = None
 
@@ -1491,8 +1493,8 @@ class MPPI_Batched(MPPI):
         es = _ES[self.dtype]
         rows = self.T * self.nu
         nb_max = min((self.K + 31) // 32 + 1, 148 * 16)
-        stride = max(16 + 2 * ((nb_max * es + 15) // 16 * 16) + ((nb_max * rows * es + 15) // 16 * 16),
-                     16 + nb_max * (rows + 2) * 8) + 64          # per-CTA partials / per-cluster records (ws_bytes)
+        stride = (max(16 + 2 * ((nb_max * es + 15) // 16 * 16) + ((nb_max * rows * es + 15) // 16 * 16),
+                      16 + nb_max * (rows + 2) * 8) + 255) // 256 * 256 + 2 * 12288 * 8   # ws_bytes: partials / records + local mailbox
         self._env_ws_stride = (stride + 255) // 256 * 256
         need = self._env_ws_stride * self.N
         if self._workspace is None or self._workspace.numel() < need:

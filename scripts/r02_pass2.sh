@@ -11,18 +11,22 @@ for v in mppi smppi kmppi; do ( timeout 60 python scripts/phase_clocks.py 8192 4
 for cs in 8 4 2 1; do
   ( MPPI_B200_CLUSTER=$cs timeout 200 python bench.py --workload pendulum_c2 --steps 1000 --warmup 20 --no-cpu-baseline --no-resident ) > gpurun_out/bench_c2_cluster$cs.json 2> gpurun_out/bench_c2_cluster$cs.err
 done
+for na in 4 1; do
+  ( MPPI_TC_NACC=$na timeout 200 python bench.py --workload mlp_c4 --steps 300 --warmup 10 --no-cpu-baseline ) > gpurun_out/bench_c4_nacc$na.json 2> gpurun_out/bench_c4_nacc$na.err
+done
+( timeout 200 python bench.py --workload mlp_c4 --mlp-mode bf16 --steps 300 --warmup 10 --no-cpu-baseline ) > gpurun_out/bench_c4_bf16.json 2> gpurun_out/bench_c4_bf16.err
 for w in pendulum_c2 nav2d_c3 pendulum_c5; do
   ( timeout 400 python bench.py --workload $w --steps 1000 --warmup 20 --cpu-seconds 4 ) > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
 done
-( nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/ubench_pipes scripts/ubench/pipes.cu && timeout 120 gpurun_out/ubench_pipes ) > gpurun_out/ubench_pipes.txt 2>&1
-rm -f gpurun_out/ubench_pipes
 echo "== pytest"; tail -25 gpurun_out/pytest_gpu.txt
 echo "== phase c2"; tail -13 gpurun_out/phase_c2.txt
 echo "== phase c2 (no cluster)"; tail -13 gpurun_out/phase_c2_nocluster.txt
 for cs in 8 4 2 1; do echo "== c2 cluster $cs"; python -c "
 import json;d=json.load(open('gpurun_out/bench_c2_cluster$cs.json'));print('flushed',round(d['ms_per_step']*1e3,2),'b2b',round(d['config']['back_to_back_ms_per_step']*1e3,2),'e2e',round(d['e2e']['ms_per_step']*1e3,2),'grid',d['config']['grid'],'regs',d['config']['regs'])" 2>&1 | tail -1; tail -2 gpurun_out/bench_c2_cluster$cs.err; done
+for f in c4_nacc4 c4_nacc1 c4_bf16; do echo "== bench $f"; python -c "
+import json;d=json.load(open('gpurun_out/bench_$f.json'));print('flushed',round(d['ms_per_step']*1e3,2),'b2b',round(d['config']['back_to_back_ms_per_step']*1e3,2),'grid',d['config']['grid'],'block',d['config']['block'],'regs',d['config']['regs'],'roofline',round(d['roofline']['frac'],4))" 2>&1 | tail -1; tail -2 gpurun_out/bench_$f.err; done
 for w in pendulum_c2 nav2d_c3 pendulum_c5; do echo "== bench $w"; python -c "
 import json;d=json.load(open('gpurun_out/bench_$w.json'));print('flushed',round(d['ms_per_step']*1e3,2),'b2b',round(d['config']['back_to_back_ms_per_step']*1e3,2),'e2e',round(d['e2e']['ms_per_step']*1e3,2),d['e2e']['api'][:30],'grid',d['config']['grid'])" 2>&1 | tail -1; tail -2 gpurun_out/bench_$w.err; done
 grep -c PASSED gpurun_out/ref_suite_report.txt; grep FAILED gpurun_out/ref_suite_report.txt
 for v in mppi smppi kmppi; do echo "== phase c3 $v"; tail -12 gpurun_out/phase_c3_$v.txt; done
-echo "== ubench"; cat gpurun_out/ubench_pipes.txt
+

@@ -182,7 +182,14 @@ def test_split_cost_rollout_is_bit_identical_to_the_single_loop(name, monkeypatc
         assert plain.launch_info.split_cost == 0
         assert split.launch_info.split_cost == (1 if split.launch_info.threads_per_sample > 1 else 0)
         assert split.launch_info.threads_per_sample == plain.launch_info.threads_per_sample
-        assert torch.equal(plain.cost_total, split.cost_total), name        # the rollout itself: bit for bit
+        # the rollout itself: same operations in the same order (fp32: bit for bit; fp64: the two kernels inline libdevice's
+        # double-precision sin / fmod in different surroundings, 1-ulp differences have been seen on B200)
+        if case["dtype"] == "f64":
+            rel = float(((plain.cost_total - split.cost_total).abs() / plain.cost_total.abs().clamp_min(1e-300)).max())
+            _record(f"{name}/split_vs_loop_cost_rel", rel)
+            assert rel <= 1e-13, (name, rel)
+        else:
+            assert torch.equal(plain.cost_total, split.cost_total), name
         # the softmin reduction is fp64 in a fixed order per launch geometry; the two kernels may get different cluster
         # sizes (different shared-memory footprints), i.e. a different — equally valid — summation order
         close = dict(rtol=0, atol=1e-12 if case["dtype"] == "f64" else 5e-7)
