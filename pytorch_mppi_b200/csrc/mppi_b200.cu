@@ -122,7 +122,7 @@ int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_p
     for (int cs = pl->g.cluster; cs >= 1; cs = (cs > 1 ? 1 : 0)) {
         const int nb = cs > 1 ? pl->g.nb : a.n_tiles;
         const int smem = make_layout<real>(pp.variant, pp.T, pp.nu, pp.S, a.R, pl->g.BD, pl->g.BS, 1,
-                                           layout_extra(pp.variant != MPPI_VARIANT_MPPI, pl->nx, cs, 0)).total;
+                                           layout_extra(pp.variant != MPPI_VARIANT_MPPI, pl->nx, cs, fused_xstage_doubles(false, 1, a.xchg_npub, a.R))).total;
         if (smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
         // cooperative: every CTA is resident or the launch fails — the CTAs wait for each other through the board
         cudaLaunchConfig_t cfg;

@@ -110,9 +110,10 @@ struct SmemLayout {
 };
 
 // `extra` word of make_layout: bit 0 = rows2 tile; bits 8..15 = nx of the split-cost state buffer; bits 16..19 = cluster
-// size of the warp-record area (0 = the kernel does not use the warp-fold tail); bits 20.. = doubles of exchange staging
+// size of the warp-record area (0 = the kernel does not use the warp-fold tail); bits 20..30 = record staging of the
+// finisher in units of 16 doubles (at most 8208 doubles: 8 ranks x 1026, or the 48 KB LL budget)
 __host__ __device__ inline int layout_extra(int rows2, int nx_split, int cluster, int xstage_doubles) {
-    return (rows2 & 1) | (nx_split << 8) | (cluster << 16) | (xstage_doubles << 20);
+    return (rows2 & 1) | (nx_split << 8) | (cluster << 16) | (((xstage_doubles + 15) / 16) << 20);
 }
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -124,7 +125,7 @@ __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a *
 template <typename real>
 __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, int S, int R, int BD, int BS, int nb, int extra) {
     SmemLayout L;
-    const int need_rows2 = extra & 1, nx_split = (extra >> 8) & 0xff, cluster = (extra >> 16) & 0xf, xstage = extra >> 20;
+    const int need_rows2 = extra & 1, nx_split = (extra >> 8) & 0xff, cluster = (extra >> 16) & 0xf, xstage = (extra >> 20) * 16;
     const int es = (int)sizeof(real);
     const int TN = T * nu, SN = S * nu, nw = BD / 32;
     int o = 16;  // [0,8): mbarrier

@@ -357,6 +357,17 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
             }
         }
         real roll = (real)0, pert = (real)0, smooth = (real)0, vprev = (real)0;
+        // debug_clocks (profiling aid, scripts/tc_phase_clocks.py): clock64() sums over the T steps of the first tile, per phase,
+        // for thread 0 (the MMA issuer) in slots 0..7 and thread 32 (a plain worker) in slots 8..15 of this CTA's row
+        const bool prof = a.dbg != nullptr && tile == blockIdx.x && (tid == 0 || tid == 32);
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
+#define TC_PROF(slot)                          \
+    if (prof) {                                \
+        const long long now_ = clock64();      \
+        pc[slot] += now_ - pt;                 \
+        pt = now_;                             \
+    }
+        if (prof) pt = clock64();
         for (int t = 0; t < T; ++t) {
             real v[NU] = {(real)0}, eps[NU] = {(real)0};
             real u = (real)0;
@@ -379,26 +390,34 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 tc::fence_async_smem();
                 tc::fence_before();
             }
+            TC_PROF(0)      // state/cost of the previous step + layer-1 operand row
             __syncthreads();
+            TC_PROF(1)      // barrier
             if (tid == 0) {
                 tc::fence_after();
                 tc::mma_f16(tmem + 0, dA1, dB1, I32, 0u);
                 tc::mma_commit(&s_mma_bar);
             }
+            TC_PROF(2)      // MMA issue (thread 0)
             float hv[16];
             {   // layer 1 -> tanh -> this thread's half of the layer-2 operand row
                 tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+                TC_PROF(3)  // commit -> mbarrier
                 tc::fence_after();
                 tc::tmem_ld16_nowait(my_lane + 16 * half, hv);
                 tc::tmem_wait_ld();
+                TC_PROF(4)  // TMEM load
 #pragma unroll
                 for (int i = 0; i < 16; ++i) hv[i] = Model::tanh_(hv[i], FAST);
                 tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);
+                TC_PROF(5)  // tanh + pack + store
                 tc::fence_async_smem();
                 tc::fence_before();
+                TC_PROF(6)  // proxy fence
             }
             mma_phase ^= 1u;
             __syncthreads();
+            TC_PROF(1)
             if (tid == 0) {
                 tc::fence_after();
 #pragma unroll
@@ -412,13 +431,16 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 }
                 tc::mma_commit(&s_mma_bar);
             }
+            TC_PROF(2)
             {   // layer 2 -> sum of the accumulators -> tanh -> half row of the layer-3 operand
                 tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+                TC_PROF(3)
                 tc::fence_after();
                 float acc[NA][16];
 #pragma unroll
                 for (int q = 0; q < NA; ++q) tc::tmem_ld16_nowait(my_lane + C2 + 32 * q + 16 * half, acc[q]);
                 tc::tmem_wait_ld();
+                TC_PROF(4)
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float sum = acc[0][i];
@@ -427,11 +449,14 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                     hv[i] = Model::tanh_(sum, FAST);
                 }
                 tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);     // MMA 2 has completed (barrier): its operand tile is free
+                TC_PROF(5)
                 tc::fence_async_smem();
                 tc::fence_before();
+                TC_PROF(6)
             }
             mma_phase ^= 1u;
             __syncthreads();
+            TC_PROF(1)
             if (tid == 0) {
                 tc::fence_after();
 #pragma unroll
@@ -445,7 +470,9 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 }
                 tc::mma_commit(&s_mma_bar);
             }
+            TC_PROF(2)
             tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+            TC_PROF(3)
             tc::fence_after();
             if (roller) {
                 float o0[NA], o1[NA];
@@ -459,6 +486,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 x[0] = O::sub(remainder<real>(O::add(th, mp.pi), mp.two_pi), mp.pi);    // pendulum_approximate.py:65
                 x[1] = O::add(x[1], s1);
             }
+            TC_PROF(4)
             // the next step's MMAs overwrite these accumulators: order the reads before the barrier that releases them
             tc::fence_before();
             mma_phase ^= 1u;
@@ -474,6 +502,12 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 }
             }
         }
+        if (prof) {
+            TC_PROF(7)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a.dbg[(size_t)blockIdx.x * 16 + (tid == 0 ? 0 : 8) + i] = (unsigned long long)pc[i];
+        }
+#undef TC_PROF
         real c_tot = O::inf();
         if (active) {
             c_tot = O::add(roll, pert);

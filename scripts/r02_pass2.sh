@@ -4,6 +4,8 @@
 set -u
 export PYTHONUNBUFFERED=1
 mkdir -p gpurun_out
+( timeout 300 /usr/local/cuda/bin/compute-sanitizer --tool memcheck --print-limit 5 python scripts/phase_clocks.py 8192 40 0 0 nav mppi ) > gpurun_out/memcheck_nav_mppi.txt 2>&1
+grep -E "ERROR SUMMARY|Invalid|at 0x|by thread|Address" gpurun_out/memcheck_nav_mppi.txt | head -12
 ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 600 ) > gpurun_out/pytest_gpu.txt 2>&1
 ( timeout 60 python scripts/phase_clocks.py 16384 30 ) > gpurun_out/phase_c2.txt 2>&1
 ( MPPI_B200_CLUSTER=1 timeout 60 python scripts/phase_clocks.py 16384 30 ) > gpurun_out/phase_c2_nocluster.txt 2>&1
