@@ -121,7 +121,7 @@ int resident_launch_t(Plan* pl, uint64_t seed, uint64_t offset_pred, int shift_p
     cudaError_t e = cudaErrorInvalidConfiguration;
     for (int cs = pl->g.cluster; cs >= 1; cs = (cs > 1 ? 1 : 0)) {
         const int nb = cs > 1 ? pl->g.nb : a.n_tiles;
-        const int smem = make_layout<real>(pp.variant, pp.T, pp.nu, pp.S, a.R, pl->g.BD, pl->g.BS, 1,
+        const int smem = make_layout<real>(pp.variant, pp.T, pp.nu, pp.S, a.R, pl->g.BD, pl->g.BS, fused_layout_nb(nb / cs, a.xchg_npub),
                                            layout_extra(pp.variant != MPPI_VARIANT_MPPI, pl->nx, cs, fused_xstage_doubles(false, 1, a.xchg_npub, a.R))).total;
         if (smem > dyn_limit) return UNSUPPORTED("resident kernel: shared-memory tile does not fit");
         // cooperative: every CTA is resident or the launch fails — the CTAs wait for each other through the board

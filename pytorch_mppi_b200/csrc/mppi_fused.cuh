@@ -105,7 +105,7 @@ template <typename real> struct KArgs {
 // ---- shared-memory carve, computed identically on host and device -------------------------------
 struct SmemLayout {
     int off_uraw, off_araw, off_thraw, off_us, off_as, off_ths, off_w, off_wsh, off_vrun, off_ws, off_red,
-        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, off_xs, off_wrec, off_xstage, total;
+        off_part, off_rows, off_rows2, off_ss, off_part2, off_numd, off_redd, off_xs, off_wrec, off_xstage, off_sqd, total;
     int LD;
 };
 
@@ -153,6 +153,14 @@ __host__ __device__ inline SmemLayout make_layout(int variant, int T, int nu, in
     // records, the cluster leader also receives its peers' through distributed shared memory
     L.off_wrec = o; o = align_up(o + cluster * (BS / 32) * (R + 2) * 8, 16);
     L.off_xstage = o; o = align_up(o + xstage * 8, 16);
+    // rescale factors of combine_records: one per record — the cluster's warp records, the staged records, or (ticket
+    // mode: the caller passes nb = number of cluster records of the grid) the records in the L2 workspace
+    {
+        int nsq = cluster * (BS / 32);
+        if (xstage / (R + 2) > nsq) nsq = xstage / (R + 2);
+        if (nb > nsq) nsq = nb;
+        L.off_sqd = o; o = align_up(o + (cluster > 0 ? nsq : 0) * 8, 16);
+    }
     L.total = o;
     return L;
 }
@@ -239,7 +247,7 @@ template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
 template <typename real> struct Smem {
     unsigned long long* bar;
     real *Uraw, *Araw, *thraw, *Us, *As, *ths, *Ws, *Wsh, *Vrun, *w_s, *red, *part, *rows, *rows2, *sS, *xs;
-    double *part2, *numd, *redd, *wrec, *xstage;
+    double *part2, *numd, *redd, *wrec, *xstage, *sqd;
     int LD;
     __device__ Smem(unsigned char* smem, const SmemLayout& L) {
         bar = reinterpret_cast<unsigned long long*>(smem);
@@ -264,6 +272,7 @@ template <typename real> struct Smem {
         xs = reinterpret_cast<real*>(smem + L.off_xs);
         wrec = reinterpret_cast<double*>(smem + L.off_wrec);
         xstage = reinterpret_cast<double*>(smem + L.off_xstage);
+        sqd = reinterpret_cast<double*>(smem + L.off_sqd);
         LD = L.LD;
     }
 };
@@ -335,32 +344,56 @@ __device__ void stage_nominal(const KArgs<real>& a, Smem<real>& sm) {
 // ---- stage A: standard normals into the tile ------------------------------------------------------
 // (thread -> sample s = tid % BS, chunk lane g = tid / BS: the tps threads of a sample split its
 // Philox chunks)
+// the rarely-taken sources of normals, out of line so that they do not sit in the hot path's instruction stream:
+// injected z (parity tests), the torch-compatible stream (one Philox call per element), recording of the draws (z_out)
 template <typename real>
-__device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, bool active, unsigned long long kg, int nvalid) {
-    const int tid = threadIdx.x, BD = blockDim.x, R = a.R, LD = sm.LD;
+__device__ __noinline__ void fill_normals_rare(const KArgs<real>& a, real* rows, int LD, int tile, bool active, unsigned long long kg, int nvalid) {
+    const int tid = threadIdx.x, BD = blockDim.x, R = a.R;
     const int BS = BD / a.tps, s_ = tid % BS, g_ = tid / BS;
     if (a.z != nullptr) {
         const size_t base = (size_t)tile * BS * R;
         const int count = nvalid * R;
         for (int e = tid; e < count; e += BD) {
             const int s = e / R, j = e - s * R;
-            sm.rows[j * LD + s] = a.z[base + e];
+            rows[j * LD + s] = a.z[base + e];
         }
         __syncthreads();
+    } else if (a.torch_total > 0 && active) {
+        // torch-compatible stream: one Philox call per element (the ATen kernel scatters each call's
+        // outputs `total` elements apart), 4x the generator work of the native stream
+        constexpr int UN = TorchNormal<real>::UNROLL;
+        real* col = rows + s_;
+        const unsigned long long off = a.offset_dev != nullptr ? __ldcg(a.offset_dev) : a.offset;
+        for (int j = g_; j < R; j += a.tps) {
+            const unsigned long long li = kg * (unsigned long long)R + (unsigned long long)j;
+            const unsigned long long idx = li % a.torch_total, m = li / a.torch_total;
+            col[j * LD] = TorchNormal<real>::one(a.seed, idx, off + m / UN, (int)(m % UN));
+        }
+    }
+}
+template <typename real>
+__device__ __noinline__ void record_normals(const KArgs<real>& a, const real* rows, int LD, int tile, int nvalid) {
+    const int tid = threadIdx.x, BD = blockDim.x, R = a.R, BS = BD / a.tps;
+    __syncthreads();
+    const size_t base = (size_t)tile * BS * R;
+    const int count = nvalid * R;
+    for (int e = tid; e < count; e += BD) {
+        const int s = e / R, j = e - s * R;
+        a.z_out[base + e] = rows[j * LD + s];
+    }
+    __syncthreads();
+}
+
+template <typename real>
+__device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, bool active, unsigned long long kg, int nvalid) {
+    const int tid = threadIdx.x, BD = blockDim.x, R = a.R, LD = sm.LD;
+    const int BS = BD / a.tps, s_ = tid % BS, g_ = tid / BS;
+    if (a.z != nullptr || a.torch_total > 0) {
+        fill_normals_rare<real>(a, sm.rows, LD, tile, active, kg, nvalid);
     } else if (active) {
         constexpr int PER = Normals<real>::PER_CALL;
         real* col = sm.rows + s_;
         const unsigned long long off = a.offset_dev != nullptr ? __ldcg(a.offset_dev) : a.offset;
-        if (a.torch_total > 0) {
-            // torch-compatible stream: one Philox call per element (the ATen kernel scatters each call's
-            // outputs `total` elements apart), 4x the generator work of the native stream
-            constexpr int UN = TorchNormal<real>::UNROLL;
-            for (int j = g_; j < R; j += a.tps) {
-                const unsigned long long li = kg * (unsigned long long)R + (unsigned long long)j;
-                const unsigned long long idx = li % a.torch_total, m = li / a.torch_total;
-                col[j * LD] = TorchNormal<real>::one(a.seed, idx, off + m / UN, (int)(m % UN));
-            }
-        } else
         for (int c = g_; c * PER < R; c += a.tps) {
             real tmp[PER];
             Normals<real>::draw(a.seed, kg, off + (unsigned long long)c, tmp);
@@ -369,16 +402,7 @@ __device__ void fill_normals(const KArgs<real>& a, Smem<real>& sm, int tile, boo
                 if (c * PER + q < R) col[(c * PER + q) * LD] = tmp[q];
         }
     }
-    if (a.z_out != nullptr) {
-        __syncthreads();
-        const size_t base = (size_t)tile * BS * R;
-        const int count = nvalid * R;
-        for (int e = tid; e < count; e += BD) {
-            const int s = e / R, j = e - s * R;
-            a.z_out[base + e] = sm.rows[j * LD + s];
-        }
-        __syncthreads();
-    }
+    if (a.z_out != nullptr) record_normals<real>(a, sm.rows, LD, tile, nvalid);
 }
 
 // value that overrides the sampled action before the clamp: null action (mppi.py:390-392) or a
@@ -924,6 +948,10 @@ __host__ __device__ inline int fused_xstage_doubles(bool sharded, int world, int
     return (npub > 1 || sharded) ? xw * npub * (R + 2) : 0;
 }
 
+// the `nb` argument of make_layout for the warp-fold tail: the records combine_records reads from the L2 workspace
+// (ticket mode: the grid's NC cluster records), 1 when they arrive as flagged words (LL mode) or there is one cluster
+__host__ __device__ inline int fused_layout_nb(int NC, int npub) { return (NC > 1 && npub != NC) ? NC : 1; }
+
 // this CTA's running warp records: (beta = +inf, eta = 0, V = 0); call before the first barrier of the kernel
 template <typename real>
 __device__ __forceinline__ void warp_records_init(const KArgs<real>& a, Smem<real>& sm) {
@@ -971,81 +999,41 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
 }
 
 // ---- fixed-order fp64 combination of records (beta_q, eta_q, V_q[R]) -----------------------------------------------
-//   beta = min beta_q ; s_q = exp(nfl (beta_q - beta)) ; eta = sum s_q eta_q ; V[j] = sum s_q V_q[j]   -> sm.numd[0 .. R+2)
-// CTA-wide (every thread calls it; two barriers).  ld(q, i) returns element i of record q.  Warp w takes the records
-// q = w, w + nw, ... (PF of them in flight: one shared-memory / L2 round trip per batch), accumulates s_q V_q[j] for all
-// rows in its own slice of sm.part2, and the slices are added in warp order — the result does not depend on timing.
-template <typename real, class Load>
-__device__ void combine_records(Load ld, int nrec, Smem<real>& sm, int R, double nfl) {
+//   beta = min beta_q ; s_q = exp(nfl (beta_q - beta)) ; eta = sum s_q eta_q ; V[j] = sum s_q V_q[j]   -> numd[0 .. R+2)
+// CTA-wide (every thread calls it; three barriers).  Record q is recs[q * (R+2) ..] in shared or global memory (generic
+// pointer, volatile loads: L2 for global).  Threads are (group g = tid / 64, column jl = tid % 64): group g adds the
+// records q = g, g + nG, ... for its columns (column 0 = eta, column 1 + j = V[j]) into part2[g][..], the groups are added
+// in order — the result does not depend on timing.  Deliberately SMALL and out of line (one copy for every call site):
+// the tail runs once per command on a cold instruction cache, where instruction count, not arithmetic, sets its time
+// (ncu: `no_instruction` is the third-largest stall of the kernel).
+template <typename real>
+__device__ __noinline__ void combine_records(const volatile double* recs, int nrec, int R, double nfl, double* part2, double* sq,
+                                             double* numd) {
     typedef Ops<real> O;
-    constexpr int PF = 8;
-    const int tid = threadIdx.x, BD = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = BD >> 5;
-    // every load that does not depend on beta is issued BEFORE beta is reduced: the lane-parallel beta loads and the
-    // first batch of this warp's records (beta_q, eta_q, row block 0) — one memory round trip for the common case
-    constexpr int NB = 4;                                  // beta loads per lane issued up front (covers 128 records)
-    double bl[NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) bl[i] = (lane + 32 * i < nrec) ? ld(lane + 32 * i, 0) : (double)INFINITY;
-    double bq[PF], eq[PF], v0[PF];
-    const int jc0 = lane < R ? lane : 0;
-#pragma unroll
-    for (int u = 0; u < PF; ++u) {
-        const int q = warp + u * nw;
-        const bool ok = q < nrec;
-        bq[u] = ok ? ld(q, 0) : (double)INFINITY;
-        eq[u] = ok ? ld(q, 1) : 0.0;
-        v0[u] = ok ? ld(q, 2 + jc0) : 0.0;
+    const int RW = R + 2, C = R + 1;                      // columns: eta, V[0..R)
+    const int tid = threadIdx.x, BD = blockDim.x, nG = BD >> 6, g = tid >> 6, jl = tid & 63;
+    if (tid < 32) {
+        double b = (double)INFINITY;
+        for (int q = tid; q < nrec; q += 32) b = fmin(b, recs[(size_t)q * RW]);
+        b = warp_min<double>(b);
+        if (tid == 0) numd[0] = b;
     }
-    double b = bl[0];
-#pragma unroll
-    for (int i = 1; i < NB; ++i) b = fmin(b, bl[i]);
-    for (int q = lane + 32 * NB; q < nrec; q += 32) b = fmin(b, ld(q, 0));
-    const double beta = warp_min<double>(b);             // every warp computes it (no barrier)
-    double* mine = sm.part2 + (size_t)warp * R;
-    for (int j = lane; j < R; j += 32) mine[j] = 0.0;
-    double eta_p = 0.0;
-    for (int q0 = warp; q0 < nrec; q0 += PF * nw) {
-        const bool first = q0 == warp;
-        double s[PF];
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int q = q0 + u * nw;
-            const bool ok = q < nrec;
-            const double bqu = first ? bq[u] : (ok ? ld(q, 0) : (double)INFINITY);
-            const double equ = first ? eq[u] : (ok ? ld(q, 1) : 0.0);
-            // the rescale factor in the controller's precision (exact for equal betas; beta_q - beta is exact in fp64)
-            s[u] = ok ? (double)O::exp_((real)(nfl * (bqu - beta))) : 0.0;
-            eta_p += s[u] * equ;
-        }
-        for (int jb = 0; jb < R; jb += 32) {
-            const int j = jb + lane;
-            const int jc = j < R ? j : 0;
-            double acc = 0.0;
-            if (first && jb == 0) {
-#pragma unroll
-                for (int u = 0; u < PF; ++u) acc += s[u] * v0[u];
-            } else {
-                double v[PF];
-#pragma unroll
-                for (int u = 0; u < PF; ++u) v[u] = (q0 + u * nw < nrec) ? ld(q0 + u * nw, 2 + jc) : 0.0;
-#pragma unroll
-                for (int u = 0; u < PF; ++u) acc += s[u] * v[u];
-            }
-            if (j < R) mine[j] += acc;
-        }
-    }
-    if (lane == 0) sm.redd[warp] = eta_p;
     __syncthreads();
-    for (int j = tid; j < R; j += BD) {
-        double t = sm.part2[j];
-        for (int w = 1; w < nw; ++w) t += sm.part2[(size_t)w * R + j];
-        sm.numd[2 + j] = t;
+    const double beta = numd[0];
+    // the rescale factors in the controller's precision (exact for equal betas; beta_q - beta is exact in fp64)
+    for (int q = tid; q < nrec; q += BD) sq[q] = (double)O::exp_((real)(nfl * (recs[(size_t)q * RW] - beta)));
+    __syncthreads();
+    for (int j = jl; j < C; j += 64) {
+        double acc = 0.0;
+#pragma unroll 4
+        for (int q = g; q < nrec; q += nG) acc += sq[q] * recs[(size_t)q * RW + 1 + j];
+        part2[(size_t)g * C + j] = acc;
     }
-    if (tid == 0) {
-        double e = sm.redd[0];
-        for (int w = 1; w < nw; ++w) e += sm.redd[w];
-        sm.numd[0] = beta;
-        sm.numd[1] = e;
+    __syncthreads();
+    for (int j = tid; j < C; j += BD) {
+        double t = part2[j];
+        for (int w = 1; w < nG; ++w) t += part2[(size_t)w * C + j];
+        numd[1 + j] = t;
     }
     __syncthreads();
 }
@@ -1054,27 +1042,29 @@ __device__ void combine_records(Load ld, int nrec, Smem<real>& sm, int R, double
 // a.peers[g], g < xw, are the mailboxes the record goes to: every rank's (sharded controller, over NVLink) or just this
 // GPU's own (single GPU: a region of the workspace) — self-validating words need no fence and no ticket, the finisher
 // sees a record one store-to-poll latency after it was written.
-template <typename real>
-__device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int xw, int rec_index, const double* src) {
-    const int nwords = 2 * (a.R + 2);
-    const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
-    const size_t off = (size_t)(a.epoch & 1ull) * a.xchg_parity_words + (size_t)rec_index * nwords;
+static __device__ __noinline__ void xchg_publish_words(unsigned long long* const* peers, int xw, unsigned long long epoch, unsigned int parity_words,
+                                                int rec_index, int R, const double* src) {
+    const int nwords = 2 * (R + 2);
+    const uint32_t flag = (uint32_t)(epoch & 0x7fffffffull) | 0x80000000u;
+    const size_t off = (size_t)(epoch & 1ull) * parity_words + (size_t)rec_index * nwords;
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(src[i >> 1]);
         const uint32_t half = (i & 1) ? (uint32_t)(bits >> 32) : (uint32_t)bits;
         const unsigned long long word = ((unsigned long long)flag << 32) | half;
-        for (int g = 0; g < xw; ++g) st_peer(a.peers[g] + off + i, word);
+        for (int g = 0; g < xw; ++g) st_peer(peers[g] + off + i, word);
     }
+}
+template <typename real>
+__device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int xw, int rec_index, const double* src) {
+    xchg_publish_words(a.peers, xw, a.epoch, a.xchg_parity_words, rec_index, a.R, src);
 }
 // all threads of the CTA; nrec records from this rank's own mailbox into sm.xstage (doubles), PB polls in flight per
 // thread.  Returns 0, or 1 on timeout.
-template <typename real>
-__device__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int own, int nrec) {
+static __device__ __noinline__ int xchg_collect_words(const unsigned long long* mine, unsigned long long epoch, unsigned long long timeout_ns,
+                                               int nwords, uint32_t* dst) {
     constexpr int PB = 8;
-    const int nwords = nrec * 2 * (a.R + 2), BD = blockDim.x;
-    const uint32_t flag = (uint32_t)(a.epoch & 0x7fffffffull) | 0x80000000u;
-    const unsigned long long* mine = a.peers[own] + (size_t)(a.epoch & 1ull) * a.xchg_parity_words;
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.xstage);
+    const int BD = blockDim.x;
+    const uint32_t flag = (uint32_t)(epoch & 0x7fffffffull) | 0x80000000u;
     __shared__ int s_timeout;
     if (threadIdx.x == 0) s_timeout = 0;
     __syncthreads();
@@ -1100,7 +1090,7 @@ __device__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int own, int n
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
                 if (t0 == 0) t0 = now;
-                if (now - t0 > a.xchg_timeout_ns || s_timeout) {
+                if (now - t0 > timeout_ns || s_timeout) {
                     s_timeout = 1;
                     break;
                 }
@@ -1109,6 +1099,11 @@ __device__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int own, int n
     }
     __syncthreads();
     return s_timeout;
+}
+template <typename real>
+__device__ __forceinline__ int xchg_collect(const KArgs<real>& a, Smem<real>& sm, int own, int nrec) {
+    return xchg_collect_words(a.peers[own] + (size_t)(a.epoch & 1ull) * a.xchg_parity_words, a.epoch, a.xchg_timeout_ns,
+                              nrec * 2 * (a.R + 2), reinterpret_cast<uint32_t*>(sm.xstage));
 }
 
 // a peer never delivered: report it (device stats, pinned host word) and return a DEFINED action — the nominal the
@@ -1171,8 +1166,7 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
 
     // (2) leader: cs x nrw warp records -> one cluster record in sm.numd
     {
-        const double* recs = sm.wrec;
-        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, cs * nrw, sm, R, nfl);
+        combine_records<real>(sm.wrec, cs * nrw, R, nfl, sm.part2, sm.sqd, sm.numd);
     }
     // (3) publish the cluster record
     if (ll) {
@@ -1198,11 +1192,9 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
             xchg_timed_out<real, VARIANT>(a, sm, NU);
             return true;
         }
-        const double* recs = sm.xstage;
-        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, xw * NC, sm, R, nfl);
+        combine_records<real>(sm.xstage, xw * NC, R, nfl, sm.part2, sm.sqd, sm.numd);
     } else if (NC > 1) {
-        const double* recs = a.crec;
-        combine_records<real>([&](int q, int i) { return __ldcg(recs + (size_t)q * RW + i); }, NC, sm, R, nfl);
+        combine_records<real>(a.crec, NC, R, nfl, sm.part2, sm.sqd, sm.numd);      // volatile loads: L2
     }
     stamp(a.dbg, 10);
     if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
@@ -1228,8 +1220,7 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
             xchg_timed_out<real, VARIANT>(a, sm, NU);
             return true;
         }
-        const double* recs = sm.xstage;
-        combine_records<real>([&](int q, int i) { return recs[(size_t)q * RW + i]; }, xw, sm, R, nfl);
+        combine_records<real>(sm.xstage, xw, R, nfl, sm.part2, sm.sqd, sm.numd);
     }
     stamp(a.dbg, 11);
     finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);
@@ -1377,8 +1368,9 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
     const KArgs<real>& a = BATCHED ? *reinterpret_cast<const KArgs<real>*>(a_env_raw) : a_in;
     const int BS = BD / a.tps;
     const int xst = fused_xstage_doubles(a.world > 1 && !a.export_partial, a.world, a.xchg_npub, a.R);
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1,
-                                           layout_extra(VARIANT != V_MPPI, SPLIT ? NX : 0, (int)cluster_nctarank(), xst));
+    const int cs_ = (int)cluster_nctarank(), NC_ = (int)gridDim.x / cs_;
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, fused_layout_nb(NC_, a.xchg_npub),
+                                           layout_extra(VARIANT != V_MPPI, SPLIT ? NX : 0, cs_, xst));
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;

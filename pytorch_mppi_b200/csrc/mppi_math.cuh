@@ -29,6 +29,12 @@ namespace mppi {
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct Ops;
 
+#if defined(__CUDACC__)
+// the library's long-division fmodf, for the cases fmod_ below does not handle itself (huge quotients, b <= 0,
+// non-finite inputs): out of line, so that its loop is not inlined into every use on the rollout's hot path
+static __device__ __noinline__ float fmodf_out_of_line(float a, float b) { return fmodf(a, b); }
+#endif
+
 template <> struct Ops<float> {
     typedef float real;
     static MPPI_HD float add(float a, float b) {
@@ -70,7 +76,7 @@ template <> struct Ops<float> {
 #if defined(__CUDA_ARCH__)
         const float fa = fabsf(a);
         const float qf = fa * __frcp_rn(b);
-        if (!(b > 0.0f) || !(qf < 2097152.0f)) return fmodf(a, b);
+        if (!(b > 0.0f) || !(qf < 2097152.0f)) return fmodf_out_of_line(a, b);
         float q = truncf(qf);
         float r = __fmaf_rn(-q, b, fa);
         if (r < 0.0f) {

@@ -112,7 +112,7 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
     CK(cudaFuncGetAttributes(&fa, (const void*)kernel));
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
     const int envs = batched ? p->n_env : 1;
-    g.cluster = 1;
+    g.cluster = 0;
     g.npub = 1;
     for (int cs = 8; cs >= 1; cs >>= 1) {
         if (cs > want && cs > 1) continue;
@@ -127,7 +127,8 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
         if (const char* e = getenv("MPPI_B200_XCHG_DIRECT"))
             if (atoi(e) == 0) npub = 1;
         const int xst = fused_xstage_doubles(sharded, world, npub, R);
-        const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, 1, layout_extra(tile2, split ? Model::NX : 0, cs, xst));
+        const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, fused_layout_nb(NC, npub),
+                                               layout_extra(tile2, split ? Model::NX : 0, cs, xst));
         if (L.total > dyn_limit) continue;
         if (cs > 1) {
             cudaLaunchConfig_t cfg;
@@ -146,6 +147,7 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
         g.npub = npub;
         break;
     }
+    if (g.cluster == 0) return UNSUPPORTED("shared-memory tile does not fit");
     c = FusedChoice{(const void*)kernel, g, split, 0, 0};
     return MPPI_OK;
 }

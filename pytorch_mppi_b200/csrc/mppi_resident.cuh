@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
         __syncthreads();
     }
     const int BS = BD / a.tps;
-    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, 1,
-                                           layout_extra(VARIANT != V_MPPI, NX, (int)cluster_nctarank(), fused_xstage_doubles(false, 1, a.xchg_npub, a.R)));
+    const int cs_ = (int)cluster_nctarank();
+    const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, fused_layout_nb((int)gridDim.x / cs_, a.xchg_npub),
+                                           layout_extra(VARIANT != V_MPPI, NX, cs_, fused_xstage_doubles(false, 1, a.xchg_npub, a.R)));
     Smem<real> sm(smem, L);
 
     // one tile per CTA

@@ -4,8 +4,8 @@
 set -u
 export PYTHONUNBUFFERED=1
 mkdir -p gpurun_out
-( timeout 300 /usr/local/cuda/bin/compute-sanitizer --tool memcheck --print-limit 5 python scripts/phase_clocks.py 8192 40 0 0 nav mppi ) > gpurun_out/memcheck_nav_mppi.txt 2>&1
-grep -E "ERROR SUMMARY|Invalid|at 0x|by thread|Address" gpurun_out/memcheck_nav_mppi.txt | head -12
+( timeout 120 python scripts/tc_phase_clocks.py 32768 30 bf16x3 ) > gpurun_out/tc_phase_clocks.txt 2>&1
+( MPPI_TC_NACC=1 timeout 120 python scripts/tc_phase_clocks.py 32768 30 bf16x3 ) >> gpurun_out/tc_phase_clocks.txt 2>&1
 ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 600 ) > gpurun_out/pytest_gpu.txt 2>&1
 ( timeout 60 python scripts/phase_clocks.py 16384 30 ) > gpurun_out/phase_c2.txt 2>&1
 ( MPPI_B200_CLUSTER=1 timeout 60 python scripts/phase_clocks.py 16384 30 ) > gpurun_out/phase_c2_nocluster.txt 2>&1
@@ -29,6 +29,7 @@ for f in c4_nacc4 c4_nacc1 c4_bf16; do echo "== bench $f"; python -c "
 import json;d=json.load(open('gpurun_out/bench_$f.json'));print('flushed',round(d['ms_per_step']*1e3,2),'b2b',round(d['config']['back_to_back_ms_per_step']*1e3,2),'grid',d['config']['grid'],'block',d['config']['block'],'regs',d['config']['regs'],'roofline',round(d['roofline']['frac'],4))" 2>&1 | tail -1; tail -2 gpurun_out/bench_$f.err; done
 for w in pendulum_c2 nav2d_c3 pendulum_c5; do echo "== bench $w"; python -c "
 import json;d=json.load(open('gpurun_out/bench_$w.json'));print('flushed',round(d['ms_per_step']*1e3,2),'b2b',round(d['config']['back_to_back_ms_per_step']*1e3,2),'e2e',round(d['e2e']['ms_per_step']*1e3,2),d['e2e']['api'][:30],'grid',d['config']['grid'])" 2>&1 | tail -1; tail -2 gpurun_out/bench_$w.err; done
+echo "== tc phases"; cat gpurun_out/tc_phase_clocks.txt
 grep -c PASSED gpurun_out/ref_suite_report.txt; grep FAILED gpurun_out/ref_suite_report.txt
 for v in mppi smppi kmppi; do echo "== phase c3 $v"; tail -12 gpurun_out/phase_c3_$v.txt; done
 

@@ -618,8 +618,8 @@ def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
         x = cpu_model.dynamics(x.view(1, -1), r["action"].view(1, -1)).view(-1)
 
 
-@pytest.mark.parametrize("variant,tile", [("mppi", 64), ("mppi", 128), ("smppi", 64), ("smppi", 128), ("kmppi", 64), ("kmppi", 128)])
-def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, tile, monkeypatch):
+@pytest.mark.parametrize("variant,nacc", [("mppi", 4), ("mppi", 1), ("smppi", 4), ("smppi", 1), ("kmppi", 4), ("kmppi", 1)])
+def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, nacc, monkeypatch):
     """PendulumMLP(tensor_cores=True): the three layers run as tcgen05 MMAs (hi/lo-split bf16 operands,
     fp32 TMEM accumulators).  Same injected noise as the FFMA kernel: costs agree to ~1e-4 relative and
     the updated plan to 2e-4 (operand split error ~2^-16 per layer, 30 steps of a chaotic rollout), for a
@@ -627,7 +627,7 @@ def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, tile, monkeypa
     import copy
     import pytorch_mppi_b200 as eng
     from oracle import mppi_oracle as orc
-    monkeypatch.setenv("MPPI_TC_TILE", str(tile))      # both tile shapes: 128 samples/CTA, or 64 + 64 helper threads
+    monkeypatch.setenv("MPPI_TC_NACC", str(nacc))      # independent TMEM accumulators per layer (4), or one chain (1)
     torch.manual_seed(25)
     net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
                               torch.nn.Linear(32, 2))
@@ -661,7 +661,7 @@ def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, tile, monkeypa
         u2 = a_tc.command(x)
         c1, c2 = a_ref.cost_total.cpu().numpy(), a_tc.cost_total.cpu().numpy()
         assert np.isfinite(c2).all()
-        assert a_tc.launch_info.block_threads == 128 and a_tc.launch_info.threads_per_sample == 128 // tile
+        assert a_tc.launch_info.block_threads == 256 and a_tc.launch_info.threads_per_sample == 2     # two threads per sample
         assert a_ref.launch_info.block_threads != 128
         np.testing.assert_allclose(c2, c1, rtol=2e-3, atol=2e-3)
         assert float(np.median(np.abs(c2 - c1) / np.maximum(1.0, np.abs(c1)))) < 2e-5
