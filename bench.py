@@ -324,10 +324,14 @@ def run_engine(args, wl):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     pg = None
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own log (NCCL_DEBUG, if the caller set it) goes to stderr: stdout carries the one JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's own output (its version banner, NCCL_DEBUG logs if the caller asked for them) goes to stderr: stdout is
+        # pointed at stderr until the JSON line is printed, so it carries that one line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
 
@@ -511,7 +515,8 @@ def run_engine(args, wl):
                        "parallelism": f"K sharded over {world} GPU(s), exchange={args.exchange if world > 1 else 'none'}",
                        "ranks_hold_identical_U": ranks_agree, "sharded_equals_unsharded": shard_check,
                        "grid": info.grid_blocks, "block": info.block_threads, "threads_per_sample": info.threads_per_sample,
-                       "smem_bytes": info.smem_bytes, "regs": info.regs_per_thread, "split_cost": info.split_cost},
+                       "smem_bytes": info.smem_bytes, "regs": info.regs_per_thread, "split_cost": info.split_cost,
+                       "cluster": info.cluster_size, "reduction_records": info.xchg_records},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": NX * 8, "d2h_bytes_per_step": NU * 4 + 8,
                     "ms_per_step": e2e_s / n_e2e * 1e3, "steps": n_e2e, "api": "MPPI.command_host(state)  [one launch per step]",
@@ -542,6 +547,9 @@ def run_engine(args, wl):
                     break
             line["cpu_baseline"] = {"value": K_gpu * T * n / el, "unit": "rollout-steps/s", "cores": cores, "kind": arm.kind,
                                     "sample": cpu_sample_text(arm, n, el, cores), "ms_per_step": el / n * 1e3}
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -20,7 +20,9 @@
 // (SMPPI :489-493, 520-570; KMPPI :617-619, 657-688).
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include "mppi_math.cuh"
 
 #ifndef MPPI_ROLLOUT_PIPELINED
@@ -1025,7 +1027,7 @@ __device__ __noinline__ void combine_records(const volatile double* recs, int nr
     __syncthreads();
     for (int j = jl; j < C; j += 64) {
         double acc = 0.0;
-#pragma unroll 4
+#pragma unroll 8
         for (int q = g; q < nrec; q += nG) acc += sq[q] * recs[(size_t)q * RW + 1 + j];
         part2[(size_t)g * C + j] = acc;
     }

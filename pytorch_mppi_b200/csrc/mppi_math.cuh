@@ -13,8 +13,21 @@
 // runs this code on the CPU.
 #pragma once
 
+#if defined(__CUDACC_RTC__)
+// run-time compilation of a user model (NVRTC has no host headers): the few names these headers take from <stdint.h>
+// / <math.h>; the math functions themselves are NVRTC built-ins
+typedef unsigned char uint8_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#ifndef INFINITY
+#define INFINITY __int_as_float(0x7f800000)
+#endif
+#else
 #include <math.h>
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define MPPI_HD __host__ __device__ __forceinline__

@@ -13,9 +13,14 @@
 // tensor pipe itself 7 % busy), so the kernel shortens the chain instead of widening the MMAs:
 //   * TWO threads per sample (256-thread CTAs): warps w and w+4 own the same 32 TMEM lanes and split the 32 hidden
 //     units — 16 tanh + 16 packs each instead of 32 (`tcgen05.ld.32x32b.x16` on their half of the columns);
-//   * NACC = 4: the 7 K-steps of a hi/lo-split layer accumulate into FOUR independent TMEM accumulators (chains of at
-//     most two dependent MMAs instead of seven), summed in registers after the load;
+//   * layer 1 (3 inputs -> 32 units, 96 FMAs per sample) runs on the FP32 pipe, in exact fp32, straight from the state in
+//     shared memory: TWO MMA round trips per step instead of three (measured per step and layer: 416 clocks to issue the
+//     K-steps + commit, 170-400 to the mbarrier, 150 for the TMEM load — profiles/r02_tc_phase_clocks_v2.txt);
+//   * the running cost of the state a step produced is evaluated one step LATER, in the shadow of the layer-2 MMA
+//     (same values, same summation order);
 //   * tanh = FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA (mppi_math.cuh).
+// Tried and dropped: four independent TMEM accumulators per layer (chains of two dependent MMAs instead of seven) —
+// 5 % slower: the MMA chain is not what the round trip waits for.
 //
 // Precision: operands are bf16.  In the default (SPLIT) mode activations and weights are split into hi + lo
 // bf16 parts and each layer is issued as  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  ("3 x bf16": the a_hi chunks are
@@ -38,12 +43,7 @@ namespace tc {
 constexpr int H = 32;             // hidden width
 constexpr int KX3 = 64;           // SPLIT: activations of layers 2 and 3 are stored as [a_hi(32) | a_lo(32)]
 constexpr int CH = 128;           // bytes of one 8-row x 16-byte core matrix
-// TMEM columns per CTA.  NACC = 1: D1 [0,32), D2 [32,64), D3 [0,16) (D1 is dead by then) = 64.
-// NACC = 4 (hi/lo split: 4 accumulators, plain bf16: 2): D1 [0,32), D2 [32, 32+32a), D3 after it, 16 columns each.
-__host__ __device__ constexpr int n_acc(int split, int nacc) { return nacc <= 1 ? 1 : (split ? 4 : 2); }
-__host__ __device__ constexpr int tmem_cols(int split, int nacc) {
-    return nacc <= 1 ? 64 : (split ? 256 : 128);
-}
+constexpr int TMEM_COLS = 64;     // D2: columns [0,32), D3: [32,48)
 
 // shared-memory operand tiles (bytes); canonical K-major/no-swizzle: core (row group g, k-chunk c) at
 // g*SBO + c*LBO, rows 16 B apart inside a core, LBO = 128 B (adjacent chunks), SBO = chunks*128 B
@@ -196,33 +196,26 @@ template <int SPLIT, int CHUNKS> __device__ __forceinline__ void write_a_half(un
 }  // namespace tc
 
 // =================================================================================================
-template <int VARIANT, int SPLIT, int FAST, int NACC>
+template <int VARIANT, int SPLIT, int FAST>
 __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_constant__ KArgs<float> a,
                                                              const __grid_constant__ PendulumMLPModel::P<float> mp) {
     typedef float real;
     typedef Ops<real> O;
     typedef PendulumMLPModel Model;
     constexpr int NX = 2, NU = 1, H = tc::H;
-    // K of layers 2 and 3: the activations (split or not) plus one 16-wide K-step whose first two columns are
-    // the constant 1: the matching rows of B hold bias_hi and bias_lo, so the MMA adds the bias for free
+    // K of layers 2 and 3: the activations (split or not) plus one 16-wide K-step whose columns 9 and 10 are the
+    // constant 1: the matching rows of B hold bias_hi and bias_lo, so the MMA adds the bias for free
     constexpr int KB = SPLIT ? tc::KX3 : H;
     constexpr int KX = KB + 16;
     constexpr int CHUNKS = KX / 8, NSTEP = KX / 16;
-    // accumulators: NA independent TMEM column blocks per layer; K-step s of the main tile goes to block s / 2, the two
-    // K-steps of the w_lo tile (SPLIT) to blocks (NSTEP + s) / 2 — chains of at most two dependent MMAs
-    constexpr int NA = tc::n_acc(SPLIT, NACC);
-    constexpr int TMEM_COLS = tc::tmem_cols(SPLIT, NACC);
-    constexpr int C2 = 32, C3 = NACC <= 1 ? 0 : 32 + 32 * NA;       // NACC = 1: D3 reuses D1's columns (dead by then)
+    constexpr int TMEM_COLS = tc::TMEM_COLS, C2 = 0, C3 = 32;
     extern __shared__ __align__(16) unsigned char smem[];
-    // one operand tile for all three layers: columns [0,KB) hold the hidden activations (layer 2's, then layer
-    // 3's); the last K-step [KB,KB+16) holds layer 1's row [x0h x0h x0l x1h x1h x1l uh uh | ul 1 1 0...], whose
-    // two constant ones double as the bias columns of layers 2 and 3 (their B tiles are zero under the stale inputs)
-    __shared__ __align__(128) unsigned char sA2[128 * KX * 2];
-    __shared__ __align__(128) unsigned char sB1[tc::B1_BYTES];
+    __shared__ __align__(128) unsigned char sA2[128 * KX * 2];                 // operand tile of layers 2 and 3
     __shared__ __align__(128) unsigned char sB2[32 * KX * 2];
     __shared__ __align__(128) unsigned char sB3[16 * KX * 2];
     __shared__ __align__(128) unsigned char sB2lo[SPLIT ? 32 * H * 2 : 128];    // w_lo tiles (K = 32), SPLIT only
     __shared__ __align__(128) unsigned char sB3lo[SPLIT ? 16 * H * 2 : 128];
+    __shared__ __align__(16) float sX[128 * 4];                                 // (x0, x1, clamped u) of every sample: layer 1's input
     __shared__ __align__(8) unsigned long long s_mma_bar;
     __shared__ uint32_t s_tmem_base;
     const int tid = threadIdx.x, BD = blockDim.x;      // BD == 256: thread = (sample row tid % 128, half tid / 128)
@@ -246,19 +239,19 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     }
     for (int i = tid; i < 128 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sA2)[i] = 0u;
     for (int i = tid; i < 32 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB2)[i] = 0u;
-    for (int i = tid; i < tc::B1_BYTES / 4; i += BD) reinterpret_cast<uint32_t*>(sB1)[i] = 0u;
     for (int i = tid; i < 16 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB3)[i] = 0u;
     if (SPLIT)
         for (int i = tid; i < 16 * H * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB3lo)[i] = 0u;
     __syncthreads();
-    // B1 (N=32 x K=16): input c in {x0,x1,u} occupies k = 3c..3c+2 as [w_hi, w_lo, w_hi]; k = 9, 10: bias hi, lo
+    // the bias K-step of the operand tile: columns KB+9, KB+10 are the constant 1 in every row (written once)
+    for (int r = tid; r < 128; r += BD) {
+        __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(sA2);
+        A[tc::tile_off(r, KB + 9, CHUNKS) / 2] = __float2bfloat16_rn(1.0f);
+        A[tc::tile_off(r, KB + 10, CHUNKS) / 2] = __float2bfloat16_rn(1.0f);
+    }
     for (int n = tid; n < H; n += BD) {
         __nv_bfloat16 bh, bl;
-        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB1);
-        tc::split_bf16(mp.b1[n], bh, bl);
-        B[tc::tile_off(n, 9, 2) / 2] = bh;
-        B[tc::tile_off(n, 10, 2) / 2] = bl;
-        B = reinterpret_cast<__nv_bfloat16*>(sB2);
+        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB2);
         tc::split_bf16(mp.b2[n], bh, bl);
         B[tc::tile_off(n, KB + 9, CHUNKS) / 2] = bh;
         B[tc::tile_off(n, KB + 10, CHUNKS) / 2] = bl;
@@ -268,15 +261,6 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
             B[tc::tile_off(n, KB + 9, CHUNKS) / 2] = bh;
             B[tc::tile_off(n, KB + 10, CHUNKS) / 2] = bl;
         }
-    }
-    for (int e = tid; e < H * 3; e += BD) {
-        const int n = e / 3, c = e - n * 3;
-        __nv_bfloat16 wh, wl;
-        tc::split_bf16(mp.W1[c * H + n], wh, wl);                 // P stores W1 transposed: W1t[c][n]
-        __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB1);
-        B[tc::tile_off(n, 3 * c + 0, 2) / 2] = wh;
-        B[tc::tile_off(n, 3 * c + 1, 2) / 2] = wl;
-        B[tc::tile_off(n, 3 * c + 2, 2) / 2] = wh;
     }
     // B2 (N=32 x K).  SPLIT: the product  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo  is issued as
     //   [a_hi | a_lo | 1 1] x [w_hi ; w_hi ; b_hi b_lo]   (the main tile, K = 80)
@@ -312,20 +296,20 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     const uint32_t tmem = s_tmem_base;
     const uint32_t my_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // warps w and w+4 own TMEM lanes 32 (w % 4) ..: lane = sample row
     uint32_t mma_phase = 0;
-    const uint64_t dB1 = tc::smem_desc(sB1, 2 * tc::CH);
     const uint64_t dA2 = tc::smem_desc(sA2, CHUNKS * tc::CH), dB2 = tc::smem_desc(sB2, CHUNKS * tc::CH),
                    dB3 = tc::smem_desc(sB3, CHUNKS * tc::CH);
     const uint64_t dB2lo = tc::smem_desc(sB2lo, 4 * tc::CH), dB3lo = tc::smem_desc(sB3lo, 4 * tc::CH);
     constexpr uint32_t I32 = tc::instr_desc(128, 32), I16 = tc::instr_desc(128, 16);
     constexpr uint64_t KSTEP = (2 * tc::CH) >> 4;                     // one K=16 step = two 8-element chunks, in 16-byte units
-    const uint64_t dA1 = dA2 + (uint64_t)(KB / 16) * KSTEP;            // layer 1 reads the tile's last K-step
+    // layer 1 on the FP32 pipe: this thread's 16 hidden units (W1 is stored transposed, W1t[c][unit])
+    const int hb = 16 * half;
 
     stage_issue<real, VARIANT, NU>(a, sm);
     bool staged = false;
     real beta_run = O::inf(), eta_run = (real)0;
 
     // Tile = 128 samples; the two threads of a sample share its draws and its colour/clamp pass (a.tps == 2), thread 0
-    // of the pair (half 0, warps 0-3) carries the state, the cost and the layer-1 operand row.
+    // of the pair (half 0, warps 0-3) carries the state and the cost.
     const int BS = BD / a.tps;
     const bool roller = half == 0;                     // warp-uniform
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -356,7 +340,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 x[1] = a.x0[1];
             }
         }
-        real roll = (real)0, pert = (real)0, smooth = (real)0, vprev = (real)0;
+        real roll = (real)0, pert = (real)0, smooth = (real)0, vprev = (real)0, u_prev = (real)0;
         // debug_clocks (profiling aid, scripts/tc_phase_clocks.py): clock64() sums over the T steps of the first tile, per phase,
         // for thread 0 (the MMA issuer) in slots 0..7 and thread 32 (a plain worker) in slots 8..15 of this CTA's row
         const bool prof = a.dbg != nullptr && tile == blockIdx.x && (tid == 0 || tid == 32);
@@ -378,76 +362,65 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 }
                 u = O::mul(nm.u_scale, v[0]);
                 const real uc = clamp<real>(u, -mp.max_torque, mp.max_torque);
-                // layer 1 operand row: [x0h x0h x0l | x1h x1h x1l | uh uh ul | 1 1 0...]
-                __nv_bfloat16 h0, l0, h1, l1, h2, l2;
-                tc::split_bf16(x[0], h0, l0);
-                tc::split_bf16(x[1], h1, l1);
-                tc::split_bf16(uc, h2, l2);
-                const __nv_bfloat16 z = __float2bfloat16_rn(0.0f), one = __float2bfloat16_rn(1.0f);
-                unsigned char* rp = sA2 + (row >> 3) * (CHUNKS * tc::CH) + (KB / 8) * tc::CH + (row & 7) * 16;
-                *reinterpret_cast<uint4*>(rp) = make_uint4(tc::pack2(h0, h0), tc::pack2(l0, h1), tc::pack2(h1, l1), tc::pack2(h2, h2));
-                *reinterpret_cast<uint4*>(rp + tc::CH) = make_uint4(tc::pack2(l2, one), tc::pack2(one, z), 0u, 0u);
-                tc::fence_async_smem();
-                tc::fence_before();
+                *reinterpret_cast<float4*>(sX + 4 * row) = make_float4(x[0], x[1], uc, 0.0f);
             }
-            TC_PROF(0)      // state/cost of the previous step + layer-1 operand row
+            TC_PROF(0)      // state of the previous step + layer-1 input
             __syncthreads();
             TC_PROF(1)      // barrier
-            if (tid == 0) {
-                tc::fence_after();
-                tc::mma_f16(tmem + 0, dA1, dB1, I32, 0u);
-                tc::mma_commit(&s_mma_bar);
-            }
-            TC_PROF(2)      // MMA issue (thread 0)
             float hv[16];
-            {   // layer 1 -> tanh -> this thread's half of the layer-2 operand row
-                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
-                TC_PROF(3)  // commit -> mbarrier
-                tc::fence_after();
-                tc::tmem_ld16_nowait(my_lane + 16 * half, hv);
-                tc::tmem_wait_ld();
-                TC_PROF(4)  // TMEM load
+            {   // layer 1 on the FP32 pipe (exact fp32): 16 units x 3 FMAs -> tanh -> this thread's half of the layer-2 operand row
+                const float4 xin = *reinterpret_cast<const float4*>(sX + 4 * row);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) hv[i] = Model::tanh_(hv[i], FAST);
+                for (int i = 0; i < 16; ++i) {
+                    float acc = mp.b1[hb + i];
+                    acc = fmaf(mp.W1[0 * H + hb + i], xin.x, acc);
+                    acc = fmaf(mp.W1[1 * H + hb + i], xin.y, acc);
+                    acc = fmaf(mp.W1[2 * H + hb + i], xin.z, acc);
+                    hv[i] = Model::tanh_(acc, FAST);
+                }
                 tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);
-                TC_PROF(5)  // tanh + pack + store
+                TC_PROF(5)  // layer 1 + tanh + pack + store
                 tc::fence_async_smem();
                 tc::fence_before();
                 TC_PROF(6)  // proxy fence
             }
-            mma_phase ^= 1u;
             __syncthreads();
             TC_PROF(1)
             if (tid == 0) {
                 tc::fence_after();
 #pragma unroll
-                for (int s = 0; s < NSTEP; ++s)
-                    tc::mma_f16(tmem + C2 + 32 * (NA > 1 ? s / 2 : 0), dA2 + s * KSTEP, dB2 + s * KSTEP, I32, (NA > 1 ? (s & 1) : (s > 0)) ? 1u : 0u);
+                for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + C2, dA2 + s * KSTEP, dB2 + s * KSTEP, I32, s > 0 ? 1u : 0u);
                 if (SPLIT) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s)
-                        tc::mma_f16(tmem + C2 + 32 * (NA > 1 ? (NSTEP + s) / 2 : 0), dA2 + s * KSTEP, dB2lo + s * KSTEP, I32,
-                                    (NA > 1 ? ((NSTEP + s) & 1) : 1) ? 1u : 0u);
+                    for (int s = 0; s < 2; ++s) tc::mma_f16(tmem + C2, dA2 + s * KSTEP, dB2lo + s * KSTEP, I32, 1u);
                 }
                 tc::mma_commit(&s_mma_bar);
             }
-            TC_PROF(2)
-            {   // layer 2 -> sum of the accumulators -> tanh -> half row of the layer-3 operand
-                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
-                TC_PROF(3)
-                tc::fence_after();
-                float acc[NA][16];
-#pragma unroll
-                for (int q = 0; q < NA; ++q) tc::tmem_ld16_nowait(my_lane + C2 + 32 * q + 16 * half, acc[q]);
-                tc::tmem_wait_ld();
-                TC_PROF(4)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float sum = acc[0][i];
-                    if (NA == 2) sum = acc[0][i] + acc[1][i];
-                    if (NA == 4) sum = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
-                    hv[i] = Model::tanh_(sum, FAST);
+            TC_PROF(2)      // MMA issue (thread 0)
+            // in the shadow of the layer-2 MMA: the running cost of the state the PREVIOUS step produced (x is x_t, the
+            // state step t-1 led to) and this step's action cost — same values and summation order as the plain loop
+            if (active) {
+                if (t > 0) roll = O::add(roll, Model::template cost<real>(mp, x, &u_prev));   // mppi.py:318-319 (step t-1)
+                pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
+                if (VARIANT == V_SMPPI) {
+                    if (t > 0) {
+                        const real d = O::mul(nm.u_scale, O::sub(v[0], vprev));
+                        smooth = O::add(smooth, O::mul(d, d));
+                    }
+                    vprev = v[0];
                 }
+            }
+            u_prev = u;
+            TC_PROF(7)      // deferred cost
+            {   // layer 2 -> tanh -> half row of the layer-3 operand
+                tc::mbar_wait_bounded(&s_mma_bar, mma_phase);
+                TC_PROF(3)  // commit -> mbarrier
+                tc::fence_after();
+                tc::tmem_ld16_nowait(my_lane + C2 + 16 * half, hv);
+                tc::tmem_wait_ld();
+                TC_PROF(4)  // TMEM load
+#pragma unroll
+                for (int i = 0; i < 16; ++i) hv[i] = Model::tanh_(hv[i], FAST);
                 tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);     // MMA 2 has completed (barrier): its operand tile is free
                 TC_PROF(5)
                 tc::fence_async_smem();
@@ -460,13 +433,10 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
             if (tid == 0) {
                 tc::fence_after();
 #pragma unroll
-                for (int s = 0; s < NSTEP; ++s)
-                    tc::mma_f16(tmem + C3 + 16 * (NA > 1 ? s / 2 : 0), dA2 + s * KSTEP, dB3 + s * KSTEP, I16, (NA > 1 ? (s & 1) : (s > 0)) ? 1u : 0u);
+                for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + C3, dA2 + s * KSTEP, dB3 + s * KSTEP, I16, s > 0 ? 1u : 0u);
                 if (SPLIT) {
 #pragma unroll
-                    for (int s = 0; s < 2; ++s)
-                        tc::mma_f16(tmem + C3 + 16 * (NA > 1 ? (NSTEP + s) / 2 : 0), dA2 + s * KSTEP, dB3lo + s * KSTEP, I16,
-                                    (NA > 1 ? ((NSTEP + s) & 1) : 1) ? 1u : 0u);
+                    for (int s = 0; s < 2; ++s) tc::mma_f16(tmem + C3, dA2 + s * KSTEP, dB3lo + s * KSTEP, I16, 1u);
                 }
                 tc::mma_commit(&s_mma_bar);
             }
@@ -475,35 +445,19 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
             TC_PROF(3)
             tc::fence_after();
             if (roller) {
-                float o0[NA], o1[NA];
-#pragma unroll
-                for (int q = 0; q < NA; ++q) tc::tmem_ld2_nowait(my_lane + C3 + 16 * q, o0[q], o1[q]);
-                tc::tmem_wait_ld();
-                float s0 = o0[0], s1 = o1[0];
-                if (NA == 2) { s0 = o0[0] + o0[1]; s1 = o1[0] + o1[1]; }
-                if (NA == 4) { s0 = (o0[0] + o0[1]) + (o0[2] + o0[3]); s1 = (o1[0] + o1[1]) + (o1[2] + o1[3]); }
-                const real th = O::add(x[0], s0);
+                float o0, o1;
+                tc::tmem_ld2(my_lane + C3, o0, o1);
+                const real th = O::add(x[0], o0);
                 x[0] = O::sub(remainder<real>(O::add(th, mp.pi), mp.two_pi), mp.pi);    // pendulum_approximate.py:65
-                x[1] = O::add(x[1], s1);
+                x[1] = O::add(x[1], o1);
             }
             TC_PROF(4)
             // the next step's MMAs overwrite these accumulators: order the reads before the barrier that releases them
             tc::fence_before();
             mma_phase ^= 1u;
-            if (active) {
-                roll = O::add(roll, Model::template cost<real>(mp, x, &u));               // mppi.py:318-319
-                pert = O::add(pert, action_cost_term<real, NU>(nm, eps, sm.Us + t * NU));
-                if (VARIANT == V_SMPPI) {
-                    if (t > 0) {
-                        const real d = O::mul(nm.u_scale, O::sub(v[0], vprev));
-                        smooth = O::add(smooth, O::mul(d, d));
-                    }
-                    vprev = v[0];
-                }
-            }
         }
+        if (active) roll = O::add(roll, Model::template cost<real>(mp, x, &u_prev));              // step T-1
         if (prof) {
-            TC_PROF(7)
 #pragma unroll
             for (int i = 0; i < 8; ++i) a.dbg[(size_t)blockIdx.x * 16 + (tid == 0 ? 0 : 8) + i] = (unsigned long long)pc[i];
         }

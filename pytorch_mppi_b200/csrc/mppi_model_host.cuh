@@ -18,18 +18,10 @@ bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, K
             p_tc.threads_per_sample = 2;
             p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
             const bool fast = p->model_params[2] != 0.0;
-            // MPPI_TC_NACC=1: one TMEM accumulator per layer (a chain of 7 dependent MMAs in hi/lo-split mode) instead
-            // of independent accumulators summed in registers — kept for A/B timing
-            const char* e_na = getenv("MPPI_TC_NACC");
-            const bool one = e_na != nullptr && atoi(e_na) == 1;
-            if (one)
-                kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1, 1> : mlp_tc_command_kernel<V, 1, 0, 1>)
-                                   : (fast ? mlp_tc_command_kernel<V, 0, 1, 1> : mlp_tc_command_kernel<V, 0, 0, 1>);
-            else
-                kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1, 4> : mlp_tc_command_kernel<V, 1, 0, 4>)
-                                   : (fast ? mlp_tc_command_kernel<V, 0, 1, 4> : mlp_tc_command_kernel<V, 0, 0, 4>);
+            kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
+                               : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
             g_tc_kernel = 1;
-            g_tc_cols = tc::tmem_cols(mode == 1, one ? 1 : 4);
+            g_tc_cols = tc::TMEM_COLS;
             // co-residency is bounded by shared memory: ask for the largest carve-out
             cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             return true;

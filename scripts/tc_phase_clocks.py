@@ -24,7 +24,7 @@ nb = c.launch_info.grid_blocks
 dbg = torch.zeros(nb, 16, dtype=torch.int64, device="cuda")
 c._debug_clocks = dbg
 c._dirty = True
-names = ["state+row1", "barrier", "mma issue", "commit->mbar", "tmem ld", "tanh+pack", "proxy fence", "tail"]
+names = ["state+input", "barrier", "mma issue", "commit->mbar", "tmem ld", "tanh+pack", "proxy fence", "deferred cost"]
 for rep in range(2):
     dbg.zero_()
     c.command(x)
