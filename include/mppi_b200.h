@@ -176,6 +176,8 @@ typedef struct MppiFusedParams {
                                     phase boundaries of each CTA's first tile; NULL on the product path   */
     void* xchg_status_host;      /* optional pinned HOST int64: the kernel stores MPPI_ERR_TIMEOUT there when a peer
                                     exchange timed out (the caller checks it before the next command)      */
+    void* user_model;            /* model == MPPI_MODEL_USER: handle from mppi_user_model_register (a model compiled at
+                                    run time), or NULL for a model linked into a variant library            */
 } MppiFusedParams;
 
 typedef struct MppiLaunchInfo {
@@ -264,6 +266,15 @@ int mppi_apply_partials(const MppiFusedParams* p, const void* partials, void* st
 
 /* Peer mailboxes for the in-kernel NVLink exchange.  The library owns these small buffers
  * (cudaMalloc + cudaIpc), because IPC handles must cover a whole allocation. */
+/* A user-written analytic model compiled at run time (the reference's plugin surface is arbitrary Python callables,
+ * mppi.py:63-64; analytic ones can be given as CUDA C++ bodies — pytorch_mppi_b200.models.CudaModel — and are compiled
+ * with NVRTC in process).  `cubin` is the compiled module, `names` the lowered names of its kernels:
+ * [0] fused_command_kernel<UserModel, real, variant, false, false>   [1] ... split-cost (or NULL)
+ * [2] ... batched, MPPI variant (or NULL)   [3] resident_command_kernel<UserModel, real, variant> (or NULL)
+ * [4] states_kernel<UserModel, real>.  The handle goes into MppiFusedParams.user_model with model = MPPI_MODEL_USER. */
+int mppi_user_model_register(const void* cubin, uint64_t cubin_bytes, int32_t nx, int32_t nu, int32_t n_params, int32_t dtype,
+                             int32_t variant, const char* const* names, void** handle_out);
+int mppi_user_model_release(void* handle);
 /* Highest command epoch this plan has used (the tag of its reduction records, shared by the launch and resident routes);
  * pass it as MppiFusedParams.epoch when re-creating the plan so that stale records can never match. */
 uint64_t mppi_plan_epoch(void* plan);

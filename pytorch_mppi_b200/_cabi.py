@@ -105,6 +105,7 @@ class MppiFusedParams(C.Structure):
         ("K_geom", C.c_int32),
         ("debug_clocks", C.c_void_p),
         ("xchg_status_host", C.c_void_p),
+        ("user_model", C.c_void_p),
     ]
 
 
@@ -147,6 +148,9 @@ SYMBOLS = [
     ("mppi_resident_stop", C.c_int, [C.c_void_p]),
     ("mppi_resident_launches", C.c_uint64, [C.c_void_p]),
     ("mppi_plan_epoch", C.c_uint64, [C.c_void_p]),
+    ("mppi_user_model_register", C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]),
+    ("mppi_user_model_release", C.c_int, [C.c_void_p]),
     ("mppi_apply_partials", C.c_int, [_P, C.c_void_p, C.c_void_p]),
     ("mppi_xchg_create", C.c_int, [C.POINTER(C.c_void_p), C.c_void_p]),
     ("mppi_xchg_open", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -27,12 +27,13 @@ def _h(*names):
 
 
 COMMON_HEADERS = _h("mppi_host.cuh", "mppi_fused.cuh", "mppi_math.cuh", "mppi_resident.cuh", "mppi_resident_host.h") + [PUBLIC_HEADER]
-MODEL_HEADERS = COMMON_HEADERS + _h("mppi_model_host.cuh", "mppi_mlp_tc.cuh")
+MODEL_HEADERS = COMMON_HEADERS + _h("mppi_mlp_tc.cuh")
+CABI_HEADERS = COMMON_HEADERS + _h("mppi_fused_host.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # name -> (source, extra defines, headers it depends on)
-UNITS = {"cabi": ("mppi_b200.cu", [], COMMON_HEADERS)}
+UNITS = {"cabi": ("mppi_b200.cu", [], CABI_HEADERS)}
 for _mid, _mname in ((1, "pendulum"), (2, "linear_point"), (3, "pendulum_mlp")):
     for _f64 in (0, 1):
         UNITS[f"model_{_mname}_{'f64' if _f64 else 'f32'}"] = (
@@ -120,6 +121,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     _link(objs, OUT)
     with open(STAMP, "w") as f:
         f.write(h)
+    # everything cached for user models was built from the previous sources: drop it (it is keyed by the source hash and
+    # would never be used again, but it travels with every snapshot of the tree)
+    udir = os.path.join(CSRC, "_user")
+    if os.path.isdir(udir):
+        for name in os.listdir(udir):
+            try:
+                os.unlink(os.path.join(udir, name))
+            except OSError:
+                pass
     return OUT
 
 

@@ -6,43 +6,60 @@
 //   mppi_b200.cu        this file: the C ABI, the model-independent kernels (sampling, softmin update, cost
 //                       accumulation, omega, apply-partials), plan commands, resident-mode backend, peer mailboxes
 //   mppi_model_tu.cu    compiled once per (registered model, dtype): fused / resident / states kernels of that model
-#include "mppi_host.cuh"
+#include "mppi_fused_host.cuh"
 
 namespace mppi_host {
 thread_local char g_cuda_err[512] = "";
 
-// one getter per (model, dtype) translation unit, all weak: the stock library links the six registry units, a user-model
-// variant library (pytorch_mppi_b200.build.build_user_model) links this unit and the two units of that model only
-#define MPPI_OPS_DECL(name) const ModelOps* name() __attribute__((weak))
-MPPI_OPS_DECL(model_ops_pendulum_f32);
-MPPI_OPS_DECL(model_ops_pendulum_f64);
-MPPI_OPS_DECL(model_ops_linear_point_f32);
-MPPI_OPS_DECL(model_ops_linear_point_f64);
-MPPI_OPS_DECL(model_ops_pendulum_mlp_f32);
-MPPI_OPS_DECL(model_ops_pendulum_mlp_f64);
-MPPI_OPS_DECL(model_ops_user_f32);
-MPPI_OPS_DECL(model_ops_user_f64);
+// one getter per (model, dtype) translation unit, all weak: the stock library links the six registry units, an
+// nvcc-built user-model variant library links this unit and the two units of that model only
+#define MPPI_KERNELS_DECL(name) const ModelKernels* name() __attribute__((weak))
+MPPI_KERNELS_DECL(model_kernels_pendulum_f32);
+MPPI_KERNELS_DECL(model_kernels_pendulum_f64);
+MPPI_KERNELS_DECL(model_kernels_linear_point_f32);
+MPPI_KERNELS_DECL(model_kernels_linear_point_f64);
+MPPI_KERNELS_DECL(model_kernels_pendulum_mlp_f32);
+MPPI_KERNELS_DECL(model_kernels_pendulum_mlp_f64);
+MPPI_KERNELS_DECL(model_kernels_user_f32);
+MPPI_KERNELS_DECL(model_kernels_user_f64);
 }  // namespace mppi_host
 
 namespace {
 
-// the (model, dtype) unit that serves these parameters, or nullptr
-const ModelOps* find_ops(const MppiFusedParams* p, int* rc) {
+// a user model compiled at run time (mppi_user_model_register): its descriptor travels in MppiFusedParams.user_model
+struct UserModelHandle {
+    uint32_t magic;
+    ModelKernels mk;
+};
+constexpr uint32_t kUserMagic = 0x4d505049u;   // "MPPI"
+
+// the (model, dtype) descriptor that serves these parameters, or nullptr
+const ModelKernels* find_kernels(const MppiFusedParams* p, int* rc) {
     *rc = MPPI_ERR_UNSUPPORTED;
     const bool f32 = p->dtype == MPPI_F32;
-    typedef const ModelOps* (*Getter)();
+    typedef const ModelKernels* (*Getter)();
     Getter get = nullptr;
     switch (p->model) {
-        case MPPI_MODEL_PENDULUM: get = f32 ? model_ops_pendulum_f32 : model_ops_pendulum_f64; break;
-        case MPPI_MODEL_LINEAR_POINT: get = f32 ? model_ops_linear_point_f32 : model_ops_linear_point_f64; break;
+        case MPPI_MODEL_PENDULUM: get = f32 ? model_kernels_pendulum_f32 : model_kernels_pendulum_f64; break;
+        case MPPI_MODEL_LINEAR_POINT: get = f32 ? model_kernels_linear_point_f32 : model_kernels_linear_point_f64; break;
         case MPPI_MODEL_PENDULUM_MLP:
             if (p->n_model_params_ext < PendulumMLPModel::N_EXT || p->model_params_ext == nullptr) {
                 *rc = MPPI_ERR_BAD_ARG;
                 return nullptr;
             }
-            get = f32 ? model_ops_pendulum_mlp_f32 : model_ops_pendulum_mlp_f64;
+            get = f32 ? model_kernels_pendulum_mlp_f32 : model_kernels_pendulum_mlp_f64;
             break;
-        case MPPI_MODEL_USER: get = f32 ? model_ops_user_f32 : model_ops_user_f64; break;
+        case MPPI_MODEL_USER:
+            if (p->user_model != nullptr) {
+                const UserModelHandle* h = reinterpret_cast<const UserModelHandle*>(p->user_model);
+                if (h->magic != kUserMagic || h->mk.is_double != (f32 ? 0 : 1)) {
+                    *rc = MPPI_ERR_BAD_ARG;
+                    return nullptr;
+                }
+                return &h->mk;
+            }
+            get = f32 ? model_kernels_user_f32 : model_kernels_user_f64;
+            break;
     }
     return get != nullptr ? get() : nullptr;      // nullptr: this library was linked without that unit
 }
@@ -160,8 +177,9 @@ static_assert((int)RES_ERR_BAD_ARG == (int)MPPI_ERR_BAD_ARG && (int)RES_ERR_TIME
 int dispatch_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
     int rc = validate(p, true);
     if (rc) return rc;
-    const ModelOps* ops = find_ops(p, &rc);
-    return ops != nullptr ? ops->run_fused(p, s, info) : rc;
+    const ModelKernels* mk = find_kernels(p, &rc);
+    if (mk == nullptr) return rc;
+    return mk->is_double ? run_fused<double>(mk, p, s, info) : run_fused<float>(mk, p, s, info);
 }
 
 // ---- generic path: sample / softmin -------------------------------------------------------------
@@ -317,8 +335,8 @@ int mppi_plan_create(const MppiFusedParams* p, void** plan_out) {
     if (rc) return rc;
     Plan* pl = new (std::nothrow) Plan();
     if (pl == nullptr) return MPPI_ERR_BAD_ARG;
-    const ModelOps* ops = find_ops(p, &rc);
-    if (ops != nullptr) rc = ops->build_plan(p, pl);
+    const ModelKernels* mk = find_kernels(p, &rc);
+    if (mk != nullptr) rc = mk->is_double ? build_plan<double>(mk, p, pl) : build_plan<float>(mk, p, pl);
     if (rc) {
         delete pl;
         return rc;
@@ -422,6 +440,72 @@ int mppi_resident_stop(void* plan) {
     return pl == nullptr ? (int)MPPI_ERR_BAD_ARG : res_stop(pl->res);
 }
 
+// ---- user models compiled at run time ----------------------------------------------------------------------------------
+// The Python side compiles `mppi_fused.cuh + mppi_resident.cuh + the user's model header` with NVRTC (in process, no
+// toolkit) into a cubin and hands it over with the lowered names of the kernels; they are loaded as a cudaLibrary_t and
+// wrapped in a ModelKernels table exactly like a registry unit's.  `names`: 6 entries, nullptr = not built:
+//   [0] fused (this variant)  [1] split-cost  [2] batched (MPPI variant only)  [3] resident  [4] states  [5] unused
+namespace {
+void user_load(const ModelKernels* mk, void* dst, const double* blob, const double* ext, int n_ext) {
+    for (int i = 0; i < mk->np; ++i) {
+        const double v = i < MPPI_MODEL_PARAM_DOUBLES ? blob[i] : ((ext != nullptr && i - MPPI_MODEL_PARAM_DOUBLES < n_ext) ? ext[i - MPPI_MODEL_PARAM_DOUBLES] : 0.0);
+        if (mk->is_double) reinterpret_cast<double*>(dst)[i] = v;
+        else reinterpret_cast<float*>(dst)[i] = (float)v;
+    }
+}
+}  // namespace
+
+int mppi_user_model_register(const void* cubin, uint64_t cubin_bytes, int32_t nx, int32_t nu, int32_t n_params, int32_t dtype,
+                             int32_t variant, const char* const* names, void** handle_out) {
+    if (cubin == nullptr || cubin_bytes == 0 || names == nullptr || handle_out == nullptr) return MPPI_ERR_BAD_ARG;
+    if (nx < 1 || nx > MPPI_MAX_NX || nu < 1 || nu > MPPI_MAX_NU || n_params < 1 || variant < 0 || variant > 2) return MPPI_ERR_BAD_ARG;
+    if (dtype != MPPI_F32 && dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
+    const int es = dtype == MPPI_F64 ? 8 : 4;
+    if (n_params * es > MPPI_MODEL_BLOCK_BYTES) return UNSUPPORTED("user model has too many parameters");
+    cudaLibrary_t lib = nullptr;
+    CK(cudaLibraryLoadData(&lib, cubin, nullptr, nullptr, 0, nullptr, nullptr, 0));
+    UserModelHandle* h = new (std::nothrow) UserModelHandle();
+    if (h == nullptr) return MPPI_ERR_BAD_ARG;
+    memset(h, 0, sizeof(*h));
+    h->magic = kUserMagic;
+    ModelKernels& mk = h->mk;
+    mk.nx = nx;
+    mk.nu = nu;
+    mk.is_double = dtype == MPPI_F64;
+    mk.np = n_params;
+    mk.param_bytes = n_params * es;
+    mk.load = user_load;
+    mk.library = (void*)lib;
+    const void** slots[5] = {&mk.fused[variant], &mk.split[variant], &mk.batched, &mk.resident[variant], &mk.states};
+    for (int i = 0; i < 5; ++i) {
+        if (names[i] == nullptr) continue;
+        cudaKernel_t k = nullptr;
+        cudaError_t e = cudaLibraryGetKernel(&k, lib, names[i]);
+        if (e != cudaSuccess) {
+            cudaLibraryUnload(lib);
+            delete h;
+            return cuda_fail(e, names[i]);
+        }
+        *slots[i] = (const void*)k;
+    }
+    if (mk.fused[variant] == nullptr || mk.states == nullptr) {
+        cudaLibraryUnload(lib);
+        delete h;
+        return MPPI_ERR_BAD_ARG;
+    }
+    *handle_out = h;
+    return MPPI_OK;
+}
+
+int mppi_user_model_release(void* handle) {
+    UserModelHandle* h = reinterpret_cast<UserModelHandle*>(handle);
+    if (h == nullptr || h->magic != kUserMagic) return MPPI_ERR_BAD_ARG;
+    if (h->mk.library != nullptr) cudaLibraryUnload((cudaLibrary_t)h->mk.library);
+    h->magic = 0;
+    delete h;
+    return MPPI_OK;
+}
+
 uint64_t mppi_plan_epoch(void* plan) {
     Plan* pl = reinterpret_cast<Plan*>(plan);
     if (pl == nullptr) return 0;
@@ -508,8 +592,9 @@ int mppi_materialize(const MppiFusedParams* p, void* perturbed_action, void* noi
              ? run_sample_any<float>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s)
              : run_sample_any<double>(p, perturbed_action, noise, noise_theta, nullptr, nullptr, 0, 0, true, s);
     if (rc || states == nullptr) return rc;
-    const ModelOps* ops = find_ops(p, &rc);
-    return ops != nullptr ? ops->run_states(p, perturbed_action, states, s) : rc;
+    const ModelKernels* mk = find_kernels(p, &rc);
+    if (mk == nullptr) return rc;
+    return mk->is_double ? run_states<double>(mk, p, perturbed_action, states, s) : run_states<float>(mk, p, perturbed_action, states, s);
 }
 
 int mppi_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, int64_t actions_stride,
@@ -520,8 +605,10 @@ int mppi_rollout_states(const MppiFusedParams* p, const void* start_states, cons
     if (p->dtype != MPPI_F32 && p->dtype != MPPI_F64) return MPPI_ERR_BAD_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = MPPI_ERR_UNSUPPORTED;
-    const ModelOps* ops = find_ops(p, &rc);
-    return ops != nullptr ? ops->rollout_states(p, start_states, actions, actions_stride, n_rollouts, T, states_out, s) : rc;
+    const ModelKernels* mk = find_kernels(p, &rc);
+    if (mk == nullptr) return rc;
+    return mk->is_double ? run_rollout_states<double>(mk, p, start_states, actions, actions_stride, n_rollouts, T, states_out, s)
+                         : run_rollout_states<float>(mk, p, start_states, actions, actions_stride, n_rollouts, T, states_out, s);
 }
 
 int mppi_sample_perturb(const MppiFusedParams* p, void* perturbed_action, void* noise, void* noise_theta, void* cost_init,

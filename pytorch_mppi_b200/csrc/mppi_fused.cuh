@@ -975,7 +975,7 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
     if (beta_new == O::inf()) return;                   // warp-uniform: no sample of this warp has a cost yet
     const real wgt = active ? O::exp_(nfl * (c_tot - beta_new)) : (real)0;                       // mppi.py:12-13, 256
     const double resc = (beta_run == O::inf()) ? 0.0 : (double)O::exp_(nfl * (beta_run - beta_new));
-    const double eta_tile = warp_sum<double>((double)wgt);
+    const double eta_tile = (double)warp_sum<real>(wgt);
     const int nv = min(32, nvalid - i0);
     for (int jb = 0; jb < R; jb += 32) {
         const int j = jb + lane;
@@ -985,13 +985,16 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
         const real a2 = VARIANT == V_SMPPI ? sm.As[jc] : (VARIANT == V_KMPPI ? sm.ths[jc] : (real)0);
         // SMPPI: the tile of effective noise (rows2, written once by transform_column) — no division here
         const real* row = (VARIANT == V_SMPPI ? sm.rows2 : sm.rows) + (size_t)jc * LD + i0;
-        double acc = 0.0;
+        // the 32 products of a warp are added in the controller's precision (as the reference's einsum does, in its own
+        // order); everything ACROSS warps, CTAs and GPUs is fp64 (measured: an fp64 inner sum costs the large-K
+        // geometry, where every warp folds, 5 us per command through F2F.F64 / DADD issue)
+        real acc = (real)0;
         for (int i = 0; i < nv; ++i) {
             const real wi = __shfl_sync(0xffffffffu, wgt, i);
             const real e = VARIANT == V_SMPPI ? row[i] : eps_of<real, VARIANT>(a.nm, row[i], us, a2);
-            acc += (double)(wi * e);                                                            // mppi.py:268
+            acc += wi * e;                                                                      // mppi.py:268
         }
-        if (jv) rec[2 + j] = rec[2 + j] * resc + acc;
+        if (jv) rec[2 + j] = rec[2 + j] * resc + (double)acc;
     }
     if (lane == 0) {
         rec[0] = (double)beta_new;
@@ -1055,6 +1058,9 @@ static __device__ __noinline__ void xchg_publish_words(unsigned long long* const
         const unsigned long long word = ((unsigned long long)flag << 32) | half;
         for (int g = 0; g < xw; ++g) st_peer(peers[g] + off + i, word);
     }
+    // remote words travel as posted NVLink writes: a system-scope fence by the storing threads makes the hub push them
+    // out instead of letting them sit in its write-combining buffers (the records are what every peer's finisher waits for)
+    if (xw > 1) __threadfence_system();
 }
 template <typename real>
 __device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int xw, int rec_index, const double* src) {

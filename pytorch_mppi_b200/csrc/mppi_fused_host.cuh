@@ -1,34 +1,31 @@
-// mppi_model_host.cuh — the launch / plan templates of one registered model (instantiated by mppi_model_tu.cu).
+// mppi_fused_host.cuh — kernel selection, launch geometry, plans and launches of the fused command, for ANY model: the
+// model enters through a ModelKernels descriptor (kernel handles + parameter packing), so this is compiled once, in
+// mppi_b200.cu, and serves the registry models and NVRTC-compiled user models alike.
 #pragma once
 #include "mppi_host.cuh"
-#include "mppi_mlp_tc.cuh"
 
 namespace {
 
 // ---- fused command ----------------------------------------------------------------------------
 // PENDULUM_MLP in fp32 with model_params[3] != 0: the tcgen05/TMEM kernel (mppi_mlp_tc.cuh).  One CTA = 256 threads = 128
 // samples (two threads per sample) = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
-template <class Model, typename real, int V, typename KernelT>
-bool select_tensor_core_route(const MppiFusedParams* p, MppiFusedParams& p_tc, KernelT& kernel) {
-    if constexpr (std::is_same<Model, PendulumMLPModel>::value && std::is_same<real, float>::value) {
+inline bool select_tensor_core_route(const ModelKernels* mk, const MppiFusedParams* p, MppiFusedParams& p_tc, const void*& kernel) {
+    if (mk->is_mlp && !mk->is_double) {
         const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
-        if ((mode == 1 || mode == 2) && p->n_env <= 1) {
+        const int fast = p->model_params[2] != 0.0 ? 1 : 0;
+        if ((mode == 1 || mode == 2) && p->n_env <= 1 && mk->tc[p->variant][mode - 1][fast] != nullptr) {
             p_tc = *p;
             p_tc.block_threads = 128;                   // samples per tile
             p_tc.threads_per_sample = 2;
             p_tc.flags &= ~(uint32_t)MPPI_FLAG_PDL;
-            const bool fast = p->model_params[2] != 0.0;
-            kernel = mode == 1 ? (fast ? mlp_tc_command_kernel<V, 1, 1> : mlp_tc_command_kernel<V, 1, 0>)
-                               : (fast ? mlp_tc_command_kernel<V, 0, 1> : mlp_tc_command_kernel<V, 0, 0>);
+            kernel = mk->tc[p->variant][mode - 1][fast];
             g_tc_kernel = 1;
-            g_tc_cols = tc::TMEM_COLS;
+            g_tc_cols = 64;                             // tc::TMEM_COLS (mppi_mlp_tc.cuh)
             // co-residency is bounded by shared memory: ask for the largest carve-out
-            cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             return true;
         }
     }
-    (void)p_tc;
-    (void)kernel;
     return false;
 }
 
@@ -49,13 +46,15 @@ struct FusedChoice {
     int split, wide, tc;
 };
 
-template <class Model, typename real, int V>
-int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& c) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+template <typename real>
+int choose_fused(const ModelKernels* mk, const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& c) {
+    if (p->nx != mk->nx || p->nu != mk->nu) return MPPI_ERR_BAD_ARG;
+    const int V = p->variant;
     const bool batched = p->n_env > 1;
     if (batched && (V != V_MPPI || p->world > 1)) return UNSUPPORTED("batched environments: MPPI variant, single GPU only");
-    auto kernel = (batched && V == V_MPPI) ? fused_command_kernel<Model, real, V_MPPI, true> : fused_command_kernel<Model, real, V, false>;
-    const bool tc_route = select_tensor_core_route<Model, real, V>(p, p_tc, kernel);
+    const void* kernel = batched ? mk->batched : mk->fused[V];
+    if (kernel == nullptr) return UNSUPPORTED("this model was built without the kernel of this controller variant");
+    const bool tc_route = select_tensor_core_route(mk, p, p_tc, kernel);
     if (tc_route) p = &p_tc;
     const int R = rows_of(p), es = (int)sizeof(real);
     const int world = p->world <= 0 ? 1 : p->world;
@@ -70,7 +69,7 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
         rc = plan_geometry(kernel, &pg, es, 0, false, g, layout_fn<real>);
         g_tc_kernel = 0;
         if (rc) return rc;
-        c = FusedChoice{(const void*)kernel, g, 0, 0, 1};
+        c = FusedChoice{kernel, g, 0, 0, 1};
         return MPPI_OK;
     }
     const int xst1 = sharded ? world * (R + 2) : 0;          // staging of the rank-record exchange
@@ -78,15 +77,15 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
     rc = plan_geometry(kernel, &pg, es, layout_extra(tile2, 0, 1, xst1), true, g, layout_fn<real>);
     if (rc) return rc;
     int split = 0;
-    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {      // its step is the network; the cost is nothing
+    if (mk->split[V] != nullptr) {      // (the MLP has none: its step is the network, the cost is nothing)
         if (!batched && (p->flags & MPPI_FLAG_SPLIT_COST) && g.tps > 1) {
-            auto k2 = fused_command_kernel<Model, real, V, false, true>;
+            const void* k2 = mk->split[V];
             MppiFusedParams p2 = pg;
             p2.block_threads = g.BS;
             p2.threads_per_sample = g.tps;
             p2.grid_blocks = g.nb;
             Geometry g2;
-            if (plan_geometry(k2, &p2, es, layout_extra(tile2, Model::NX, 1, xst1), true, g2, layout_fn<real>) == MPPI_OK &&
+            if (plan_geometry(k2, &p2, es, layout_extra(tile2, mk->nx, 1, xst1), true, g2, layout_fn<real>) == MPPI_OK &&
                 g2.BS == g.BS && g2.tps == g.tps) {
                 kernel = k2;
                 g = g2;
@@ -101,7 +100,7 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
     int want = 8;
     if (const char* e = getenv("MPPI_B200_CLUSTER")) want = atoi(e);
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, (const void*)kernel));
+    CK(cudaFuncGetAttributes(&fa, kernel));
     const int dyn_limit = di.max_smem_optin - (int)fa.sharedSizeBytes;
     const int envs = batched ? p->n_env : 1;
     g.cluster = 0;
@@ -120,14 +119,14 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
             if (atoi(e) == 0) npub = 1;
         const int xst = fused_xstage_doubles(sharded, world, npub, R);
         const SmemLayout L = make_layout<real>(p->variant, p->T, p->nu, p->S, R, g.BD, g.BS, fused_layout_nb(NC, npub),
-                                               layout_extra(tile2, split ? Model::NX : 0, cs, xst));
+                                               layout_extra(tile2, split ? mk->nx : 0, cs, xst));
         if (L.total > dyn_limit) continue;
         if (cs > 1) {
             cudaLaunchConfig_t cfg;
             cudaLaunchAttribute at[3];
             launch_config(cfg, at, nbp, g.BD, L.total, nullptr, (p->flags & MPPI_FLAG_PDL) != 0, envs, cs);
             int max_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void*)kernel, &cfg) != cudaSuccess) {
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) {
                 cudaGetLastError();
                 continue;
             }
@@ -140,7 +139,7 @@ int choose_fused(const MppiFusedParams*& p, MppiFusedParams& p_tc, FusedChoice& 
         break;
     }
     if (g.cluster == 0) return UNSUPPORTED("shared-memory tile does not fit");
-    c = FusedChoice{(const void*)kernel, g, split, 0, 0};
+    c = FusedChoice{kernel, g, split, 0, 0};
     return MPPI_OK;
 }
 
@@ -149,13 +148,13 @@ template <typename real> void finish_kargs(const MppiFusedParams* p, const Fused
     a.xchg_npub = c.g.npub > 0 ? c.g.npub : 1;
 }
 
-template <class Model, typename real, int V>
-int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
+template <typename real>
+int run_fused(const ModelKernels* mk, const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info) {
     const bool batched = p->n_env > 1;
     if (batched && info == nullptr && !(p->flags & MPPI_FLAG_STATE_DEVICE)) return MPPI_ERR_BAD_ARG;   // states are (n_env, nx) on the device
     MppiFusedParams p_tc;
     FusedChoice c;
-    int rc = choose_fused<Model, real, V>(p, p_tc, c);
+    int rc = choose_fused<real>(mk, p, p_tc, c);
     if (rc) return rc;
     const Geometry& g = c.g;
     const uint64_t need_ws = ws_bytes(g.nb, rows_of(p), (int)sizeof(real));
@@ -189,62 +188,49 @@ int run_fused(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* inf
         return MPPI_ERR_WORKSPACE;
     if (a.world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
     if (a.export_partial && p->partial_out == nullptr) return MPPI_ERR_BAD_ARG;
-    typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    alignas(16) unsigned char mp[MPPI_MODEL_BLOCK_BYTES];
+    if (mk->param_bytes > (int)sizeof(mp)) return UNSUPPORTED("model parameter block too large");
+    mk->load(mk, mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
     if ((rc = refuse_capture(stream, g)) != MPPI_OK) return rc;
     if (a.world == 1 || a.export_partial) {       // plan-less single-GPU launches draw their record tags from one process-wide counter
         static unsigned long long s_epoch = 0;
         a.epoch = __atomic_add_fetch(&s_epoch, 1ull, __ATOMIC_RELAXED);
     }
-    void* argv2[2] = {(void*)&a, (void*)&mp};
+    void* argv2[2] = {(void*)&a, (void*)mp};
     cudaError_t e = launch_raw(c.kernel, g.nb, g.BD, g.smem, stream, argv2, a.pdl != 0, a.n_env, g.cluster);
     if (e != cudaSuccess) return cuda_fail(e, "fused launch");
     return MPPI_OK;
 }
 
-template <class Model, typename real>
-int run_fused_variant(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) {
-    switch (p->variant) {
-        case MPPI_VARIANT_MPPI: return run_fused<Model, real, V_MPPI>(p, s, info);
-        case MPPI_VARIANT_SMPPI: return run_fused<Model, real, V_SMPPI>(p, s, info);
-        case MPPI_VARIANT_KMPPI: return run_fused<Model, real, V_KMPPI>(p, s, info);
-    }
-    return MPPI_ERR_BAD_ARG;
-}
-
-
-template <class Model, typename real, int V> int build_plan(const MppiFusedParams* p, Plan* pl) {
+template <typename real> int build_plan(const ModelKernels* mk, const MppiFusedParams* p, Plan* pl) {
     const bool batched = p->n_env > 1;
+    const int V = p->variant;
     MppiFusedParams p_tc;
     FusedChoice c;
-    int rc = choose_fused<Model, real, V>(p, p_tc, c);
+    int rc = choose_fused<real>(mk, p, p_tc, c);
     if (rc) return rc;
     pl->g = c.g;
     if (p->U == nullptr || p->cost_total == nullptr || p->nominal_used == nullptr || p->stats == nullptr || p->workspace == nullptr)
         return MPPI_ERR_BAD_ARG;
     if (p->workspace_bytes < ws_bytes(pl->g.nb, rows_of(p), (int)sizeof(real))) return MPPI_ERR_WORKSPACE;
-    static_assert(sizeof(typename Model::template P<real>) <= sizeof(pl->mparams), "model parameter block too large");
+    if (mk->param_bytes > (int)sizeof(pl->mparams)) return UNSUPPORTED("model parameter block too large");
     KArgs<real>* a = reinterpret_cast<KArgs<real>*>(pl->kargs);
     finish_kargs<real>(p, c, *a);
     if (a->world > 1 && rows_of(p) > MPPI_XCHG_MAX_R) return UNSUPPORTED("T*nu exceeds the peer mailbox record size");
-    typename Model::template P<real>* mp = reinterpret_cast<typename Model::template P<real>*>(pl->mparams);
-    Model::template load<real>(*mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    mk->load(mk, pl->mparams, p->model_params, p->model_params_ext, p->n_model_params_ext);
     pl->kernel = c.kernel;
     pl->res_kernel = nullptr;
     pl->res_xchg = 0;
-    if constexpr (!std::is_same<Model, PendulumMLPModel>::value) {
-        // resident mode runs the split-cost rollout with one tile per CTA: exactly the single-GPU plans that took it
-        // (the resident grid is a cooperative launch without clusters; it carries its own tail, mppi_resident.cuh)
-        if (c.split && !batched && !a->export_partial && a->world == 1 && a->n_tiles <= pl->g.nb && pl->g.nb <= a->n_tiles + pl->g.cluster - 1)
-            pl->res_kernel = (const void*)resident_command_kernel<Model, real, V>;
+    // resident mode runs the split-cost rollout with one tile per CTA: exactly the single-GPU plans that took it, with
+    // the launch route's grid and cluster size (mppi_resident.cuh)
+    if (c.split && !batched && !a->export_partial && a->world == 1 && a->n_tiles <= pl->g.nb && pl->g.nb <= a->n_tiles + pl->g.cluster - 1) {
+        pl->res_kernel = mk->resident[V];
         // the one instantiation with %globaltimer stamps (a profiling aid, scripts/resident_timeline.py)
-        if constexpr (std::is_same<Model, PendulumModel>::value && std::is_same<real, float>::value && V == V_MPPI) {
-            if (pl->res_kernel != nullptr && p->debug_clocks != nullptr)
-                pl->res_kernel = (const void*)resident_command_kernel<Model, real, V, true>;
-        }
+        if (pl->res_kernel != nullptr && p->debug_clocks != nullptr && V == V_MPPI && mk->resident_stamped != nullptr)
+            pl->res_kernel = mk->resident_stamped;
     }
     pl->is_double = sizeof(real) == 8;
-    pl->nx = Model::NX;
+    pl->nx = mk->nx;
     pl->upc_nu = p->u_per_command * p->nu;
     pl->pdl = (p->flags & MPPI_FLAG_PDL) ? 1 : 0;
     pl->epoch = p->epoch;
@@ -254,33 +240,34 @@ template <class Model, typename real, int V> int build_plan(const MppiFusedParam
     return MPPI_OK;
 }
 
-template <class Model, typename real> int build_plan_variant(const MppiFusedParams* p, Plan* pl) {
-    switch (p->variant) {
-        case MPPI_VARIANT_MPPI: return build_plan<Model, real, V_MPPI>(p, pl);
-        case MPPI_VARIANT_SMPPI: return build_plan<Model, real, V_SMPPI>(p, pl);
-        case MPPI_VARIANT_KMPPI: return build_plan<Model, real, V_KMPPI>(p, pl);
-    }
-    return MPPI_ERR_BAD_ARG;
-}
-
-template <class Model, typename real>
-int run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStream_t stream) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
-    KArgs<real> a;
-    fill_kargs<real>(p, a, 128, 1);
-    typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    states_kernel<Model, real><<<(p->K + 127) / 128, 128, 0, stream>>>((const real*)pa, (real*)states, a, mp,
-                                                                        (long long)p->T * p->nu);
-    CK(cudaGetLastError());
+template <typename real>
+int launch_states(const ModelKernels* mk, const MppiFusedParams* p, KArgs<real>& a, int n, const void* actions, void* states,
+                  long long stride, cudaStream_t stream) {
+    alignas(16) unsigned char mp[MPPI_MODEL_BLOCK_BYTES];
+    if (mk->param_bytes > (int)sizeof(mp)) return UNSUPPORTED("model parameter block too large");
+    mk->load(mk, mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
+    const real* pa = (const real*)actions;
+    real* st = (real*)states;
+    void* argv[5] = {(void*)&pa, (void*)&st, (void*)&a, (void*)mp, (void*)&stride};
+    cudaError_t e = cudaLaunchKernel(mk->states, dim3((n + 127) / 128), dim3(128), argv, 0, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "states launch");
     return MPPI_OK;
 }
 
+// states along the rollouts of the last command's perturbed actions (mppi.py:307-322)
+template <typename real>
+int run_states(const ModelKernels* mk, const MppiFusedParams* p, const void* pa, void* states, cudaStream_t stream) {
+    if (p->nx != mk->nx || p->nu != mk->nu) return MPPI_ERR_BAD_ARG;
+    KArgs<real> a;
+    fill_kargs<real>(p, a, 128, 1);
+    return launch_states<real>(mk, p, a, p->K, pa, states, (long long)p->T * p->nu, stream);
+}
+
 // get_rollouts (mppi.py:425-448): n start states, each rolled through an action sequence
-template <class Model, typename real>
-int run_rollout_states(const MppiFusedParams* p, const void* start_states, const void* actions, long long stride, int n, int T,
-                       void* states, cudaStream_t stream) {
-    if (p->nx != Model::NX || p->nu != Model::NU) return MPPI_ERR_BAD_ARG;
+template <typename real>
+int run_rollout_states(const ModelKernels* mk, const MppiFusedParams* p, const void* start_states, const void* actions, long long stride,
+                       int n, int T, void* states, cudaStream_t stream) {
+    if (p->nx != mk->nx || p->nu != mk->nu) return MPPI_ERR_BAD_ARG;
     KArgs<real> a;
     memset(&a, 0, sizeof(a));
     a.nm.u_scale = (real)p->u_scale;
@@ -288,11 +275,7 @@ int run_rollout_states(const MppiFusedParams* p, const void* start_states, const
     a.T = T;
     a.state_dev = (const real*)start_states;
     a.state_per_sample = 1;
-    typename Model::template P<real> mp;
-    Model::template load<real>(mp, p->model_params, p->model_params_ext, p->n_model_params_ext);
-    states_kernel<Model, real><<<(n + 127) / 128, 128, 0, stream>>>((const real*)actions, (real*)states, a, mp, stride);
-    CK(cudaGetLastError());
-    return MPPI_OK;
+    return launch_states<real>(mk, p, a, n, actions, states, stride, stream);
 }
 
 }  // namespace

@@ -23,6 +23,8 @@ namespace mppi_host {
 // last error text of the calling thread (one definition, in mppi_b200.cu)
 extern thread_local char g_cuda_err[512];
 
+#define MPPI_MODEL_BLOCK_BYTES 12288     // largest Model::P<real> a kernel takes by value (the MLP's weights: 10 KB in fp64)
+
 struct Geometry {
     int BD, BS, tps, nb, smem, occ, regs;   // BD = BS * tps threads per CTA, BS samples per tile
     int cluster;                            // thread-block-cluster size of the launch (1: none); nb is a multiple of it
@@ -51,18 +53,29 @@ struct Plan {
     unsigned long long epoch, host_epoch;
     unsigned long long res_epoch_off;  // resident mode: record-mailbox epoch of command seq = res_epoch_off + seq
     alignas(16) unsigned char kargs[sizeof(KArgs<double>)];
-    alignas(16) unsigned char mparams[12288];
+    alignas(16) unsigned char mparams[MPPI_MODEL_BLOCK_BYTES];
 };
 
-// what one (model, dtype) translation unit exports to the dispatch in mppi_b200.cu
-struct ModelOps {
-    int (*run_fused)(const MppiFusedParams* p, cudaStream_t stream, MppiLaunchInfo* info);
-    int (*build_plan)(const MppiFusedParams* p, Plan* pl);
-    int (*run_states)(const MppiFusedParams* p, const void* perturbed_action, void* states, cudaStream_t stream);
-    int (*rollout_states)(const MppiFusedParams* p, const void* start_states, const void* actions, long long stride, int n,
-                          int T, void* states, cudaStream_t stream);
+// What one (model, dtype) pair contributes: its kernels (as launchable handles) and how to pack its parameter block.
+// The six registry units (mppi_model_tu.cu) each export one statically; a user model compiled at run time with NVRTC
+// (mppi_user_model_register) gets one on the heap.  Everything that selects and launches kernels (mppi_fused_host.cuh)
+// works on this descriptor, so it is compiled once, not per model.
+struct ModelKernels {
+    int nx, nu;
+    int is_double;
+    int is_mlp;                      // PendulumMLP: no split-cost / resident variants; tensor-core kernels in `tc`
+    int np;                          // run-time user models: reals in the parameter block (P = { real v[np]; })
+    int param_bytes;                 // sizeof(Model::P<real>)
+    void (*load)(const ModelKernels* self, void* dst, const double* blob, const double* ext, int n_ext);
+    const void* fused[3];            // fused_command_kernel<Model, real, V, false, false>, V = MPPI / SMPPI / KMPPI
+    const void* split[3];            // ... SPLIT = true (nullptr: not available)
+    const void* batched;             // fused_command_kernel<Model, real, V_MPPI, true>
+    const void* resident[3];         // resident_command_kernel<Model, real, V> (nullptr: not available)
+    const void* resident_stamped;    // the one instantiation with %globaltimer stamps, or nullptr
+    const void* states;              // states_kernel<Model, real>
+    const void* tc[3][2][2];         // mlp_tc_command_kernel<V, SPLIT = 2 - mode, FAST>, [V][mode - 1][fast]; fp32 MLP only
+    void* library;                   // run-time user models: the cudaLibrary_t that owns the kernels
 };
-
 }  // namespace mppi_host
 
 using namespace mppi_host;

@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     Smem<real> sm(smem, L);
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
+    if (a.dbg != nullptr && tid == 32) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.dbg[(size_t)blockIdx.x * 16 + 12] = gt;
+    }
 
     // ---- one-time setup: TMEM, MMA barrier, bf16 weight tiles (hi/lo split, K-extended) -----------------
     if (warp == 0) {
@@ -351,7 +356,11 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
         pc[slot] += now_ - pt;                 \
         pt = now_;                             \
     }
-        if (prof) pt = clock64();
+        unsigned long long gt_loop0 = 0;
+        if (prof) {
+            pt = clock64();
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_loop0));
+        }
         for (int t = 0; t < T; ++t) {
             real v[NU] = {(real)0}, eps[NU] = {(real)0};
             real u = (real)0;
@@ -458,8 +467,19 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
         }
         if (active) roll = O::add(roll, Model::template cost<real>(mp, x, &u_prev));              // step T-1
         if (prof) {
+            if (tid == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a.dbg[(size_t)blockIdx.x * 16 + (tid == 0 ? 0 : 8) + i] = (unsigned long long)pc[i];
+                for (int i = 0; i < 8; ++i) a.dbg[(size_t)blockIdx.x * 16 + i] = (unsigned long long)pc[i];
+            } else {     // the worker: its waiting / loading / tanh / cost sums, then wall-clock stamps of the rollout loop
+                a.dbg[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)pc[3];
+                a.dbg[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)pc[4];
+                a.dbg[(size_t)blockIdx.x * 16 + 10] = (unsigned long long)pc[5];
+                a.dbg[(size_t)blockIdx.x * 16 + 11] = (unsigned long long)(pc[0] + pc[1] + pc[2] + pc[6] + pc[7]);
+                a.dbg[(size_t)blockIdx.x * 16 + 13] = gt_loop0;
+                unsigned long long gt1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+                a.dbg[(size_t)blockIdx.x * 16 + 14] = gt1;
+            }
         }
 #undef TC_PROF
         real c_tot = O::inf();
@@ -478,6 +498,11 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TMEM_COLS) : "memory");
     }
     publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
+    if (a.dbg != nullptr && tid == 32) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        a.dbg[(size_t)blockIdx.x * 16 + 15] = gt;
+    }
 }
 
 #endif  // __CUDACC__

@@ -1,12 +1,15 @@
 // mppi_model_tu.cu — one translation unit per (registered model, dtype): the fused command kernels
 // (fused_command_kernel<Model, real, V, ...>, all variants and instantiations), the resident command kernels and the
-// states kernel of that model, with the host code that selects and launches them (mppi_model_host.cuh).
+// states kernel of that model — and, for the fp32 MLP, the tcgen05 kernels.  The unit contains no launch logic: it
+// exports ONE symbol, mppi_host::model_kernels_<model>_<dtype>(), a table of kernel handles plus the parameter packer,
+// which the generic host code in mppi_b200.cu (mppi_fused_host.cuh) works on.
 //
 // Compiled several times by pytorch_mppi_b200/build.py:
 //     nvcc ... -DMPPI_TU_MODEL=<1 pendulum | 2 linear point | 3 pendulum MLP | 100 user> -DMPPI_TU_F64=<0|1> -c
-// (user model: additionally -DMPPI_USER_MODEL_HEADER="<generated header>", see models.CudaModel).
-// Each unit exports ONE symbol, mppi_host::model_ops_<model>_<dtype>(), which mppi_b200.cu's dispatch calls.
-#include "mppi_model_host.cuh"
+// (user model built with nvcc: additionally -DMPPI_USER_MODEL_HEADER="<generated header>"; the default route for user
+// models is NVRTC at run time, mppi_user_model_register — same kernels, same table).
+#include "mppi_host.cuh"
+#include "mppi_mlp_tc.cuh"
 
 #ifndef MPPI_TU_MODEL
 #error "MPPI_TU_MODEL must be defined (see pytorch_mppi_b200/build.py)"
@@ -42,23 +45,54 @@ typedef mppi::UserModel TuModel;
 #error "unknown MPPI_TU_MODEL"
 #endif
 
-#define MPPI_TU_CAT2(a, b, c) model_ops_##a##_##b
+#define MPPI_TU_CAT2(a, b, c) model_kernels_##a##_##b
 #define MPPI_TU_CAT(a, b) MPPI_TU_CAT2(a, b, )
 #define MPPI_TU_GETTER MPPI_TU_CAT(MPPI_TU_NAME, MPPI_TU_SUFFIX)
 
 namespace {
 
-int tu_run_fused(const MppiFusedParams* p, cudaStream_t s, MppiLaunchInfo* info) { return run_fused_variant<TuModel, TuReal>(p, s, info); }
-int tu_build_plan(const MppiFusedParams* p, Plan* pl) { return build_plan_variant<TuModel, TuReal>(p, pl); }
-int tu_run_states(const MppiFusedParams* p, const void* pa, void* states, cudaStream_t s) { return run_states<TuModel, TuReal>(p, pa, states, s); }
-int tu_rollout_states(const MppiFusedParams* p, const void* x0, const void* act, long long stride, int n, int T, void* out, cudaStream_t s) {
-    return run_rollout_states<TuModel, TuReal>(p, x0, act, stride, n, T, out, s);
+constexpr bool kIsMlp = MPPI_TU_MODEL == 3;
+typedef TuModel::P<TuReal> TuParams;
+static_assert(sizeof(TuParams) <= MPPI_MODEL_BLOCK_BYTES, "model parameter block too large");
+
+void tu_load(const ModelKernels*, void* dst, const double* blob, const double* ext, int n_ext) {
+    TuModel::load<TuReal>(*reinterpret_cast<TuParams*>(dst), blob, ext, n_ext);
 }
 
-const ModelOps g_ops = {tu_run_fused, tu_build_plan, tu_run_states, tu_rollout_states};
+template <int V> const void* split_kernel() {
+    if constexpr (kIsMlp) return nullptr;                     // its step is the network; the cost is nothing
+    else return (const void*)fused_command_kernel<TuModel, TuReal, V, false, true>;
+}
+template <int V> const void* resident_kernel() {
+    if constexpr (kIsMlp) return nullptr;
+    else return (const void*)resident_command_kernel<TuModel, TuReal, V>;
+}
+const void* stamped_resident_kernel() {
+    if constexpr (MPPI_TU_MODEL == 1 && !MPPI_TU_F64) return (const void*)resident_command_kernel<TuModel, TuReal, V_MPPI, true>;
+    else return nullptr;
+}
+template <int V, int SPLIT, int FAST> const void* tc_kernel() {
+    if constexpr (kIsMlp && !MPPI_TU_F64) return (const void*)mlp_tc_command_kernel<V, SPLIT, FAST>;
+    else return nullptr;
+}
+
+const ModelKernels g_kernels = {
+    TuModel::NX, TuModel::NU, MPPI_TU_F64, kIsMlp ? 1 : 0, 0, (int)sizeof(TuParams), tu_load,
+    {(const void*)fused_command_kernel<TuModel, TuReal, V_MPPI, false>, (const void*)fused_command_kernel<TuModel, TuReal, V_SMPPI, false>,
+     (const void*)fused_command_kernel<TuModel, TuReal, V_KMPPI, false>},
+    {split_kernel<V_MPPI>(), split_kernel<V_SMPPI>(), split_kernel<V_KMPPI>()},
+    (const void*)fused_command_kernel<TuModel, TuReal, V_MPPI, true>,
+    {resident_kernel<V_MPPI>(), resident_kernel<V_SMPPI>(), resident_kernel<V_KMPPI>()},
+    stamped_resident_kernel(),
+    (const void*)states_kernel<TuModel, TuReal>,
+    {{{tc_kernel<V_MPPI, 1, 0>(), tc_kernel<V_MPPI, 1, 1>()}, {tc_kernel<V_MPPI, 0, 0>(), tc_kernel<V_MPPI, 0, 1>()}},
+     {{tc_kernel<V_SMPPI, 1, 0>(), tc_kernel<V_SMPPI, 1, 1>()}, {tc_kernel<V_SMPPI, 0, 0>(), tc_kernel<V_SMPPI, 0, 1>()}},
+     {{tc_kernel<V_KMPPI, 1, 0>(), tc_kernel<V_KMPPI, 1, 1>()}, {tc_kernel<V_KMPPI, 0, 0>(), tc_kernel<V_KMPPI, 0, 1>()}}},
+    nullptr,
+};
 
 }  // namespace
 
 namespace mppi_host {
-const ModelOps* MPPI_TU_GETTER() { return &g_ops; }
+const ModelKernels* MPPI_TU_GETTER() { return &g_kernels; }
 }  // namespace mppi_host

@@ -222,8 +222,9 @@ class CudaModel(AnalyticModel):
     """A user-written analytic model compiled INTO the fused kernel.
 
     The reference takes arbitrary Python callables (mppi.py:63-64); those cannot be inlined into CUDA, so for
-    analytic dynamics/costs you give the two function bodies as CUDA C++ and the engine JIT-builds (nvcc, cached)
-    a variant of its library with your model in the registry.  Inside the bodies:
+    analytic dynamics/costs you give the two function bodies as CUDA C++ and the engine compiles the fused / split-cost /
+    resident / states kernels for your model at run time with NVRTC (in process, cached on disk: pytorch_mppi_b200.rtc)
+    and loads them into the stock library (`mppi_user_model_register`).  Inside the bodies:
 
         x[NX]      state (read/write in `step_code`, read-only in `cost_code` / `terminal_code`)
         u[NU]      action, already multiplied by u_scale
@@ -247,6 +248,7 @@ class CudaModel(AnalyticModel):
         self._step_code, self._cost_code, self._terminal_code = step_code, cost_code, terminal_code
         self._dyn, self._cost, self._term = dynamics, running_cost, terminal_cost
         self._lib_path = None
+        self._rtc_handles = {}
 
     @property
     def has_terminal(self):
@@ -293,8 +295,31 @@ struct UserModel {{
 }}  // namespace mppi
 """
 
+    def compile_rtc(self, dtype, variant):
+        """(cubin bytes, lowered kernel names) of this model's kernels for one dtype and controller variant
+        (0 MPPI / 1 SMPPI / 2 KMPPI): NVRTC, cached on disk.  Needs no GPU."""
+        from . import rtc
+        return rtc.compile_user_model(self.header_text(), "float" if dtype == torch.float32 else "double", int(variant))
+
+    def rtc_handle(self, lib, dtype, variant):
+        """The handle `MppiFusedParams.user_model` takes: the compiled kernels registered with the C library on the
+        CURRENT CUDA device (once per (library, dtype, variant, device))."""
+        import ctypes as C
+        key = (id(lib), dtype, int(variant), torch.cuda.current_device())
+        if key not in self._rtc_handles:
+            cubin, names = self.compile_rtc(dtype, variant)
+            arr = (C.c_char_p * len(names))(*[None if n is None else n.encode() for n in names])
+            handle = C.c_void_p()
+            buf = C.create_string_buffer(cubin, len(cubin))
+            rc = lib.mppi_user_model_register(buf, len(cubin), self.nx, self.nu, max(len(self.params), 1),
+                                              _cabi.F32 if dtype == torch.float32 else _cabi.F64, int(variant), arr, C.byref(handle))
+            _cabi.check(rc, "mppi_user_model_register")
+            self._rtc_handles[key] = handle
+        return self._rtc_handles[key]
+
     def library_path(self):
-        """Path of the (cached) variant library with this model compiled in; builds it on first use."""
+        """The nvcc route (MPPI_B200_USER_MODEL_BUILD=nvcc): path of a (cached) variant library with this model linked in;
+        builds it on first use.  Needs the CUDA toolkit."""
         if self._lib_path is None:
             from . import build
             self._lib_path = build.build_user_model(self.header_text())

@@ -173,7 +173,10 @@ class MPPI:
             m = resolve_fused_model(dynamics, running_cost, terminal_state_cost)
             if m is not None and m.nx == self.nx and m.nu == self.nu:
                 self._model = m
-                if hasattr(m, "library_path"):          # user model: its kernels live in a JIT-built variant library
+                # user model: its kernels are compiled at run time with NVRTC and registered with the stock library
+                # (_pack); MPPI_B200_USER_MODEL_BUILD=nvcc builds a variant library with the toolkit instead
+                self._user_model_nvcc = hasattr(m, "library_path") and os.environ.get("MPPI_B200_USER_MODEL_BUILD", "rtc") == "nvcc"
+                if self._user_model_nvcc:
                     self._lib = _cabi.load(m.library_path())
         if rng not in ("philox", "torch"):
             raise ValueError("rng must be 'philox' (one subsequence per sample) or 'torch' (the stream torch.randn draws on CUDA)")
@@ -347,6 +350,10 @@ class MPPI:
         p.struct_size = C.sizeof(_cabi.MppiFusedParams)
         p.variant = self._VARIANT
         p.model = self._model.model_id if self._model is not None else 0
+        p.user_model = None
+        if self._model is not None and hasattr(self._model, "rtc_handle") and not getattr(self, "_user_model_nvcc", False):
+            with torch.cuda.device(self.d):
+                p.user_model = self._model.rtc_handle(self._lib, self.dtype, self._VARIANT)
         p.dtype = _DT[self.dtype]
         p.K, p.T, p.nx, p.nu = self._K_local, self.T, self.nx, nu
         p.S = 0

@@ -24,18 +24,17 @@ nb = c.launch_info.grid_blocks
 dbg = torch.zeros(nb, 16, dtype=torch.int64, device="cuda")
 c._debug_clocks = dbg
 c._dirty = True
-names = ["state+input", "barrier", "mma issue", "commit->mbar", "tmem ld", "tanh+pack", "proxy fence", "deferred cost"]
+names0 = ["state+input", "barrier", "mma issue", "commit->mbar", "tmem ld", "tanh+pack", "proxy fence", "deferred cost"]
+names1 = ["commit->mbar", "tmem ld", "tanh+pack", "everything else"]
 for rep in range(2):
     dbg.zero_()
     c.command(x)
     torch.cuda.synchronize()
     d = dbg.cpu().numpy().astype(np.float64)
-    print(f"rep {rep}: K={K} T={T} {mode} grid={nb} block={c.launch_info.block_threads}  (clocks per rollout STEP, median over CTAs)")
-    for who, off in (("thread 0 (issuer)", 0), ("thread 32 (worker)", 8)):
-        tot = 0.0
-        parts = []
-        for i, n in enumerate(names):
-            v = float(np.median(d[:, off + i])) / T
-            tot += v
-            parts.append(f"{n} {v:7.0f}")
-        print(f"  {who:20s} " + " | ".join(parts) + f" | sum {tot:7.0f}")
+    print(f"rep {rep}: K={K} T={T} {mode} grid={nb} block={c.launch_info.block_threads}  (clocks per rollout STEP: median / max over CTAs)")
+    print("  thread 0 (issuer):  " + " | ".join(f"{n} {np.median(d[:, i]) / T:6.0f}/{d[:, i].max() / T:6.0f}" for i, n in enumerate(names0) if i != 6))
+    print("  thread 32 (worker): " + " | ".join(f"{n} {np.median(d[:, 8 + i]) / T:6.0f}/{d[:, 8 + i].max() / T:6.0f}" for i, n in enumerate(names1)))
+    t0 = d[:, 12].min()
+    for n, col in (("kernel entry", 12), ("rollout loop begins", 13), ("rollout loop ends", 14), ("CTA done", 15)):
+        v = d[:, col]
+        print(f"  {n:22s} min {(v.min() - t0) / 1e3:8.2f} us  median {(np.median(v) - t0) / 1e3:8.2f}  max {(v.max() - t0) / 1e3:8.2f}")

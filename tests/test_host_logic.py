@@ -180,6 +180,23 @@ def test_cuda_model_builds_a_variant_library():
     assert torch.equal(m.dynamics(s, torch.zeros(8, 1)), ref.dynamics(s, torch.zeros(8, 1)))
 
 
+def test_cuda_model_compiles_with_nvrtc_in_process():
+    """The default route for user models: NVRTC compiles the fused / split-cost / batched / resident / states kernels of
+    the model from the engine's own kernel headers — no nvcc, no GPU — and returns a cubin plus the lowered names the C
+    library resolves (`mppi_user_model_register`); the result is cached on disk."""
+    from tests.user_models import pendulum_user_model
+    m = pendulum_user_model()
+    cubin, names = m.compile_rtc(torch.float32, 0)
+    assert cubin[:4] == b"\x7fELF" and len(cubin) > 100000
+    assert len(names) == 5 and all(n is not None for n in names)
+    assert "fused_command_kernel" in names[0] and "UserModel" in names[0] and "states_kernel" in names[4]
+    assert "resident_command_kernel" in names[3]
+    again, names2 = m.compile_rtc(torch.float32, 0)                  # disk cache
+    assert again == cubin and names2 == names
+    _, names_k = m.compile_rtc(torch.float64, 2)                     # KMPPI, fp64: no batched kernel
+    assert names_k[2] is None and "Li2E" in names_k[0] and "dLi2" in names_k[0].replace("UserModelE", "")
+
+
 def test_bf16_split_contraction_precision_model():
     """The arithmetic contract of the tensor-core MLP route (csrc/mppi_mlp_tc.cuh), restated with torch's
     round-to-nearest bf16 casts:  v = hi + lo (both bf16), layer = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo + b_hi + b_lo
