@@ -1016,21 +1016,24 @@ __device__ __noinline__ void combine_records(const volatile double* recs, int nr
                                              double* numd) {
     typedef Ops<real> O;
     const int RW = R + 2, C = R + 1;                      // columns: eta, V[0..R)
-    const int tid = threadIdx.x, BD = blockDim.x, nG = BD >> 6, g = tid >> 6, jl = tid & 63;
-    if (tid < 32) {
-        double b = (double)INFINITY;
-        for (int q = tid; q < nrec; q += 32) b = fmin(b, recs[(size_t)q * RW]);
-        b = warp_min<double>(b);
-        if (tid == 0) numd[0] = b;
-    }
+    const int tid = threadIdx.x, BD = blockDim.x, nG = BD >> 6, g = tid >> 6, jl = tid & 63, nw = BD >> 5;
+    // beta: ONE load per thread (record tid; more only for grids above blockDim records), warp minima through sq[]
+    const double b_mine = tid < nrec ? recs[(size_t)tid * RW] : (double)INFINITY;
+    double b = b_mine;
+    for (int q = tid + BD; q < nrec; q += BD) b = fmin(b, recs[(size_t)q * RW]);
+    b = warp_min<double>(b);
+    if ((tid & 31) == 0) part2[tid >> 5] = b;
     __syncthreads();
-    const double beta = numd[0];
+    double beta = part2[0];
+    for (int w = 1; w < nw; ++w) beta = fmin(beta, part2[w]);
     // the rescale factors in the controller's precision (exact for equal betas; beta_q - beta is exact in fp64)
-    for (int q = tid; q < nrec; q += BD) sq[q] = (double)O::exp_((real)(nfl * (recs[(size_t)q * RW] - beta)));
+    if (tid < nrec) sq[tid] = (double)O::exp_((real)(nfl * (b_mine - beta)));
+    for (int q = tid + BD; q < nrec; q += BD) sq[q] = (double)O::exp_((real)(nfl * (recs[(size_t)q * RW] - beta)));
     __syncthreads();
+    if (tid == 0) numd[0] = beta;
     for (int j = jl; j < C; j += 64) {
         double acc = 0.0;
-#pragma unroll 8
+#pragma unroll 16
         for (int q = g; q < nrec; q += nG) acc += sq[q] * recs[(size_t)q * RW + 1 + j];
         part2[(size_t)g * C + j] = acc;
     }
