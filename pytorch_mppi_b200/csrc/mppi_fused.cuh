@@ -31,10 +31,11 @@
 #ifndef MPPI_ROLLOUT_UNROLL
 #define MPPI_ROLLOUT_UNROLL 2
 #endif
-// minimum resident CTAs per SM promised to ptxas for the fused kernel: 0 = unspecified (ptxas then keeps 512-thread
-// CTAs at 64 registers, two per SM — what large K wants); 1 lifts the cap (no spills, one 512-thread CTA per SM)
+// minimum resident CTAs per SM promised to ptxas for the fused kernel: 2 keeps 512-thread CTAs at 64 registers, two per
+// SM — what large K wants (left unspecified, ptxas sizes the kernel for its out-of-line tail functions: 128 registers,
+// one CTA per SM, and BASELINE config 5 loses 25 %); the split-cost variant (small K, one CTA per SM) lifts the cap
 #ifndef MPPI_FUSED_MIN_BLOCKS
-#define MPPI_FUSED_MIN_BLOCKS 0
+#define MPPI_FUSED_MIN_BLOCKS 2
 #endif
 #define MPPI_PRAGMA_(x) _Pragma(#x)
 #define MPPI_UNROLL_N(n) MPPI_PRAGMA_(unroll n)
@@ -1033,7 +1034,7 @@ __device__ __noinline__ void combine_records(const volatile double* recs, int nr
     if (tid == 0) numd[0] = beta;
     for (int j = jl; j < C; j += 64) {
         double acc = 0.0;
-#pragma unroll 16
+#pragma unroll 8
         for (int q = g; q < nrec; q += nG) acc += sq[q] * recs[(size_t)q * RW + 1 + j];
         part2[(size_t)g * C + j] = acc;
     }
@@ -1061,9 +1062,8 @@ static __device__ __noinline__ void xchg_publish_words(unsigned long long* const
         const unsigned long long word = ((unsigned long long)flag << 32) | half;
         for (int g = 0; g < xw; ++g) st_peer(peers[g] + off + i, word);
     }
-    // remote words travel as posted NVLink writes: a system-scope fence by the storing threads makes the hub push them
-    // out instead of letting them sit in its write-combining buffers (the records are what every peer's finisher waits for)
-    if (xw > 1) __threadfence_system();
+    // (measured and rejected: a system-scope fence after the remote stores, meant to push the posted NVLink writes out
+    // sooner, costs 4.5 us per command at two GPUs — 24.2 against 19.7 us back to back)
 }
 template <typename real>
 __device__ __forceinline__ void xchg_publish(const KArgs<real>& a, int xw, int rec_index, const double* src) {
@@ -1367,7 +1367,11 @@ MPPI_UNROLL_N(2)
 // MINB: minimum resident CTAs per SM promised to ptxas.  0 (the default) keeps 512-thread CTAs at 64 registers, which the
 // two-CTA-per-SM geometry of large K needs but which spills the tail's prefetch array; 1 lifts the cap (96 registers, no
 // spills) for launches that place at most one CTA on an SM (MPPI_FLAG_WIDE_REGS; the split-cost variant always has it).
-template <class Model, typename real, int VARIANT, bool BATCHED, bool SPLIT = false, int MINB = (SPLIT ? 1 : MPPI_FUSED_MIN_BLOCKS)>
+// the MLP's step keeps 64 activations live: it gets the whole register file (one CTA per SM) instead of the 64-register cap
+template <class Model> struct FusedMinBlocks { static constexpr int value = MPPI_FUSED_MIN_BLOCKS; };
+template <> struct FusedMinBlocks<PendulumMLPModel> { static constexpr int value = 1; };
+
+template <class Model, typename real, int VARIANT, bool BATCHED, bool SPLIT = false, int MINB = (SPLIT ? 1 : FusedMinBlocks<Model>::value)>
 __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_constant__ KArgs<real> a_in,
                                                             const __grid_constant__ typename Model::template P<real> mp) {
     typedef Ops<real> O;
