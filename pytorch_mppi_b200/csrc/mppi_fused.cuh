@@ -587,12 +587,15 @@ __device__ void fold_tile(const KArgs<real>& a, Smem<real>& sm, real c_tot, bool
 
 // ---- peer exchange over NVLink mailboxes (LL-style 8-byte records: payload32 | flag32) ----------
 // mailbox layout per rank: [2 parity][MPPI_MAX_RANKS src][MPPI_XCHG_MAX_WORDS] u64
+// relaxed.sys, not volatile: the words are self-validating, so nothing orders one against another — and ptxas completes
+// every volatile access before it issues the next (a thread polling 8 words paid 8 L2 round trips per sweep; the same
+// serialisation made a 32-record combine from shared memory cost 1.5 us)
 __device__ __forceinline__ void st_peer(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_poll(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -1013,7 +1016,7 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
 // the tail runs once per command on a cold instruction cache, where instruction count, not arithmetic, sets its time
 // (ncu: `no_instruction` is the third-largest stall of the kernel).
 template <typename real>
-__device__ __noinline__ void combine_records(const volatile double* recs, int nrec, int R, double nfl, double* part2, double* sq,
+__device__ __noinline__ void combine_records(const double* recs, int nrec, int R, double nfl, double* part2, double* sq,
                                              double* numd) {
     typedef Ops<real> O;
     const int RW = R + 2, C = R + 1;                      // columns: eta, V[0..R)
@@ -1032,11 +1035,27 @@ __device__ __noinline__ void combine_records(const volatile double* recs, int nr
     for (int q = tid + BD; q < nrec; q += BD) sq[q] = (double)O::exp_((real)(nfl * (recs[(size_t)q * RW] - beta)));
     __syncthreads();
     if (tid == 0) numd[0] = beta;
+    // the loads of a batch are issued together, THEN used: written as `acc += sq[q] * recs[..]` in one loop, ptxas keeps
+    // every volatile load next to its DFMA and a thread waits one L2 round trip per record (K = 131072: 293 records in
+    // the L2 workspace, 42 per thread — 9 us; batched: 6 round trips)
+    constexpr int UB = 8;
     for (int j = jl; j < C; j += 64) {
         double acc = 0.0;
-#pragma unroll 8
-        for (int q = g; q < nrec; q += nG) acc += sq[q] * recs[(size_t)q * RW + 1 + j];
-        part2[(size_t)g * C + j] = acc;
+        const double* col = recs + 1 + j;
+        for (int q0 = g; q0 < nrec; q0 += nG * UB) {
+            double v[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int q = q0 + u * nG;
+                v[u] = q < nrec ? col[(unsigned)(q * RW)] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int q = q0 + u * nG;
+                if (q < nrec) acc += sq[q] * v[u];
+            }
+        }
+        part2[g * C + j] = acc;
     }
     __syncthreads();
     for (int j = tid; j < C; j += BD) {
@@ -1045,6 +1064,106 @@ __device__ __noinline__ void combine_records(const volatile double* recs, int nr
         numd[1 + j] = t;
     }
     __syncthreads();
+}
+
+// ---- the same combination for records in the L2 workspace (ticket mode: grids of hundreds of CTAs) ---------------------
+// ld.global.cg loads (L2; no SM of this launch has the lines in L1), UB of them in flight per thread before the first is
+// used.  The volatile form above leaves one L2 round trip per record on the critical path — at K = 131072 (293 records,
+// 42 per thread) that was 9 us of a 47 us command.
+template <typename real>
+__device__ __noinline__ void combine_global(const double* recs, int nrec, int R, double nfl, double* part2, double* sq, double* numd) {
+    typedef Ops<real> O;
+    const int RW = R + 2, C = R + 1;
+    const int tid = threadIdx.x, BD = blockDim.x, nG = BD >> 6, g = tid >> 6, jl = tid & 63, nw = BD >> 5;
+    double b = (double)INFINITY;
+    for (int q = tid; q < nrec; q += BD) b = fmin(b, __ldcg(recs + (size_t)q * RW));
+    b = warp_min<double>(b);
+    if ((tid & 31) == 0) part2[tid >> 5] = b;
+    __syncthreads();
+    double beta = part2[0];
+    for (int w = 1; w < nw; ++w) beta = fmin(beta, part2[w]);
+    for (int q = tid; q < nrec; q += BD) {
+        const double bq = __ldcg(recs + (size_t)q * RW);
+        sq[q] = bq == (double)INFINITY ? 0.0 : (double)O::exp_((real)(nfl * (bq - beta)));
+    }
+    __syncthreads();
+    if (tid == 0) numd[0] = beta;
+    constexpr int UB = 8;
+    for (int j = jl; j < C; j += 64) {
+        double acc = 0.0;
+        const double* col = recs + 1 + j;
+        for (int q0 = g; q0 < nrec; q0 += nG * UB) {
+            double v[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int q = q0 + u * nG;
+                v[u] = q < nrec ? __ldcg(col + (size_t)q * RW) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int q = q0 + u * nG;
+                if (q < nrec) acc += sq[q] * v[u];
+            }
+        }
+        part2[g * C + j] = acc;
+    }
+    __syncthreads();
+    for (int j = tid; j < C; j += BD) {
+        double t = part2[j];
+        for (int w = 1; w < nG; ++w) t += part2[w * C + j];
+        numd[1 + j] = t;
+    }
+    __syncthreads();
+}
+
+// ---- the same combination for at most 64 records, WITHOUT CTA barriers or scratch -------------------------------------
+// Only the warps that own a column block take part (warp w: columns 32 w + lane, stride 32 P): each computes beta and the
+// rescale factors for itself (lane l holds those of records l and l + 32, handed round with shuffles) and adds its columns
+// over the records in ascending order (two interleaved chains).  The other warps of the CTA go straight to the one
+// barrier at the end.  This is the form the tail uses at every size that matters for latency: 16 warp records per cluster
+// and 32 cluster records per GPU at BASELINE config 2 — the barrier-and-scratch form above cost 2.3 + 2.9 us there
+// (every warp of the CTA walks its ~600 instructions, contending with the co-resident CTA at large K), this one a fraction.
+template <typename real>
+__device__ __noinline__ void combine_narrow(const double* recs, int nrec, int R, double nfl, double* numd) {
+    typedef Ops<real> O;
+    const int RW = R + 2, C = R + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int P = min(nw, (C + 31) >> 5);
+    if (warp < P) {
+        const double b0 = lane < nrec ? recs[lane * RW] : (double)INFINITY;
+        const double b1 = lane + 32 < nrec ? recs[(lane + 32) * RW] : (double)INFINITY;
+        const double beta = warp_min<double>(fmin(b0, b1));
+        // in the controller's precision (exact for equal betas; beta_q - beta is exact in fp64); an empty record weighs 0
+        const double s0 = b0 == (double)INFINITY ? 0.0 : (double)O::exp_((real)(nfl * (b0 - beta)));
+        const double s1 = b1 == (double)INFINITY ? 0.0 : (double)O::exp_((real)(nfl * (b1 - beta)));
+        for (int jb = warp * 32; jb < C; jb += P * 32) {
+            const int j = jb + lane;
+            const double* col = recs + 1 + (j < C ? j : 0);
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int q0 = 0; q0 < nrec; q0 += 4) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = q0 + u < nrec ? col[(q0 + u) * RW] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = q0 + u;                       // q >= nrec: that lane's factor is 0 and v is 0
+                    const double sq = __shfl_sync(0xffffffffu, q < 32 ? s0 : s1, q & 31);
+                    if (u & 1) acc1 += sq * v[u];
+                    else acc0 += sq * v[u];
+                }
+            }
+            if (j < C) numd[1 + j] = acc0 + acc1;
+        }
+        if (threadIdx.x == 0) numd[0] = beta;
+    }
+    __syncthreads();
+}
+#define MPPI_COMBINE_NARROW_MAX 64
+
+template <typename real>
+__device__ __forceinline__ void combine(Smem<real>& sm, const double* recs, int nrec, int R, double nfl) {
+    if (nrec <= MPPI_COMBINE_NARROW_MAX) combine_narrow<real>(recs, nrec, R, nfl, sm.numd);
+    else combine_records<real>(recs, nrec, R, nfl, sm.part2, sm.sqd, sm.numd);
 }
 
 // ---- record mailboxes: records of (R+2) doubles as LL words (payload32 | flag32), record r at word r * 2 (R+2) ------
@@ -1177,8 +1296,9 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
 
     // (2) leader: cs x nrw warp records -> one cluster record in sm.numd
     {
-        combine_records<real>(sm.wrec, cs * nrw, R, nfl, sm.part2, sm.sqd, sm.numd);
+        combine<real>(sm, sm.wrec, cs * nrw, R, nfl);
     }
+    stamp(a.dbg, 9);
     // (3) publish the cluster record
     if (ll) {
         xchg_publish<real>(a, xw, xr * NC + cid, sm.numd);
@@ -1203,9 +1323,10 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
             xchg_timed_out<real, VARIANT>(a, sm, NU);
             return true;
         }
-        combine_records<real>(sm.xstage, xw * NC, R, nfl, sm.part2, sm.sqd, sm.numd);
+        stamp(a.dbg, 12);
+        combine<real>(sm, sm.xstage, xw * NC, R, nfl);
     } else if (NC > 1) {
-        combine_records<real>(a.crec, NC, R, nfl, sm.part2, sm.sqd, sm.numd);      // volatile loads: L2
+        combine_global<real>(a.crec, NC, R, nfl, sm.part2, sm.sqd, sm.numd);
     }
     stamp(a.dbg, 10);
     if (a.export_partial) {   // library-collective route: caller all-gathers, mppi_apply_partials finishes
@@ -1231,7 +1352,7 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
             xchg_timed_out<real, VARIANT>(a, sm, NU);
             return true;
         }
-        combine_records<real>(sm.xstage, xw, R, nfl, sm.part2, sm.sqd, sm.numd);
+        combine<real>(sm, sm.xstage, xw, R, nfl);
     }
     stamp(a.dbg, 11);
     finish_update<real, VARIANT>(a, sm.numd, sm.Us, sm.As, sm.ths, sm.Ws, NU);

@@ -130,6 +130,8 @@ int choose_fused(const ModelKernels* mk, const MppiFusedParams*& p, MppiFusedPar
                 cudaGetLastError();
                 continue;
             }
+            if (getenv("MPPI_B200_DEBUG_GEOM"))
+                fprintf(stderr, "[mppi_b200] cluster %d: grid %d, smem %d, max active clusters %d (need %d)\n", cs, nbp, L.total, max_clusters, NC * envs);
             if (max_clusters < NC * envs) continue;                       // a cluster left for a second wave doubles the time
         }
         g.cluster = cs;

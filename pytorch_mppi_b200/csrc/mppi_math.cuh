@@ -525,6 +525,40 @@ struct PendulumMLPModel {
 #endif
     }
     static MPPI_HD double tanh_(double x, int) { return tanh(x); }
+    // Four tanh at once, in place.  fp32 exp mode: FIVE XU operations instead of eight — 1 - 2/a_i with a_i = 1 + e^{2 x_i}
+    // needs four reciprocals, and ONE rcp of the product a0 a1 a2 a3 serves them all (1/a0 = r (a2 a3) a1, ...): 4 EX2 +
+    // 1 RCP + 10 FMUL/FFMA.  x is clamped at 10 from above (tanh(10) rounds to 1.0f) so the product stays below e^80; abs
+    // error < 1e-6.  The MLP rollout is bound by the XU pipe (16 lanes per clock per SM), not by FP32 issue.
+    static MPPI_HD void tanh4_(float* v, int mode) {
+#if defined(__CUDA_ARCH__)
+        if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = tanh_(v[i], 1);
+            return;
+        }
+        float a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float t;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fminf(v[i], 10.0f) * 2.8853900817779268f));
+            a[i] = 1.0f + t;
+        }
+        const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+        r *= -2.0f;
+        const float r01 = r * p23, r23 = r * p01;        // -2 / (a0 a1), -2 / (a2 a3)
+        v[0] = fmaf(r01, a[1], 1.0f);
+        v[1] = fmaf(r01, a[0], 1.0f);
+        v[2] = fmaf(r23, a[3], 1.0f);
+        v[3] = fmaf(r23, a[2], 1.0f);
+#else
+        for (int i = 0; i < 4; ++i) v[i] = tanhf(v[i]);
+#endif
+    }
+    static MPPI_HD void tanh4_(double* v, int) {
+        for (int i = 0; i < 4; ++i) v[i] = tanh(v[i]);
+    }
 
     template <typename real> static MPPI_HD void step(const P<real>& p, real* x, const real* u) {
         const real uc = clamp<real>(u[0], -p.max_torque, p.max_torque);
@@ -554,7 +588,9 @@ struct PendulumMLPModel {
 #pragma unroll
             for (int k = 0; k < NB; ++k) acc[k] = fma(W1[2 * H + ib + k], uc, acc[k]);
 #pragma unroll
-            for (int k = 0; k < NB; ++k) h1[ib + k] = tanh_(acc[k], p.tanh_mode);
+            for (int k = 0; k < NB; k += 4) tanh4_(acc + k, p.tanh_mode);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) h1[ib + k] = acc[k];
         }
 #pragma unroll
         for (int ib = 0; ib < H; ib += NB) {
@@ -568,7 +604,9 @@ struct PendulumMLPModel {
                 for (int k = 0; k < NB; ++k) acc[k] = fma(W2[j * H + ib + k], hj, acc[k]);
             }
 #pragma unroll
-            for (int k = 0; k < NB; ++k) h2[ib + k] = tanh_(acc[k], p.tanh_mode);
+            for (int k = 0; k < NB; k += 4) tanh4_(acc + k, p.tanh_mode);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) h2[ib + k] = acc[k];
         }
         // output layer: 2 x 4 partial sums, combined at the end
         real oa[4] = {p.b3[0], (real)0, (real)0, (real)0}, ob[4] = {p.b3[1], (real)0, (real)0, (real)0};

@@ -68,6 +68,13 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one thread of a CONVERGED warp (elect.sync).  The MMA issue must be guarded by this, not by `tid == 0`: ptxas wraps every
+// tcgen05 instruction it cannot prove single-threaded in an ELECT / BRA.U.ANY loop (~80 clocks per MMA, measured)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(void* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -230,6 +237,14 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         a.dbg[(size_t)blockIdx.x * 16 + 12] = gt;
     }
+    // prologue / epilogue wall-clock stamps of thread 32 go to a second block of rows (gridDim.x + blockIdx.x): the debug
+    // buffer scripts/tc_phase_clocks.py hands in has 2 x grid rows
+#define TC_STAMP(slot)                                                               \
+    if (a.dbg != nullptr && tid == 32) {                                             \
+        unsigned long long gt_;                                                      \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                      \
+        a.dbg[((size_t)gridDim.x + blockIdx.x) * 16 + (slot)] = gt_;                 \
+    }
 
     // ---- one-time setup: TMEM, MMA barrier, bf16 weight tiles (hi/lo split, K-extended) -----------------
     if (warp == 0) {
@@ -298,6 +313,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     tc::fence_before();
     __syncthreads();
     tc::fence_after();
+    TC_STAMP(0)     // TMEM allocated, weight tiles built
     const uint32_t tmem = s_tmem_base;
     const uint32_t my_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // warps w and w+4 own TMEM lanes 32 (w % 4) ..: lane = sample row
     uint32_t mma_phase = 0;
@@ -324,14 +340,17 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
         const int nvalid = min(BS, a.K - tile * BS);
         const unsigned long long kg = (unsigned long long)(a.k_offset + k);
         fill_normals<real>(a, sm, tile, in_range, kg, nvalid);
+        if (tile == blockIdx.x) TC_STAMP(1)     // normals drawn
         if (!staged) {
             stage_finish<real, VARIANT, NU>(a, sm);
             staged = true;
         } else {
             __syncthreads();
         }
+        if (tile == blockIdx.x) TC_STAMP(2)     // nominal staged
         if (in_range) transform_column<real, VARIANT, NU>(a, sm, kg);
         __syncthreads();
+        if (tile == blockIdx.x) TC_STAMP(3)     // perturbed actions built
 
         // ---- rollout: the MMAs are CTA-wide, so every thread keeps the step's three barriers ----------------
         real x[NX] = {(real)0, (real)0};
@@ -385,8 +404,10 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                     acc = fmaf(mp.W1[0 * H + hb + i], xin.x, acc);
                     acc = fmaf(mp.W1[1 * H + hb + i], xin.y, acc);
                     acc = fmaf(mp.W1[2 * H + hb + i], xin.z, acc);
-                    hv[i] = Model::tanh_(acc, FAST);
+                    hv[i] = acc;
                 }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) Model::tanh4_(hv + i, FAST);
                 tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);
                 TC_PROF(5)  // layer 1 + tanh + pack + store
                 tc::fence_async_smem();
@@ -395,7 +416,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
             }
             __syncthreads();
             TC_PROF(1)
-            if (tid == 0) {
+            if (warp == 0 && tc::elect_one()) {
                 tc::fence_after();
 #pragma unroll
                 for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + C2, dA2 + s * KSTEP, dB2 + s * KSTEP, I32, s > 0 ? 1u : 0u);
@@ -429,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
                 tc::tmem_wait_ld();
                 TC_PROF(4)  // TMEM load
 #pragma unroll
-                for (int i = 0; i < 16; ++i) hv[i] = Model::tanh_(hv[i], FAST);
+                for (int i = 0; i < 16; i += 4) Model::tanh4_(hv + i, FAST);
                 tc::write_a_half<SPLIT, CHUNKS>(sA2, row, half, hv);     // MMA 2 has completed (barrier): its operand tile is free
                 TC_PROF(5)
                 tc::fence_async_smem();
@@ -439,7 +460,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
             mma_phase ^= 1u;
             __syncthreads();
             TC_PROF(1)
-            if (tid == 0) {
+            if (warp == 0 && tc::elect_one()) {
                 tc::fence_after();
 #pragma unroll
                 for (int s = 0; s < NSTEP; ++s) tc::mma_f16(tmem + C3, dA2 + s * KSTEP, dB3 + s * KSTEP, I16, s > 0 ? 1u : 0u);
@@ -490,6 +511,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
         }
         real w_unused;
         fold_tile<real, VARIANT, false>(a, sm, c_tot, active, nvalid, beta_run, eta_run, w_unused);
+        if (tile == blockIdx.x) TC_STAMP(4)     // tile folded
     }
     if (!staged) stage_finish<real, VARIANT, NU>(a, sm);
     tc::fence_before();
@@ -497,12 +519,14 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TMEM_COLS) : "memory");
     }
+    TC_STAMP(5)         // TMEM released
     publish_and_finish<real, VARIANT, NU>(a, sm, beta_run, eta_run);
     if (a.dbg != nullptr && tid == 32) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         a.dbg[(size_t)blockIdx.x * 16 + 15] = gt;
     }
+#undef TC_STAMP
 }
 
 #endif  // __CUDACC__

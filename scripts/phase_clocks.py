@@ -39,7 +39,7 @@ nb = ctrl.launch_info.grid_blocks
 dbg = torch.zeros(nb, 16, dtype=torch.int64, device="cuda")
 ctrl._debug_clocks = dbg
 ctrl._dirty = True
-names = ["start", "staged", "filled", "transformed", "rolled", "folded", "published", "end(last)", "L:fence", "L:beta", "L:eta", "L:numer"]
+names = ["start", "staged", "filled", "transformed", "rolled", "folded", "tail entered", "CTA exit", "L:published", "combined#1", "L:combined#2", "L:numer", "L:collected"]
 for rep in range(3):
     dbg.zero_()
     torch.cuda.synchronize()
