@@ -299,7 +299,7 @@ def make_engine(eng, wl, K_global, dev, pg, exchange, seed=1234):
         return eng.MPPI(m.dynamics, m.running_cost, 2, torch.tensor(wl["sigma"]), u_min=torch.tensor(-UMAX),
                         u_max=torch.tensor(UMAX), U_init=U0, **kw)
     if wl["model"] == "mlp":
-        m = eng.PendulumMLP(make_mlp_net().to(dev), tensor_cores=wl.get("tensor_cores", "bf16x3"))
+        m = eng.PendulumMLP(make_mlp_net().to(dev), tensor_cores=wl.get("tensor_cores", "auto"))
         torch.manual_seed(0)
         U0 = torch.randn(T, 1)
         return eng.MPPI(m.dynamics, m.running_cost, 2, torch.tensor(wl["sigma"]), u_min=torch.tensor(-UMAX),
@@ -565,7 +565,7 @@ def main():
     ap.add_argument("--workload", default="pendulum_c2", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
-    ap.add_argument("--mlp-mode", default="bf16x3", choices=["bf16x3", "bf16"],
+    ap.add_argument("--mlp-mode", default="auto", choices=["auto", "bf16x3", "bf16"],
                     help="mlp_c4 operand precision on the tensor cores: hi/lo-split bf16 (fp32-grade layer outputs, the parity "
                          "route) or plain bf16")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

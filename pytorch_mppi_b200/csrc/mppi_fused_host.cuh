@@ -11,7 +11,11 @@ namespace {
 // samples (two threads per sample) = the 128 lanes of an M=128 accumulator tile; it does not take part in PDL.
 inline bool select_tensor_core_route(const ModelKernels* mk, const MppiFusedParams* p, MppiFusedParams& p_tc, const void*& kernel) {
     if (mk->is_mlp && !mk->is_double) {
-        const int mode = (int)p->model_params[3];      // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16
+        int mode = (int)p->model_params[3];            // 1: hi/lo-split bf16 operands ("3 x bf16"), 2: plain bf16, 3: automatic
+        // automatic (the Python default): the tensor-core kernel with split operands — the parity route — wherever it
+        // exists (fp32, one environment); it is faster than the FFMA kernel at every K from 1024 to 131072
+        // (profiles/r02_c4_routes.txt: 78 against 113 us at K = 1024, 102 against 141 at 32768, 320 against 337 at 131072)
+        if (mode == 3) mode = 1;
         const int fast = p->model_params[2] != 0.0 ? 1 : 0;
         if ((mode == 1 || mode == 2) && p->n_env <= 1 && mk->tc[p->variant][mode - 1][fast] != nullptr) {
             p_tc = *p;

@@ -247,6 +247,18 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     }
 
     // ---- one-time setup: TMEM, MMA barrier, bf16 weight tiles (hi/lo split, K-extended) -----------------
+    // The weights are kernel parameters (constant bank), cold in this SM's constant cache at every launch: the tile build
+    // below walked them with one dependent miss after another (the setup took 5-6 us of a 100 us command).  Every thread
+    // now requests its words first — all lines in flight while TMEM is allocated and the tiles are zeroed — and parks
+    // them in shared memory, which the tile build reads.
+    constexpr int NPW = (int)(sizeof(PendulumMLPModel::P<float>) / 4);
+    __shared__ __align__(16) float sP[NPW];
+    float pw_reg[(NPW + 255) / 256];
+    {
+        const float* pw = reinterpret_cast<const float*>(&mp);
+#pragma unroll
+        for (int i = 0; i < (NPW + 255) / 256; ++i) pw_reg[i] = tid + i * 256 < NPW ? pw[tid + i * 256] : 0.0f;
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                      "r"((uint32_t)TMEM_COLS)
@@ -262,7 +274,11 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     for (int i = tid; i < 16 * KX * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB3)[i] = 0u;
     if (SPLIT)
         for (int i = tid; i < 16 * H * 2 / 4; i += BD) reinterpret_cast<uint32_t*>(sB3lo)[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < (NPW + 255) / 256; ++i)
+        if (tid + i * 256 < NPW) sP[tid + i * 256] = pw_reg[i];
     __syncthreads();
+    const PendulumMLPModel::P<float>& ms = *reinterpret_cast<const PendulumMLPModel::P<float>*>(sP);
     // the bias K-step of the operand tile: columns KB+9, KB+10 are the constant 1 in every row (written once)
     for (int r = tid; r < 128; r += BD) {
         __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(sA2);
@@ -272,12 +288,12 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     for (int n = tid; n < H; n += BD) {
         __nv_bfloat16 bh, bl;
         __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB2);
-        tc::split_bf16(mp.b2[n], bh, bl);
+        tc::split_bf16(ms.b2[n], bh, bl);
         B[tc::tile_off(n, KB + 9, CHUNKS) / 2] = bh;
         B[tc::tile_off(n, KB + 10, CHUNKS) / 2] = bl;
         if (n < 2) {
             B = reinterpret_cast<__nv_bfloat16*>(sB3);
-            tc::split_bf16(mp.b3[n], bh, bl);
+            tc::split_bf16(ms.b3[n], bh, bl);
             B[tc::tile_off(n, KB + 9, CHUNKS) / 2] = bh;
             B[tc::tile_off(n, KB + 10, CHUNKS) / 2] = bl;
         }
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     for (int e = tid; e < H * H; e += BD) {
         const int n = e / H, k = e - n * H;
         __nv_bfloat16 wh, wl;
-        tc::split_bf16(mp.W2[k * H + n], wh, wl);                 // W2t[k][n] = W2[n][k]
+        tc::split_bf16(ms.W2[k * H + n], wh, wl);                 // W2t[k][n] = W2[n][k]
         __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB2);
         B[tc::tile_off(n, k, CHUNKS) / 2] = wh;
         if (SPLIT) {
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(256, 2) mlp_tc_command_kernel(const __grid_con
     for (int e = tid; e < 2 * H; e += BD) {
         const int n = e / H, k = e - n * H;
         __nv_bfloat16 wh, wl;
-        tc::split_bf16(mp.W3[n * H + k], wh, wl);
+        tc::split_bf16(ms.W3[n * H + k], wh, wl);
         __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(sB3);
         B[tc::tile_off(n, k, CHUNKS) / 2] = wh;
         if (SPLIT) {

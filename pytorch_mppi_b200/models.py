@@ -179,7 +179,7 @@ class PendulumMLP(AnalyticModel):
     nx, nu = 2, 1
     H = 32
 
-    def __init__(self, net: torch.nn.Sequential, max_torque=2.0, w_thdot=0.1, fast_tanh=False, tensor_cores=False):
+    def __init__(self, net: torch.nn.Sequential, max_torque=2.0, w_thdot=0.1, fast_tanh=False, tensor_cores="auto"):
         lin = [m for m in net if isinstance(m, torch.nn.Linear)]
         act = [m for m in net if not isinstance(m, torch.nn.Linear)]
         shapes = [tuple(l.weight.shape) for l in lin]
@@ -191,9 +191,13 @@ class PendulumMLP(AnalyticModel):
         # (csrc/mppi_mlp_tc.cuh).  True / "bf16x3": operands are hi/lo-split bf16, layer outputs agree with the
         # fp32 FFMA kernel to ~1e-5 relative.  "bf16": plain bf16 operands for the two hidden-layer products
         # (~2^-8 relative; the state inputs stay split), the fastest route.
-        if tensor_cores not in (False, True, None, "bf16x3", "bf16"):
-            raise ValueError("tensor_cores must be False, True, 'bf16x3' or 'bf16'")
-        self.tensor_cores = {False: 0, None: 0, True: 1, "bf16x3": 1, "bf16": 2}[tensor_cores]
+        # "auto" (default): "bf16x3" wherever the tensor-core kernel exists (fp32 controllers, one environment), the FFMA
+        # kernel elsewhere (fp64, MPPI_Batched); False pins the FFMA kernel.
+        if not any(tensor_cores is v or tensor_cores == v for v in (False, True, None, "auto", "bf16x3", "bf16")):
+            raise ValueError("tensor_cores must be 'auto', False, True, 'bf16x3' or 'bf16'")
+        if tensor_cores is True:
+            tensor_cores = "bf16x3"
+        self.tensor_cores = {False: 0, None: 0, "bf16x3": 1, "bf16": 2, "auto": 3}[tensor_cores]
 
     def param_blob(self):
         return [self.max_torque, self.w_thdot, 1.0 if self.fast_tanh else 0.0, float(self.tensor_cores)]

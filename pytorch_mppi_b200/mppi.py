@@ -449,7 +449,7 @@ class MPPI:
             self.launch_info = info
             need = int(info.workspace_bytes)
         else:
-            need = 16 + 148 * 16 * (2 + self._noise_rows()) * 8 + 256 + 2 * 12288 * 8
+            need = 32 + 148 * 16 * (4 + self._noise_rows()) * 8 + 256 + 2 * 12288 * 8
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = torch.zeros(need, device=self.d, dtype=torch.uint8)
         p.workspace = self._workspace.data_ptr()

@@ -29,8 +29,8 @@ nb = ctrl.launch_info.grid_blocks
 dbg = torch.zeros(nb, 16, dtype=torch.int64, device=dev)
 ctrl._debug_clocks = dbg
 ctrl._dirty = True
-names = {0: "start", 3: "transformed", 4: "rolled", 5: "folded", 6: "cluster done", 8: "published (finisher)", 10: "all records in + combined",
-         11: "numerators", 7: "end"}
+names = {0: "start", 3: "transformed", 4: "rolled", 5: "folded", 6: "tail entered (cluster barrier)", 9: "cluster record combined",
+         8: "L: record published", 12: "L: all records collected", 10: "L: records combined", 11: "L: numerators", 7: "CTA exit"}
 for rep in range(4):
     dbg.zero_()
     dist.barrier()
@@ -43,13 +43,13 @@ for rep in range(4):
     t_start = torch.tensor([int(d[:, 0][d[:, 0] > 0].min())], dtype=torch.int64, device=dev)
     starts = [torch.zeros_like(t_start) for _ in range(world)]
     dist.all_gather(starts, t_start)
-    t0 = min(int(s.item()) for s in starts)
+    t0 = int(t_start.item())      # per rank: the GPUs' global timers are NOT synchronised (measured: 0.4 s apart)
     lines = [f"rep {rep} rank {rank}: start offset {(int(t_start.item()) - t0) / 1e3:.2f} us  grid={nb} cluster={ctrl.launch_info.cluster_size} records={ctrl.launch_info.xchg_records}"]
     for slot, n in names.items():
         col = d[:, slot]
         col = col[col > 0]
         if len(col):
-            lines.append(f"    {n:28s} min {(col.min() - t0) / 1e3:7.2f}  median {(np.median(col) - t0) / 1e3:7.2f}  max {(col.max() - t0) / 1e3:7.2f}")
+            lines.append(f"    {n:32s} min {(col.min() - t0) / 1e3:7.2f}  median {(np.median(col) - t0) / 1e3:7.2f}  max {(col.max() - t0) / 1e3:7.2f}")
     for r in range(world):
         if r == rank and rep >= 2:
             print("\n".join(lines), flush=True)

@@ -589,7 +589,7 @@ def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
                               torch.nn.Linear(32, 2)).to(dtype)
     import copy
     cpu_model = eng.PendulumMLP(copy.deepcopy(net))
-    gpu_model = eng.PendulumMLP(copy.deepcopy(net).cuda())
+    gpu_model = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores=False)      # the FFMA kernel (fp64 has no other)
     K, T = 4096, 30
     g = torch.Generator().manual_seed(2)
     U0 = torch.randn(T, 1, generator=g, dtype=dtype)
@@ -620,6 +620,25 @@ def test_fused_mlp_dynamics_matches_oracle(dtype, tol):
         x = cpu_model.dynamics(x.view(1, -1), r["action"].view(1, -1)).view(-1)
 
 
+def test_mlp_default_route_is_the_tensor_core_kernel_in_fp32():
+    """PendulumMLP() without a route argument ("auto"): fp32 controllers run the tcgen05 kernel with split operands (the
+    parity route), fp64 controllers and MPPI_Batched the FFMA kernel."""
+    import copy
+    import pytorch_mppi_b200 as eng
+    torch.manual_seed(25)
+    net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(), torch.nn.Linear(32, 2))
+    geo = {}
+    for dt in (torch.float32, torch.float64):
+        m = eng.PendulumMLP(copy.deepcopy(net).to(dt).cuda())
+        c = eng.MPPI(m.dynamics, m.running_cost, 2, torch.tensor(1.0, dtype=dt), num_samples=2048, horizon=10, device="cuda",
+                     u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0))
+        a = c.command(torch.tensor([3.0, 0.5], dtype=dt))
+        assert torch.isfinite(a).all()
+        geo[dt] = (c.launch_info.block_threads, c.launch_info.threads_per_sample)
+    assert geo[torch.float32] == (256, 2)          # the tensor-core kernel: two threads per sample, 128 samples per CTA
+    assert geo[torch.float64] != (256, 2)
+
+
 @pytest.mark.parametrize("variant", ["mppi", "smppi", "kmppi"])
 def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, monkeypatch):
     """PendulumMLP(tensor_cores=True): the three layers run as tcgen05 MMAs (hi/lo-split bf16 operands,
@@ -633,7 +652,7 @@ def test_fused_mlp_tensor_core_route_matches_fp32_kernel(variant, monkeypatch):
     net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
                               torch.nn.Linear(32, 2))
     cpu_model = eng.PendulumMLP(copy.deepcopy(net))
-    ffma = eng.PendulumMLP(copy.deepcopy(net).cuda())
+    ffma = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores=False)
     tcm = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores=True)
     K, T = 4096 + 37, 30
     cls = {"mppi": eng.MPPI, "smppi": eng.SMPPI, "kmppi": eng.KMPPI}[variant]
@@ -684,7 +703,7 @@ def test_fused_mlp_tensor_core_bf16_mode_is_close_and_controls():
     torch.manual_seed(25)
     net = torch.nn.Sequential(torch.nn.Linear(3, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
                               torch.nn.Linear(32, 2))
-    ffma = eng.PendulumMLP(copy.deepcopy(net).cuda())
+    ffma = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores=False)
     tcm = eng.PendulumMLP(copy.deepcopy(net).cuda(), tensor_cores="bf16", fast_tanh=True)
     K, T = 8192, 20
     mk = lambda m: eng.MPPI(m.dynamics, m.running_cost, 2, torch.tensor(1.0), num_samples=K, horizon=T, U_init=torch.zeros(T, 1),
