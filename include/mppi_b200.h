@@ -61,8 +61,9 @@ typedef enum MppiModel {
  *  LINEAR_POINT : [0..3]=B(2x2 row-major) [4..5]=goal [6..9]=Q [10]=has_R [11..14]=R
  *                 [15]=terminal_scale [16]=n_hills(<=3) then per hill h at 17+7h:
  *                 Qh(4) centre(2) height(1)
- *  PENDULUM_MLP : [0]=max_torque [1]=w_thdot [2]=tanh_mode(0 exp-based, 1 MUFU.TANH) [3]=tensor_cores (fp32 only:
- *                 tcgen05/TMEM kernel, fp32 accumulate; 1 = hi/lo-split bf16 operands, 2 = plain bf16); the 1,250 weights go in
+ *  PENDULUM_MLP : [0]=max_torque [1]=w_thdot [2]=tanh_mode(0 exp-based, 1 MUFU.TANH) [3]=tensor_cores (0 = FFMA kernel;
+ *                 tcgen05/TMEM kernel, fp32 accumulate: 1 = hi/lo-split bf16 operands, 2 = plain bf16; 3 = automatic:
+ *                 mode 1 wherever that kernel exists — fp32, one environment — else the FFMA kernel); the 1,250 weights go in
  *                 model_params_ext: W1 (32x3 row-major), b1 (32), W2 (32x32), b2 (32), W3 (2x32), b3 (2)
  */
 
