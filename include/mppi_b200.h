@@ -81,9 +81,9 @@ enum {
     MPPI_FLAG_PDL = 1u << 8,              /* programmatic dependent launch: the kernel may start while the previous
                                              kernel on the stream is finishing; it draws its Philox normals (shared
                                              memory only) and touches global memory only after griddepcontrol.wait */
-    MPPI_FLAG_WIDE_REGS = 1u << 10,       /* launches that need at most one CTA per SM (and do not take the split-cost
-                                             rollout) use the instantiation compiled without the 64-register cap: no spills
-                                             in the last-CTA tail.  Same source, same results.                          */
+    MPPI_FLAG_WIDE_REGS = 1u << 10,       /* retired (accepted and ignored; the bit stays reserved): round 1's opt-in
+                                             instantiation without the 64-register cap.  The split-cost kernels have the
+                                             whole register file anyway, the single-loop kernels of large K need the cap. */
     MPPI_FLAG_SPLIT_COST = 1u << 9        /* small problems (threads_per_sample > 1): the rollout thread runs the bare state
                                              recurrence, the sample's helper threads evaluate the T running costs in
                                              parallel from the stored states, summed in the reference's order (same
@@ -189,7 +189,7 @@ typedef struct MppiLaunchInfo {
     int32_t tma_staging;         /* 1 if the nominal sequence is staged with cp.async.bulk (TMA)         */
     int32_t threads_per_sample;
     int32_t split_cost;          /* 1 if MPPI_FLAG_SPLIT_COST was honoured for these dimensions          */
-    int32_t wide_regs;           /* 1 if MPPI_FLAG_WIDE_REGS was honoured for these dimensions           */
+    int32_t wide_regs;           /* always 0 (MPPI_FLAG_WIDE_REGS is retired)                            */
     int32_t cluster_size;        /* thread-block-cluster size of the launch (1 = no cluster): the CTAs of a cluster
                                     reduce their softmin partials through distributed shared memory        */
     int32_t xchg_records;        /* sharded controllers: records each rank publishes per command (its cluster records

@@ -1485,10 +1485,11 @@ MPPI_UNROLL_N(2)
 // order t = 0..T-1.  Same operations, same rounding, same summation order as the fused loop — the single
 // resident warp just stops carrying the cost's ~45 instructions per step on its critical path.
 //
-// MINB: minimum resident CTAs per SM promised to ptxas.  0 (the default) keeps 512-thread CTAs at 64 registers, which the
-// two-CTA-per-SM geometry of large K needs but which spills the tail's prefetch array; 1 lifts the cap (96 registers, no
-// spills) for launches that place at most one CTA on an SM (MPPI_FLAG_WIDE_REGS; the split-cost variant always has it).
-// the MLP's step keeps 64 activations live: it gets the whole register file (one CTA per SM) instead of the 64-register cap
+// MINB: minimum resident CTAs per SM promised to ptxas.  The split-cost kernels (one CTA per SM by construction) get 1: the
+// whole register file.  The single-loop kernels of the analytic models get 2 = a 64-register cap (20 B of spill): the
+// two-CTA-per-SM geometry of large K needs it, and without the promise the out-of-line tail functions push ptxas to 128
+// registers and one CTA per SM (measured at K = 131072: 42 -> 53 us).  The MLP's step keeps 64 activations live: it gets
+// the whole register file (one CTA per SM) — under the cap it spilled 340 B per thread.
 template <class Model> struct FusedMinBlocks { static constexpr int value = MPPI_FUSED_MIN_BLOCKS; };
 template <> struct FusedMinBlocks<PendulumMLPModel> { static constexpr int value = 1; };
 
