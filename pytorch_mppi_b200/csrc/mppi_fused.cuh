@@ -942,6 +942,7 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank
 __device__ __forceinline__ void st_dsmem_f64(uint32_t addr, double v) {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
@@ -973,6 +974,9 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
     const int R = a.R, LD = sm.LD, i0 = w * 32;
     double* rec = sm.wrec + (size_t)w * (R + 2);
     const real nfl = a.nm.neg_inv_lambda;
+    // the 32 columns this warp reads below were written by its own lanes (one sample per thread: no CTA barrier in
+    // between) — order them
+    __syncwarp();
     const real cmin = warp_min<real>(active ? c_tot : O::inf());
     const real beta_run = (real)rec[0];                 // a value of type `real`, kept in a double slot
     const real beta_new = cmin < beta_run ? cmin : beta_run;
@@ -1000,6 +1004,7 @@ __device__ __forceinline__ void warp_fold(const KArgs<real>& a, Smem<real>& sm, 
         }
         if (jv) rec[2 + j] = rec[2 + j] * resc + (double)acc;
     }
+    __syncwarp();                    // every lane has read the running record
     if (lane == 0) {
         rec[0] = (double)beta_new;
         rec[1] = rec[1] * resc + eta_tile;
@@ -1278,6 +1283,7 @@ __device__ bool warp_tail(const KArgs<real>& a, Smem<real>& sm) {
 
     // (1) warp records -> the cluster leader's shared memory
     if (cs > 1) {
+        if (!PERSISTENT) cluster_wait_acquire();             // phase 0 (arrived at kernel entry): every CTA of the cluster runs
         if (cr != 0 && warp < nrw) {
             const uint32_t dst = mapa_shared(smem_u32(sm.wrec), 0) + (uint32_t)(((cr * nrw + warp) * RW) * 8);
             const double* rec = sm.wrec + (size_t)warp * RW;
@@ -1512,6 +1518,9 @@ __global__ void __launch_bounds__(512, MINB) fused_command_kernel(const __grid_c
     const NoiseModel<real>& nm = a.nm;
     const int T = a.T;
     warp_records_init<real>(a, sm);      // published by the barrier in stage_issue
+    // phase 0 of the cluster barrier: "this CTA has started" — the tail waits for it before the first store into the
+    // leader's shared memory (distributed shared memory may only be touched once its CTA is known to be running)
+    if (cs_ > 1) cluster_arrive_relaxed();
 
     stamp(a.dbg, 0);
     // Programmatic dependent launch: this grid may be resident while the previous kernel on the stream is

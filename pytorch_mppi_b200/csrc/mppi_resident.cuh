@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(640, 1) resident_command_kernel(const __grid_c
     const SmemLayout L = make_layout<real>(VARIANT, a.T, NU, a.S, a.R, BD, BS, fused_layout_nb((int)gridDim.x / cs_, a.xchg_npub),
                                            layout_extra(VARIANT != V_MPPI, NX, cs_, fused_xstage_doubles(false, 1, a.xchg_npub, a.R)));
     Smem<real> sm(smem, L);
+    // distributed shared memory may only be touched once its CTA is known to be running: one cluster barrier at entry
+    if (cs_ > 1) {
+        cluster_arrive_relaxed();
+        cluster_wait_acquire();
+    }
 
     // one tile per CTA
     const int k = blockIdx.x * BS + (tid % BS);
