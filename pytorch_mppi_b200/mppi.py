@@ -295,9 +295,19 @@ class MPPI:
         tn = self.T * self.nu
         self._Ubuf = torch.zeros(_pad16(tn, es), device=self.d, dtype=self.dtype)
         if U_init is None:
-            self.U = self._sample_noise((self.T,))                                          # mppi.py:144-145
+            self.U = self._one_draw_for_all_ranks(self._sample_noise((self.T,)))            # mppi.py:144-145
         else:
             self.U = U_init
+
+    def _one_draw_for_all_ranks(self, t):
+        """A nominal drawn at random (U_init=None, reset()) has to be ONE draw for a sharded controller: every rank adds
+        the same update to its copy of U, so the copies must start equal.  Rank 0's draw is broadcast."""
+        if self._world > 1:
+            import torch.distributed as dist
+            t = t.to(self.d, self.dtype).contiguous()
+            src = dist.get_global_rank(self._pg, 0) if hasattr(dist, "get_global_rank") else 0
+            dist.broadcast(t, src=src, group=self._pg)
+        return t
 
     def _alloc_results(self):
         K, tn = self._K_local, self.T * self.nu
@@ -770,7 +780,7 @@ class MPPI:
 
     def reset(self):
         """mppi.py:286-290"""
-        self.U = self._sample_noise((self.T,))
+        self.U = self._one_draw_for_all_ranks(self._sample_noise((self.T,)))
 
     def change_horizon(self, horizon):
         """mppi.py:277-284"""

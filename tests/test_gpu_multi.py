@@ -100,6 +100,20 @@ def _worker(rank, world, port, out, mode):
             dist.all_gather(lst, many.U.detach().clone().contiguous())
             results[name] = (float((one.U - many.U).abs().max()), worst, all(torch.equal(lst[0], t) for t in lst))
             results[name + f"/records={many.launch_info.xchg_records}/cluster={many.launch_info.cluster_size}"] = (0.0, 0.0, True)
+        # a nominal drawn at random (no U_init; reset()) is one draw for the whole controller, whatever the ranks' torch seeds
+        torch.manual_seed(1000 + rank)
+        rnd = eng.MPPI(pend.dynamics, pend.running_cost, 2, torch.tensor(10.0), num_samples=4096, horizon=12, device=dev,
+                       u_min=torch.tensor(-2.0), u_max=torch.tensor(2.0), rng_seed=5, process_group=dist.group.WORLD)
+        same = True
+        for step in range(2):
+            a = rnd.command([3.0, 0.5])
+            lst = [torch.zeros_like(rnd.U) for _ in range(world)]
+            dist.all_gather(lst, rnd.U.detach().clone().contiguous())
+            acts = [torch.zeros_like(a) for _ in range(world)]
+            dist.all_gather(acts, a.contiguous())
+            same = same and all(torch.equal(lst[0], t) for t in lst) and all(torch.equal(acts[0], t) for t in acts)
+            rnd.reset()
+        results["random_nominal_is_shared"] = (0.0, 0.0, same)
         # a peer that never delivers: the waiting rank gives up after the timeout, returns the un-updated nominal as
         # the action, and its NEXT command raises (the timeout used to be silent)
         if mode == MODES[0]:
