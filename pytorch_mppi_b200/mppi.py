@@ -449,6 +449,8 @@ class MPPI:
         if self._world > 1 and self._exchange == "p2p":
             if getattr(self, "_xchg_status", None) is None:
                 self._xchg_status = torch.zeros(1, dtype=torch.int64).pin_memory()     # written by the kernel on a peer timeout
+                # read on every command: through ctypes (0.07 us), not int(tensor[0]) (2.2 us)
+                self._xchg_status_word = C.c_longlong.from_address(self._xchg_status.data_ptr())
             p.xchg_status_host = self._xchg_status.data_ptr()
         self._variant_pack(p)
         # workspace sized for the worst-case geometry of these dimensions
@@ -466,6 +468,10 @@ class MPPI:
         p.workspace_bytes = self._workspace.numel()
         if self._world > 1:
             self._setup_exchange(p)
+            if self._model is not None:       # the exchange mode depends on the peers: report the geometry of the real plan
+                info = _cabi.MppiLaunchInfo()
+                _cabi.check(self._lib.mppi_fused_query(C.byref(p), C.byref(info)), "mppi_fused_query")
+                self.launch_info = info
         self._dirty = False
         if self._model is not None:
             self._make_plan(p)
@@ -843,10 +849,10 @@ class MPPI:
         """A peer exchange that timed out inside an earlier command left this rank's nominal one update behind its
         peers (the kernel returned the un-updated nominal as the action and flagged a pinned status word): refuse to
         continue silently."""
-        st = getattr(self, "_xchg_status", None)
-        if st is not None and int(st[0]) != 0:
-            code = int(st[0])
-            st[0] = 0
+        st = getattr(self, "_xchg_status_word", None)
+        if st is not None and st.value != 0:
+            code = int(st.value)
+            st.value = 0
             raise _cabi.MppiLibraryError(
                 f"a peer exchange of an earlier command() timed out on rank {self._rank} (status {code}): this rank's nominal "
                 "sequence is now out of step with its peers; reset() / re-synchronise U across ranks before continuing "

@@ -130,6 +130,34 @@ def test_world2_gloo_exchange_matches_single_process():
     assert len(out) == 2 and max(out.values()) < 1e-12
 
 
+def _nominal_worker(rank, world, port, out):
+    import types
+    import torch.distributed as dist
+    from pytorch_mppi_b200.mppi import MPPI
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                              # every process draws differently ...
+    fake = types.SimpleNamespace(_world=world, _pg=dist.group.WORLD, d=torch.device("cpu"), dtype=torch.float64)
+    t = MPPI._one_draw_for_all_ranks(fake, torch.randn(7, 2, dtype=torch.float64))
+    lst = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(lst, t)
+    torch.manual_seed(100)
+    out[rank] = bool(all(torch.equal(lst[0], u) for u in lst)) and bool(torch.equal(t, torch.randn(7, 2, dtype=torch.float64)))
+    dist.destroy_process_group()
+
+
+def test_world2_random_nominal_is_rank0s_draw():
+    """Sharded controllers add the same update to every rank's copy of U: a nominal drawn at random (U_init=None, reset())
+    must therefore be ONE draw — rank 0's, broadcast (the host logic; the controllers themselves: tests/test_gpu_multi.py)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_nominal_worker, args=(2, port, out), nprocs=2, join=True)
+    assert len(out) == 2 and all(out.values())
+
+
 def test_philox_known_answers():
     # Random123 kat_vectors: philox4x32_10
     v = po.philox4x32_10(np.zeros((1, 4), dtype=np.uint32), (0, 0))[0]
