@@ -225,6 +225,31 @@ def test_cuda_model_compiles_with_nvrtc_in_process():
     assert names_k[2] is None and "Li2E" in names_k[0] and "dLi2" in names_k[0].replace("UserModelE", "")
 
 
+def test_tanh4_shared_reciprocal_formula():
+    """csrc/mppi_math.cuh `tanh4_`: four tanh with ONE reciprocal — 1 - 2/a_i, a_i = 1 + e^{2 x_i}, 1/a_0 = r (a_2 a_3) a_1
+    with r = 1/(a_0 a_1 a_2 a_3), inputs clamped at 10 from above.  The same operations in numpy float32 (exact exp2 and
+    reciprocal standing in for MUFU.EX2 / MUFU.RCP, which add ~2 ulp each): the product never overflows and the result
+    stays within 1e-6 of tanh over the whole range, groups mixing saturated and small arguments included."""
+    import numpy as np
+    f = np.float32
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-20, 20, (20000, 4)), rng.normal(0, 1.5, (20000, 4)), rng.normal(0, 1e-3, (2000, 4)),
+                        np.array([[50.0, -50.0, 0.0, 9.99], [10.0, 10.0, 10.0, 10.0], [-87.0, 88.0, 1e-8, -1e-8],
+                                  [np.inf, -np.inf, 3.0, -3.0]])]).astype(f)
+    with np.errstate(over="raise", invalid="raise"):
+        t = np.exp2((np.minimum(x, f(10.0)) * f(2.8853900817779268)).astype(f)).astype(f)
+        a = (f(1.0) + t).astype(f)
+        p01, p23 = (a[:, 0] * a[:, 1]).astype(f), (a[:, 2] * a[:, 3]).astype(f)
+        r = (f(1.0) / (p01 * p23).astype(f)).astype(f)
+        r = (r * f(-2.0)).astype(f)
+        r01, r23 = (r * p23).astype(f), (r * p01).astype(f)
+        y = np.stack([r01 * a[:, 1] + f(1.0), r01 * a[:, 0] + f(1.0), r23 * a[:, 3] + f(1.0), r23 * a[:, 2] + f(1.0)], 1).astype(f)
+    assert np.isfinite(y).all() and float((p01 * p23).max()) < 1e35            # e^80 at most: no overflow
+    want = np.tanh(x.astype(np.float64))
+    assert float(np.abs(y - want).max()) < 1e-6
+    assert (np.abs(y) <= 1.0 + 2.4e-7).all()            # the shared reciprocal can land one ulp outside [-1, 1]; nothing relies on the bound
+
+
 def test_bf16_split_contraction_precision_model():
     """The arithmetic contract of the tensor-core MLP route (csrc/mppi_mlp_tc.cuh), restated with torch's
     round-to-nearest bf16 casts:  v = hi + lo (both bf16), layer = a_hi*w_hi + a_lo*w_hi + a_hi*w_lo + b_hi + b_lo
