@@ -107,9 +107,34 @@ def _compile_all(units, verbose=False):
     return [objs[n] for n in sorted(objs)]
 
 
+class _BuildLock:
+    """One builder at a time per tree: the ranks of a multi-GPU job that all find the library stale must not run nvcc
+    into the same object files.  (flock on a file next to the library; released when the process ends, whatever happens.)"""
+
+    def __enter__(self):
+        import fcntl
+        os.makedirs(OBJ, exist_ok=True)
+        self._f = open(os.path.join(OBJ, ".build.lock"), "w")
+        fcntl.flock(self._f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self._f, fcntl.LOCK_UN)
+        self._f.close()
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
+    with _BuildLock():
+        if not force and not needs_build():        # another process built it while this one waited
+            return OUT
+        return _build_locked(force, verbose)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     h = source_hash()          # of the sources as compiled (taken before nvcc runs)
     if force:
         for name in UNITS:
@@ -118,7 +143,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             except OSError:
                 pass
     objs = _compile_all(UNITS, verbose)
-    _link(objs, OUT)
+    tmp = OUT + f".{os.getpid()}.tmp"
+    _link(objs, tmp)
+    os.replace(tmp, OUT)
     with open(STAMP, "w") as f:
         f.write(h)
     # everything cached for user models was built from the previous sources: drop it (it is keyed by the source hash and
@@ -145,6 +172,13 @@ def build_user_model(header_text: str, verbose: bool = False) -> str:
     out = os.path.join(udir, f"libmppi_b200_user_{tag}.so")
     if os.path.exists(out):
         return out
+    with _BuildLock():
+        if os.path.exists(out):
+            return out
+        return _build_user_model_locked(header_text, tag, udir, hdr, out, verbose)
+
+
+def _build_user_model_locked(header_text, tag, udir, hdr, out, verbose):
     with open(hdr, "w") as f:
         f.write(header_text)
     base = _compile_all({"cabi": UNITS["cabi"]}, verbose)          # normally cached
@@ -154,7 +188,9 @@ def build_user_model(header_text: str, verbose: bool = False) -> str:
     with concurrent.futures.ThreadPoolExecutor(max_workers=2) as ex:
         futs = [ex.submit(_compile_unit, name, *spec, verbose, header_text, udir) for name, spec in units.items()]
         uobjs = [f.result()[0] for f in futs]
-    _link(base + uobjs, out)
+    tmp = out + f".{os.getpid()}.tmp"
+    _link(base + uobjs, tmp)
+    os.replace(tmp, out)
     return out
 
 

@@ -128,11 +128,15 @@ def compile_user_model(header_text: str, real: str, variant: int):
         data = cubin.raw
     finally:
         lib.nvrtcDestroyProgram(C.byref(prog))
+    # several processes (one per GPU) may compile the same model at the same time: both files appear atomically, the
+    # names first — a reader that finds the cubin finds complete names
     os.makedirs(CACHE, exist_ok=True)
+    tmp = names_path + f".{os.getpid()}.tmp"
+    with open(tmp, "w") as g:
+        json.dump(lowered, g)
+    os.replace(tmp, names_path)
     tmp = cubin_path + f".{os.getpid()}.tmp"
     with open(tmp, "wb") as f:
         f.write(data)
     os.replace(tmp, cubin_path)
-    with open(names_path, "w") as g:
-        json.dump(lowered, g)
     return data, lowered
