@@ -38,3 +38,27 @@ def test_engine_arm_refuses_to_run_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert not any(ln.startswith('{"metric"') for ln in r.stdout.splitlines())
+
+
+def test_bench_helpers_statistics_bytes_and_workloads():
+    """The pure parts of bench.py: trimmed statistics (tests/benchmark_mppi.py:84-113), SURVEY §8(d)'s algorithmic bytes,
+    the workload table against BASELINE.json, and the committed traffic file the roofline object reads."""
+    sys.path.insert(0, ROOT)
+    import bench
+    st = bench.trimmed_stats([5.0] + [1.0] * 18 + [0.1])            # one outlier each side: both trimmed away
+    assert st["n"] == 20 and st["trimmed_mean"] == 1.0 and st["median"] == 1.0 and st["min"] == 0.1 and st["max"] == 5.0
+    assert bench.trimmed_stats([2.0, 4.0])["trimmed_mean"] == 3.0
+    c2 = bench.WORKLOADS["pendulum_c2"]
+    b_min, b_full = bench.algorithmic_bytes(c2, c2["K"])
+    assert (b_min, b_full) == (65784, 2097400)                      # SURVEY §8(d): 4(nx + 2 T nu + K); + 4K + 4 K T nu
+    c3 = bench.WORKLOADS["nav2d_c3"]
+    assert bench.algorithmic_bytes(c3, c3["K"])[0] == 4 * (2 + 2 * (40 * 2 + 5 * 2) + 8192)    # KMPPI: control points too
+    base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
+    text = json.dumps(base)
+    for name, wl in bench.WORKLOADS.items():
+        assert wl["K"] > 0 and wl["T"] > 0 and wl["variant"] in ("mppi", "smppi", "kmppi"), name
+    assert "16384" in text and c2["K"] == 16384 and c2["T"] == 30    # the configuration the metric is quoted on
+    for name in bench.WORKLOADS:
+        t = bench.load_traffic(name)
+        assert t is None or (isinstance(t, int) and 10_000 < t < 10_000_000), (name, t)
+    assert bench.load_traffic("pendulum_c2") is not None             # the default workload has a committed capture
